@@ -1,0 +1,57 @@
+"""Synthetic workloads of the shapes the reference's tests and benches use.
+
+Distribution parity only: the reference draws from rand 0.8 `StdRng` (ChaCha12), which is not
+vendored under the reference tree, so byte parity of the datasets is unpinned.
+Generators follow `tests/recall_test.rs:38-67,112-131` and `benches/comparison.rs:80-121`
+(corpus and queries share ONE basis).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _normalise(v: np.ndarray) -> np.ndarray:
+    n = np.sqrt((v.astype(np.float32) ** 2).sum(axis=1, dtype=np.float32, keepdims=True))
+    n[n == 0] = 1.0
+    return (v / n).astype(np.float32)
+
+
+def unit_vectors(rng: np.random.Generator, n: int, dim: int) -> np.ndarray:
+    """`unit_vector`: dim draws of U(-1,1), L2-normalised (tests/recall_test.rs:38-47)."""
+    return _normalise(rng.uniform(-1.0, 1.0, size=(n, dim)).astype(np.float32))
+
+
+def uniform_dataset(n: int, nq: int, dim: int, seed: int):
+    """`uniform_dataset` (tests/recall_test.rs:112-117)."""
+    rng = np.random.default_rng(seed)
+    return unit_vectors(rng, n, dim), unit_vectors(rng, nq, dim)
+
+
+def embedding_rows(rng: np.random.Generator, basis: np.ndarray, n: int, chunk: int = 65536) -> np.ndarray:
+    """`embedded_vector`: 16 U(-1,1) coefficients over a fixed basis, normalised (:52-67)."""
+    out = np.empty((n, basis.shape[1]), dtype=np.float32)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        coeff = rng.uniform(-1.0, 1.0, size=(e - s, basis.shape[0])).astype(np.float32)
+        out[s:e] = _normalise(coeff @ basis)
+    return out
+
+
+def embedding_dataset(n: int, nq: int, seed: int, dim: int = 768, intrinsic: int = 16):
+    """`embedding_dataset` (tests/recall_test.rs:119-131): basis, then rows, then queries, one stream."""
+    rng = np.random.default_rng(seed)
+    basis = unit_vectors(rng, intrinsic, dim)
+    return embedding_rows(rng, basis, n), embedding_rows(rng, basis, nq)
+
+
+def temporal_attrs(n: int, seed: int, now_secs: int, span_days: float = 30.0):
+    """Timestamps uniform over the last `span_days`; decay_rate 0 (-> base) for half the rows, else one
+    of the `examples/sample_vectors.json` rates."""
+    rng = np.random.default_rng(seed ^ 0x7E11)
+    age = rng.uniform(0.0, span_days * 86400.0, size=n)
+    ts = now_secs - age
+    ts_secs = np.floor(ts).astype(np.uint64)
+    ts_nanos = ((ts - np.floor(ts)) * 1e9).astype(np.uint32)
+    rates = np.array([0.0, 0.0, 0.0, 0.0, 0.05, 0.1, 0.15, 0.2, 0.25], dtype=np.float32)
+    decay = rates[rng.integers(0, len(rates), size=n)]
+    return ts_secs, ts_nanos, decay
