@@ -1,0 +1,852 @@
+// api.cu — the C ABI (include/chronomind_b200.h): index lifecycle on the host, flattening to the device
+// layout, and the search entry points that enqueue the kernels. No CPU search path exists here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <thread>
+#include <unordered_map>
+
+#include "cm_internal.h"
+#include "kernels.h"
+
+namespace cm {
+
+// ---- errors / counters -----------------------------------------------------------------------------------
+static thread_local std::string tl_error;
+static thread_local cm_counters tl_counters;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string& msg) { tl_error = msg; }
+void count_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  tl_counters.kernel_launches++;
+}
+
+static cm_status fail(cm_status st, const std::string& msg) {
+  set_error(msg);
+  return st;
+}
+static cm_status cuda_fail(cudaError_t e, const char* what) {
+  return fail(CM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CM_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+// ---- device buffers ----------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Scratch for one in-flight search call. Calls on different host threads take different workspaces.
+struct Workspace {
+  DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable;
+  cudaStream_t stream = nullptr;  // host-buffer variants
+  unsigned hnsw_grid = 0;
+  void release() {
+    for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable}) b->release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+struct WorkspacePool {
+  std::mutex mu;
+  std::vector<Workspace*> free_list;
+  std::vector<Workspace*> all;
+  Workspace* acquire() {
+    std::lock_guard<std::mutex> g(mu);
+    if (!free_list.empty()) {
+      Workspace* w = free_list.back();
+      free_list.pop_back();
+      return w;
+    }
+    Workspace* w = new Workspace();
+    all.push_back(w);
+    return w;
+  }
+  void give_back(Workspace* w) {
+    std::lock_guard<std::mutex> g(mu);
+    free_list.push_back(w);
+  }
+  ~WorkspacePool() {
+    for (Workspace* w : all) {
+      w->release();
+      delete w;
+    }
+  }
+};
+
+struct WorkspaceLease {
+  WorkspacePool* pool;
+  Workspace* ws;
+  explicit WorkspaceLease(const cm_index* idx) : pool((WorkspacePool*)idx->workspace_pool), ws(pool->acquire()) {}
+  ~WorkspaceLease() { pool->give_back(ws); }
+};
+
+constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited table: 128 Ki entries
+constexpr size_t kDistWorkspaceBytes = 1ull << 30;  // fp32 scan: distance block [QB][n] floats
+
+static void free_device(DeviceIndex& d) {
+  if (d.device < 0) return;
+  cudaSetDevice(d.device);
+  for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.ts_secs, (void*)d.ts_nanos, (void*)d.decay,
+                  (void*)d.nbr0, (void*)d.deg0, (void*)d.upper_base, (void*)d.nbr_up, (void*)d.deg_up})
+    if (p) cudaFree(p);
+  d = DeviceIndex();
+}
+
+template <class F>
+static void parallel_rows(uint64_t n, F f) {
+  unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < 4096 || hw == 1) {
+    for (uint64_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> ts;
+  uint64_t chunk = (n + hw - 1) / hw;
+  for (uint64_t s = 0; s < n; s += chunk) {
+    uint64_t e = std::min(n, s + chunk);
+    ts.emplace_back([=] {
+      for (uint64_t i = s; i < e; ++i) f(i);
+    });
+  }
+  for (auto& t : ts) t.join();
+}
+
+static uint32_t hash_bits_for(uint32_t ef) {
+  uint32_t want = std::max(2048u, 32u * ef);
+  uint32_t bits = 11;
+  while ((1u << bits) < want) ++bits;
+  return std::min(bits, 15u);
+}
+
+// ---- search plumbing (device pointers, async on `s`) --------------------------------------------------------
+struct PreparedQueries {
+  const float* qn = nullptr;
+  uint32_t ld = 0;
+  bool degenerate = false;
+};
+
+static cm_status prepare_queries(const cm_index* idx, Workspace* ws, const float* q_dev, uint32_t nq, uint32_t qdim,
+                                 uint32_t* bad_row, cudaStream_t s, PreparedQueries* out) {
+  const DeviceIndex& d = idx->dev;
+  out->degenerate = qdim != d.dim;
+  out->ld = d.dim_pad;
+  if (out->degenerate) {  // distances are all 2.0; the query values are never read
+    out->qn = nullptr;
+    return CM_OK;
+  }
+  CM_CUDA(ws->qn.ensure((size_t)std::max(nq, 1u) * d.dim_pad * sizeof(float)));
+  CM_CUDA(launch_preprocess_rows(q_dev, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
+  out->qn = ws->qn.as<float>();
+  return CM_OK;
+}
+
+// Exact top-`k` by (distance, handle) into ids/dist [nq][k] (device).
+static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
+                            uint32_t* ids, float* dist, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  if (nq == 0) return CM_OK;
+  if (d.n == 0) {
+    CM_CUDA(cudaMemsetAsync(ids, 0xFF, (size_t)nq * k * 4, s));
+    CM_CUDA(launch_fill(dist, (uint64_t)nq * k, INFINITY, s));
+    return CM_OK;
+  }
+  // fp32 CUDA-core scan in query blocks: D[QB][n] then select.
+  uint64_t ldD = (d.n + 3) & ~3ull;
+  uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
+  qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
+  CM_CUDA(ws->D.ensure(qb * ldD * sizeof(float)));
+  float* D = ws->D.as<float>();
+  for (uint32_t q0 = 0; q0 < nq; q0 += (uint32_t)qb) {
+    uint32_t nb = std::min<uint32_t>((uint32_t)qb, nq - q0);
+    if (pq.degenerate)
+      CM_CUDA(launch_fill(D, (uint64_t)nb * ldD, 2.0f, s));
+    else
+      CM_CUDA(launch_exact_dist(pq.qn + (size_t)q0 * pq.ld, nb, pq.ld, d.x32, d.n, d.dim, d.dim_pad, D, ldD, s));
+    CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, d.deleted, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, k, s));
+  }
+  tl_counters.dist_evals += (uint64_t)nq * d.n;
+  return CM_OK;
+}
+
+// HNSW candidate pool [nq][ef] (tombstones filtered, ascending) into ws->pool_*.
+static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t ef,
+                           cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  if (!d.has_graph) return fail(CM_ERR_STATE, "HNSW search needs cm_index_build_graph / cm_index_load_graph before upload");
+  CM_CUDA(ws->pool_ids.ensure((size_t)std::max(nq, 1u) * ef * 4));
+  CM_CUDA(ws->pool_dist.ensure((size_t)std::max(nq, 1u) * ef * 4));
+  if (nq == 0) return CM_OK;
+  if (!d.has_entry) {  // empty index: search returns [] (:474-476)
+    CM_CUDA(cudaMemsetAsync(ws->pool_ids.p, 0xFF, (size_t)nq * ef * 4, s));
+    CM_CUDA(launch_fill(ws->pool_dist.as<float>(), (uint64_t)nq * ef, INFINITY, s));
+    return CM_OK;
+  }
+  uint32_t hb = hash_bits_for(ef);
+  unsigned grid = 0;
+  cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid);
+  if (ge != cudaSuccess) return fail(CM_ERR_INVALID_ARGUMENT, "ef / dim too large for the HNSW kernel's shared memory");
+  CM_CUDA(ws->small.ensure(256));
+  CM_CUDA(ws->gtable.ensure(((size_t)grid << kGHashBits) * 4));
+  CM_CUDA(cudaMemsetAsync(ws->small.p, 0, 160, s));  // counters + work counter (bad_row at 192 is the caller's)
+  HnswLaunch l;
+  l.q = pq.qn;
+  l.nq = nq;
+  l.ldq = pq.ld;
+  l.ef = ef;
+  l.degenerate = pq.degenerate ? 1 : 0;
+  l.pool_ids = ws->pool_ids.as<uint32_t>();
+  l.pool_dist = ws->pool_dist.as<float>();
+  l.counters = ws->small.as<unsigned long long>();          // 8 x u64 at offset 0
+  l.work_counter = ws->small.as<uint32_t>() + 32;           // offset 128
+  l.hash_bits = hb;
+  l.gtable = ws->gtable.as<uint32_t>();
+  l.ghash_bits = kGHashBits;
+  l.grid = grid;
+  CM_CUDA(launch_hnsw_search(d, l, s));
+  return CM_OK;
+}
+
+static cm_status check_search_args(const cm_index* idx, const void* q, uint32_t nq, uint32_t k, const void* ids,
+                                   const void* out) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  if (!idx->uploaded) return fail(CM_ERR_CUDA, "index is not resident on a CUDA device (call cm_index_upload); there is no CPU path");
+  if (nq && (!q || !ids || !out)) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  if (k == 0 || k > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "k/ef must be in [1, CM_MAX_K]");
+  return CM_OK;
+}
+
+static cm_status set_device(const cm_index* idx) {
+  CM_CUDA(cudaSetDevice(idx->dev.device));
+  return CM_OK;
+}
+
+static cm_status strided_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                              cudaStream_t s) {
+  if (rows == 0 || width == 0) return CM_OK;
+  CM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, s));
+  return CM_OK;
+}
+
+static cm_status search_exact_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim,
+                                       uint32_t k, uint32_t* ids, float* dist, cudaStream_t s) {
+  PreparedQueries pq;
+  cm_status st = prepare_queries(idx, ws, q, nq, qdim, nullptr, s, &pq);
+  if (st != CM_OK) return st;
+  return exact_topk(idx, ws, pq, nq, k, ids, dist, s);
+}
+
+static cm_status search_hnsw_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim,
+                                      uint32_t ef, uint32_t k, uint32_t* ids, float* dist, cudaStream_t s) {
+  PreparedQueries pq;
+  cm_status st = prepare_queries(idx, ws, q, nq, qdim, nullptr, s, &pq);
+  if (st != CM_OK) return st;
+  uint32_t pool = std::max(ef, k);  // PyO3 Index.query: ef = ef_search.max(n)
+  st = hnsw_pool(idx, ws, pq, nq, pool, s);
+  if (st != CM_OK) return st;
+  st = strided_copy(ids, (size_t)k * 4, ws->pool_ids.p, (size_t)pool * 4, (size_t)k * 4, nq, s);
+  if (st != CM_OK) return st;
+  return strided_copy(dist, (size_t)k * 4, ws->pool_dist.p, (size_t)pool * 4, (size_t)k * 4, nq, s);
+}
+
+static cm_status search_temporal_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq,
+                                          uint32_t qdim, uint32_t k, uint32_t ef_search, float w, float base,
+                                          uint64_t now_secs, uint32_t now_nanos, int exact, uint32_t* bad_row,
+                                          uint32_t* ids, float* score, float* dist, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  uint64_t ef64 = std::max<uint64_t>(ef_search, (uint64_t)k * 3);  // OVERSAMPLE (src/store.rs:40,323)
+  if (ef64 > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "max(ef_search, 3k) exceeds CM_MAX_K");
+  uint32_t ef = (uint32_t)ef64;
+  PreparedQueries pq;
+  cm_status st = prepare_queries(idx, ws, q, nq, qdim, bad_row, s, &pq);
+  if (st != CM_OK) return st;
+  if (exact) {
+    CM_CUDA(ws->pool_ids.ensure((size_t)std::max(nq, 1u) * ef * 4));
+    CM_CUDA(ws->pool_dist.ensure((size_t)std::max(nq, 1u) * ef * 4));
+    st = exact_topk(idx, ws, pq, nq, ef, ws->pool_ids.as<uint32_t>(), ws->pool_dist.as<float>(), s);
+  } else {
+    st = hnsw_pool(idx, ws, pq, nq, ef, s);
+  }
+  if (st != CM_OK) return st;
+  CM_CUDA(launch_rerank(ws->pool_ids.as<uint32_t>(), ws->pool_dist.as<float>(), nq, ef, k, d.ts_secs, d.ts_nanos,
+                        d.decay, w, base, now_secs, now_nanos, ids, score, dist, s));
+  return CM_OK;
+}
+
+static void fetch_hnsw_counters(Workspace* ws) {
+  if (!ws->small.p) return;
+  unsigned long long c[8];
+  if (cudaMemcpy(c, ws->small.p, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  tl_counters.dist_evals += c[0];
+  tl_counters.expansions += c[1];
+  tl_counters.list_entries += c[2];
+  tl_counters.fallback_queries += c[3];
+}
+
+}  // namespace cm
+
+using namespace cm;
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+const char* cm_last_error(void) { return tl_error.c_str(); }
+const char* cm_version(void) { return "chronomind_b200 0.1.0 (sm_100a)"; }
+const char* cm_metric_name(void) { return "cosine"; }  // src/metric.rs:201-203
+uint64_t cm_launch_count(void) { return g_launches.load(); }
+cm_status cm_last_counters(cm_counters* out) {
+  if (!out) return fail(CM_ERR_INVALID_ARGUMENT, "null out");
+  *out = tl_counters;
+  return CM_OK;
+}
+
+void cm_config_default(cm_config* c) {  // src/config.rs:73-85, 27-35
+  if (!c) return;
+  c->dimensions = 768;
+  c->max_memories = 100000;
+  c->base_decay_rate = 0.1f;
+  c->temporal_weight = 0.3f;
+  c->similarity_threshold = 0.95f;
+  c->max_relationships = 50;
+  c->index.max_connections = 16;
+  c->index.ef_construction = 200;
+  c->index.ef_search = 50;
+}
+
+static cm_index* new_index(const cm_config& cfg, uint64_t n, uint32_t dim) {
+  cm_index* idx = new cm_index();
+  idx->config = cfg;
+  idx->n = n;
+  idx->dim = dim;
+  idx->deleted.assign(n, 0);
+  idx->ts_secs.assign(n, 0);
+  idx->ts_nanos.assign(n, 0);
+  idx->decay.assign(n, 0.0f);
+  idx->live = n;
+  idx->workspace_pool = new WorkspacePool();
+  return idx;
+}
+
+cm_status cm_index_from_matrix(const float* x, uint64_t n, uint32_t dim, const cm_config* cfg, cm_index** out) {
+  if (!out) return fail(CM_ERR_INVALID_ARGUMENT, "null out");
+  *out = nullptr;
+  if (n && !x) return fail(CM_ERR_INVALID_ARGUMENT, "null matrix");
+  cm_config c;
+  if (cfg)
+    c = *cfg;
+  else
+    cm_config_default(&c);
+  c.dimensions = dim;
+  cm_status st = validate_config(c);
+  if (st != CM_OK) return st;
+  if (n > kArenaCapacity)
+    return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
+  cm_index* idx = new_index(c, n, dim);
+  idx->x.resize(n * (uint64_t)dim);
+  float* dst = idx->x.data();
+  parallel_rows(n, [=](uint64_t i) { preprocess_row(x + i * dim, dim, dst + i * dim); });
+  *out = idx;
+  return CM_OK;
+}
+
+cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
+  if (!out || !path) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  SnapshotData snap;
+  cm_status st = read_snapshot(path, &snap);
+  if (st != CM_OK) return st;
+  uint64_t n = snap.memories.size();
+  uint32_t dim = (uint32_t)snap.config.dimensions;
+  if (n > kArenaCapacity)
+    return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
+  cm_index* idx = new_index(snap.config, n, dim);
+  idx->x.resize(n * (uint64_t)dim);
+  const float* src = snap.vectors.data();
+  float* dst = idx->x.data();
+  parallel_rows(n, [=](uint64_t i) { preprocess_row(src + i * dim, dim, dst + i * dim); });
+  idx->ext_ids.resize(n);
+  // Replay ChronoMind::insert's handle bookkeeping (src/store.rs:226-264): a repeated id publishes the new
+  // handle and tombstones the one it replaces; capacity counts distinct ids.
+  std::unordered_map<std::string, uint32_t> by_id;
+  by_id.reserve(n * 2);
+  for (uint64_t i = 0; i < n; ++i) {
+    const SnapshotMemory& m = snap.memories[i];
+    idx->ext_ids[i] = m.id;
+    idx->ts_secs[i] = m.ts_secs;
+    idx->ts_nanos[i] = m.ts_nanos;
+    idx->decay[i] = m.decay_rate;
+    auto it = by_id.find(m.id);
+    if (it != by_id.end()) {
+      idx->deleted[it->second] = 1;
+      idx->live--;
+      it->second = (uint32_t)i;
+    } else {
+      if (by_id.size() >= snap.config.max_memories) {
+        cm_index_free(idx);
+        return fail(CM_ERR_CAPACITY_EXCEEDED, "store is at capacity (" + std::to_string(snap.config.max_memories) + " memories)");
+      }
+      by_id.emplace(m.id, (uint32_t)i);
+    }
+  }
+  *out = idx;
+  return CM_OK;
+}
+
+cm_status cm_index_set_attrs(cm_index* idx, const uint64_t* ts_secs, const uint32_t* ts_nanos, const float* decay_rate,
+                             const uint8_t* deleted) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  uint64_t n = idx->n;
+  if (decay_rate)
+    for (uint64_t i = 0; i < n; ++i)
+      if (!std::isfinite(decay_rate[i]) || decay_rate[i] < 0.0f)  // Memory::validate (src/types.rs:112-118)
+        return fail(CM_ERR_INVALID_VECTOR, "invalid vector data: vector has an invalid decay rate");
+  if (ts_nanos)
+    for (uint64_t i = 0; i < n; ++i)
+      if (ts_nanos[i] >= 1000000000u) return fail(CM_ERR_INVALID_ARGUMENT, "timestamp nanoseconds out of range");
+  if (ts_secs) std::copy(ts_secs, ts_secs + n, idx->ts_secs.begin());
+  if (ts_nanos) std::copy(ts_nanos, ts_nanos + n, idx->ts_nanos.begin());
+  if (decay_rate) std::copy(decay_rate, decay_rate + n, idx->decay.begin());
+  if (deleted) {
+    uint64_t live = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      idx->deleted[i] = deleted[i] ? 1 : 0;
+      live += deleted[i] ? 0 : 1;
+    }
+    idx->live = live;
+  }
+  return CM_OK;
+}
+
+cm_status cm_index_remove(cm_index* idx, uint32_t handle, int* removed) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  int r = 0;
+  if (handle < idx->n && !idx->deleted[handle]) {
+    idx->deleted[handle] = 1;
+    idx->live--;
+    r = 1;
+  }
+  if (removed) *removed = r;
+  return CM_OK;
+}
+
+cm_status cm_index_build_graph(cm_index* idx, uint64_t layer_seed, int threads) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  build_graph(idx->x.data(), idx->n, idx->dim, idx->config.index, layer_seed, threads, &idx->graph);
+  return CM_OK;
+}
+
+cm_status cm_index_set_shard(cm_index* idx, uint32_t shard_rank, uint32_t shard_count) {
+  if (!idx || shard_count == 0 || shard_rank >= shard_count) return fail(CM_ERR_INVALID_ARGUMENT, "bad shard");
+  idx->shard_rank = shard_rank;
+  idx->shard_count = shard_count;
+  return CM_OK;
+}
+
+cm_status cm_index_upload(cm_index* idx, int device) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(CM_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(CM_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  free_device(idx->dev);
+  idx->uploaded = false;
+  CM_CUDA(cudaSetDevice(device));
+  DeviceIndex& d = idx->dev;
+  d.device = device;
+  d.n = idx->n;
+  d.dim = idx->dim;
+  d.dim_pad = (idx->dim + 7) & ~7u;
+  d.live = idx->live;
+  cudaDeviceProp prop;
+  CM_CUDA(cudaGetDeviceProperties(&prop, device));
+  d.sm_count = prop.multiProcessorCount;
+  uint64_t n = idx->n;
+  size_t rows = std::max<uint64_t>(n, 1);
+  CM_CUDA(cudaMalloc(&d.x32, rows * d.dim_pad * sizeof(float)));
+  if (n) {
+    if (d.dim_pad != d.dim) CM_CUDA(cudaMemset(d.x32, 0, rows * d.dim_pad * sizeof(float)));
+    CM_CUDA(cudaMemcpy2D(d.x32, (size_t)d.dim_pad * 4, idx->x.data(), (size_t)d.dim * 4, (size_t)d.dim * 4, n,
+                         cudaMemcpyHostToDevice));
+  }
+  CM_CUDA(cudaMalloc(&d.deleted, rows));
+  CM_CUDA(cudaMalloc(&d.ts_secs, rows * 8));
+  CM_CUDA(cudaMalloc(&d.ts_nanos, rows * 4));
+  CM_CUDA(cudaMalloc(&d.decay, rows * 4));
+  if (n) {
+    CM_CUDA(cudaMemcpy(d.deleted, idx->deleted.data(), n, cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMemcpy(d.ts_secs, idx->ts_secs.data(), n * 8, cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMemcpy(d.ts_nanos, idx->ts_nanos.data(), n * 4, cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMemcpy(d.decay, idx->decay.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  const Graph& g = idx->graph;
+  d.has_graph = g.built;
+  if (g.built) {
+    d.cap0 = g.cap0;
+    d.capU = g.capU;
+    d.has_entry = g.entry != kEmptyEntry;
+    d.entry_id = (uint32_t)g.entry;
+    d.entry_top = d.has_entry ? (uint32_t)(g.entry >> 32) : 0;
+    auto up = [&](uint32_t** dst, const std::vector<uint32_t>& v) -> cudaError_t {
+      cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * 4);
+      if (e != cudaSuccess) return e;
+      if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+      return e;
+    };
+    CM_CUDA(up(&d.nbr0, g.nbr0));
+    CM_CUDA(up(&d.deg0, g.deg0));
+    CM_CUDA(up(&d.upper_base, g.upper_base));
+    CM_CUDA(up(&d.nbr_up, g.nbr_up));
+    CM_CUDA(up(&d.deg_up, g.deg_up));
+  }
+  CM_CUDA(cudaDeviceSynchronize());
+  idx->uploaded = true;
+  return CM_OK;
+}
+
+void cm_index_free(cm_index* idx) {
+  if (!idx) return;
+  if (idx->dev.device >= 0) cudaSetDevice(idx->dev.device);
+  delete (WorkspacePool*)idx->workspace_pool;
+  free_device(idx->dev);
+  delete idx;
+}
+
+uint64_t cm_index_slots(const cm_index* idx) { return idx ? idx->n : 0; }
+uint64_t cm_index_len(const cm_index* idx) { return idx ? idx->live : 0; }
+uint32_t cm_index_dim(const cm_index* idx) { return idx ? idx->dim : 0; }
+cm_status cm_index_get_config(const cm_index* idx, cm_config* out) {
+  if (!idx || !out) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = idx->config;
+  return CM_OK;
+}
+const char* cm_index_external_id(const cm_index* idx, uint32_t handle) {
+  if (!idx || handle >= idx->ext_ids.size()) return "";
+  return idx->ext_ids[handle].c_str();
+}
+int cm_index_check_invariants(const cm_index* idx) {
+  if (!idx || !idx->graph.built) return -1;
+  return check_graph_invariants(idx->graph);
+}
+uint64_t cm_index_entry(const cm_index* idx) { return idx && idx->graph.built ? idx->graph.entry : kEmptyEntry; }
+uint32_t cm_index_top_layer(const cm_index* idx, uint32_t handle) {
+  if (!idx || !idx->graph.built || handle >= idx->n) return 0;
+  return idx->graph.top_layer[handle];
+}
+uint32_t cm_index_neighbors(const cm_index* idx, uint32_t handle, uint32_t layer, uint32_t* out, uint32_t cap) {
+  if (!idx || !idx->graph.built || handle >= idx->n || layer > idx->graph.top_layer[handle]) return 0;
+  uint32_t deg;
+  const uint32_t* l = idx->graph.list(handle, layer, &deg);
+  for (uint32_t i = 0; i < deg && i < cap; ++i) out[i] = l[i];
+  return deg;
+}
+cm_status cm_index_vector(const cm_index* idx, uint32_t handle, float* out) {
+  if (!idx || !out || handle >= idx->n) return fail(CM_ERR_INVALID_ARGUMENT, "bad handle");
+  std::memcpy(out, idx->x.data() + (uint64_t)handle * idx->dim, (size_t)idx->dim * 4);
+  return CM_OK;
+}
+
+// ---- graph sidecar ------------------------------------------------------------------------------------------
+// "CMGRAPH1" | n u64 | cap0 u32 | capU u32 | entry u64 | slots u64 | top_layer[n] u8 | deg0[n] | nbr0[n*cap0] |
+// upper_base[n] | deg_up[slots] | nbr_up[slots*capU]   (all little endian)
+cm_status cm_index_save_graph(const cm_index* idx, const char* path) {
+  if (!idx || !path) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  const Graph& g = idx->graph;
+  if (!g.built) return fail(CM_ERR_STATE, "no graph to save");
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(CM_ERR_IO, std::string("io error: cannot open ") + path);
+  uint64_t slots = g.deg_up.size();
+  bool ok = std::fwrite("CMGRAPH1", 1, 8, f) == 8;
+  auto w = [&](const void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes); };
+  w(&g.n, 8);
+  w(&g.cap0, 4);
+  w(&g.capU, 4);
+  w(&g.entry, 8);
+  w(&slots, 8);
+  w(g.top_layer.data(), g.top_layer.size());
+  w(g.deg0.data(), g.deg0.size() * 4);
+  w(g.nbr0.data(), g.nbr0.size() * 4);
+  w(g.upper_base.data(), g.upper_base.size() * 4);
+  w(g.deg_up.data(), g.deg_up.size() * 4);
+  w(g.nbr_up.data(), g.nbr_up.size() * 4);
+  ok = (std::fclose(f) == 0) && ok;
+  return ok ? CM_OK : fail(CM_ERR_IO, "io error: short write");
+}
+
+cm_status cm_index_load_graph(cm_index* idx, const char* path) {
+  if (!idx || !path) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(CM_ERR_IO, std::string("io error: cannot open ") + path);
+  Graph g;
+  char magic[8];
+  uint64_t slots = 0;
+  bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "CMGRAPH1", 8) == 0;
+  auto r = [&](void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes); };
+  r(&g.n, 8);
+  r(&g.cap0, 4);
+  r(&g.capU, 4);
+  r(&g.entry, 8);
+  r(&slots, 8);
+  if (!ok || g.n != idx->n || g.cap0 != idx->config.index.max_connections * 2 ||
+      g.capU != idx->config.index.max_connections || slots > g.n * 32) {
+    std::fclose(f);
+    return fail(CM_ERR_INVALID_SNAPSHOT, "invalid snapshot: graph sidecar does not match this index");
+  }
+  g.top_layer.resize(g.n);
+  g.deg0.resize(g.n);
+  g.nbr0.resize(g.n * g.cap0);
+  g.upper_base.resize(g.n);
+  g.deg_up.resize(slots);
+  g.nbr_up.resize(slots * g.capU);
+  r(g.top_layer.data(), g.top_layer.size());
+  r(g.deg0.data(), g.deg0.size() * 4);
+  r(g.nbr0.data(), g.nbr0.size() * 4);
+  r(g.upper_base.data(), g.upper_base.size() * 4);
+  r(g.deg_up.data(), g.deg_up.size() * 4);
+  r(g.nbr_up.data(), g.nbr_up.size() * 4);
+  std::fclose(f);
+  if (!ok) return fail(CM_ERR_INVALID_SNAPSHOT, "invalid snapshot: truncated graph sidecar");
+  g.built = true;
+  for (uint64_t i = 0; i < g.n; ++i) {  // bounds before trusting it on the device
+    uint32_t t = g.top_layer[i];
+    if (t > kMaxLayer || (t > 0 && (uint64_t)g.upper_base[i] + t > slots))
+      return fail(CM_ERR_INVALID_SNAPSHOT, "invalid snapshot: corrupt graph sidecar");
+  }
+  if (check_graph_invariants(g) != 0) return fail(CM_ERR_INVALID_SNAPSHOT, "invalid snapshot: graph sidecar fails invariants");
+  idx->graph = std::move(g);
+  return CM_OK;
+}
+
+// ---- search: device buffers -----------------------------------------------------------------------------------
+cm_status cm_search_exact_dev(const cm_index* idx, const void* q, uint32_t nq, uint32_t k, void* ids, void* dist,
+                              void* stream) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, dist);
+  if (st != CM_OK) return st;
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  return search_exact_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, k, (uint32_t*)ids, (float*)dist,
+                               (cudaStream_t)stream);
+}
+
+cm_status cm_search_hnsw_dev(const cm_index* idx, const void* q, uint32_t nq, uint32_t ef, uint32_t k, void* ids,
+                             void* dist, void* stream) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, dist);
+  if (st != CM_OK) return st;
+  if (ef > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "ef exceeds CM_MAX_K");
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  return search_hnsw_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, ef, k, (uint32_t*)ids, (float*)dist,
+                              (cudaStream_t)stream);
+}
+
+cm_status cm_search_temporal_dev(const cm_index* idx, const void* q, uint32_t nq, uint32_t k, uint32_t ef_search,
+                                 float w, float base, uint64_t now_secs, uint32_t now_nanos, int exact, void* ids,
+                                 void* score, void* dist, void* stream) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, score);
+  if (st != CM_OK) return st;
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  return search_temporal_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, k, ef_search, w, base, now_secs,
+                                  now_nanos, exact, nullptr, (uint32_t*)ids, (float*)score, (float*)dist,
+                                  (cudaStream_t)stream);
+}
+
+cm_status cm_merge_topk_dev(const void* ids, const void* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
+                            uint32_t out_len, void* out_ids, void* out_dist, int device, void* stream) {
+  if (!ids || !dist || !out_ids || !out_dist || n_shards == 0 || len == 0 || out_len == 0)
+    return fail(CM_ERR_INVALID_ARGUMENT, "bad merge arguments");
+  if ((uint64_t)n_shards * len > 16384) return fail(CM_ERR_INVALID_ARGUMENT, "n_shards * len exceeds 16384");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_merge_topk((const uint32_t*)ids, (const float*)dist, n_shards, nq, len, out_len, (uint32_t*)out_ids,
+                            (float*)out_dist, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_rerank_dev(const void* pool_ids, const void* pool_dist, uint32_t nq, uint32_t pool, uint32_t k,
+                        const void* ts_secs, const void* ts_nanos, const void* decay_rate, float w, float base,
+                        uint64_t now_secs, uint32_t now_nanos, void* out_ids, void* out_score, void* out_dist,
+                        int device, void* stream) {
+  if (!pool_ids || !pool_dist || !ts_secs || !ts_nanos || !decay_rate || !out_ids || !out_score || pool == 0 ||
+      k == 0 || pool > 8192)
+    return fail(CM_ERR_INVALID_ARGUMENT, "bad rerank arguments");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_rerank((const uint32_t*)pool_ids, (const float*)pool_dist, nq, pool, k, (const uint64_t*)ts_secs,
+                        (const uint32_t*)ts_nanos, (const float*)decay_rate, w, base, now_secs, now_nanos,
+                        (uint32_t*)out_ids, (float*)out_score, (float*)out_dist, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_metric_preprocess_dev(const void* x, uint64_t n, uint32_t dim, void* out, int device, void* stream) {
+  if (n && (!x || !out)) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_preprocess_rows((const float*)x, n, dim, dim, (float*)out, dim, nullptr, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_metric_distance_prepared_dev(const void* a, const void* b, uint64_t n, uint32_t dim, void* out, int device,
+                                          void* stream) {
+  if (n && (!a || !b || !out)) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_pair_distance((const float*)a, (const float*)b, n, dim, dim, (float*)out, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_set_exact_engine(cm_index* idx, int engine) {
+  if (!idx || engine < 0 || engine > 2) return fail(CM_ERR_INVALID_ARGUMENT, "engine must be 0, 1 or 2");
+  idx->exact_engine = engine;
+  return CM_OK;
+}
+
+// ---- search: host buffers -----------------------------------------------------------------------------------------
+// Stage q on the device, run the device path on the workspace's stream, copy results back, synchronise.
+struct HostCall {
+  Workspace* ws;
+  cudaStream_t s;
+  float* q_dev = nullptr;
+  uint32_t* ids_dev = nullptr;
+  float* a_dev = nullptr;
+  float* b_dev = nullptr;
+};
+
+static cm_status host_begin(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
+                            HostCall* hc) {
+  if (!ws->stream) CM_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+  hc->ws = ws;
+  hc->s = ws->stream;
+  size_t qbytes = (size_t)nq * qdim * sizeof(float);
+  CM_CUDA(ws->qraw.ensure(std::max<size_t>(qbytes, 16)));
+  CM_CUDA(ws->out_ids.ensure(std::max<size_t>((size_t)nq * k * 4, 16)));
+  CM_CUDA(ws->out_a.ensure(std::max<size_t>((size_t)nq * k * 4, 16)));
+  CM_CUDA(ws->out_b.ensure(std::max<size_t>((size_t)nq * k * 4, 16)));
+  hc->q_dev = ws->qraw.as<float>();
+  hc->ids_dev = ws->out_ids.as<uint32_t>();
+  hc->a_dev = ws->out_a.as<float>();
+  hc->b_dev = ws->out_b.as<float>();
+  if (qbytes) CM_CUDA(cudaMemcpyAsync(hc->q_dev, q, qbytes, cudaMemcpyHostToDevice, hc->s));
+  (void)idx;
+  return CM_OK;
+}
+
+cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k, uint32_t* ids,
+                          float* dist) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, dist);
+  if (st != CM_OK) return st;
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  HostCall hc;
+  if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
+  st = search_exact_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, hc.ids_dev, hc.a_dev, hc.s);
+  if (st != CM_OK) return st;
+  size_t ob = (size_t)nq * k * 4;
+  if (ob) {
+    CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+    CM_CUDA(cudaMemcpyAsync(dist, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+  }
+  CM_CUDA(cudaStreamSynchronize(hc.s));
+  return CM_OK;
+}
+
+cm_status cm_search_hnsw(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t ef, uint32_t k,
+                         uint32_t* ids, float* dist) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, dist);
+  if (st != CM_OK) return st;
+  if (ef > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "ef exceeds CM_MAX_K");
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  HostCall hc;
+  if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
+  if (ef == 0) {  // search(.., 0) == [] (:470-472)
+    for (size_t i = 0; i < (size_t)nq * k; ++i) {
+      ids[i] = CM_NO_ID;
+      dist[i] = INFINITY;
+    }
+    return CM_OK;
+  }
+  st = search_hnsw_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, ef, k, hc.ids_dev, hc.a_dev, hc.s);
+  if (st != CM_OK) return st;
+  size_t ob = (size_t)nq * k * 4;
+  if (ob) {
+    CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+    CM_CUDA(cudaMemcpyAsync(dist, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+  }
+  CM_CUDA(cudaStreamSynchronize(hc.s));
+  fetch_hnsw_counters(lease.ws);
+  return CM_OK;
+}
+
+cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
+                             uint32_t ef_search, float w, float base, uint64_t now_secs, uint32_t now_nanos, int exact,
+                             uint32_t* ids, float* score, float* dist) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, score);
+  if (st != CM_OK) return st;
+  // validate_query (src/store.rs:379-392): dimensions first, then finiteness (checked on the device below).
+  if (qdim != idx->dim) {
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "invalid dimensions: got %u, expected %u", qdim, idx->dim);
+    return fail(CM_ERR_INVALID_DIMENSIONS, buf);
+  }
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  HostCall hc;
+  if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
+  CM_CUDA(lease.ws->small.ensure(256));
+  uint32_t* bad_row = lease.ws->small.as<uint32_t>() + 48;  // offset 192
+  CM_CUDA(cudaMemsetAsync(bad_row, 0xFF, 4, hc.s));
+  st = search_temporal_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, ef_search, w, base, now_secs, now_nanos, exact,
+                                bad_row, hc.ids_dev, hc.a_dev, hc.b_dev, hc.s);
+  if (st != CM_OK) return st;
+  uint32_t bad = 0xFFFFFFFFu;
+  CM_CUDA(cudaMemcpyAsync(&bad, bad_row, 4, cudaMemcpyDeviceToHost, hc.s));
+  size_t ob = (size_t)nq * k * 4;
+  if (ob) {
+    CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+    CM_CUDA(cudaMemcpyAsync(score, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+    if (dist) CM_CUDA(cudaMemcpyAsync(dist, hc.b_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+  }
+  CM_CUDA(cudaStreamSynchronize(hc.s));
+  if (!exact) fetch_hnsw_counters(lease.ws);
+  if (bad != 0xFFFFFFFFu)
+    return fail(CM_ERR_INVALID_VECTOR,
+                "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");
+  return CM_OK;
+}
+
+}  // extern "C"

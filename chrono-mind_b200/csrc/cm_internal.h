@@ -1,0 +1,150 @@
+// cm_internal.h — shared declarations between the host runtime (index, snapshot, graph builder) and the
+// CUDA side. Not part of the ABI.
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/chronomind_b200.h"
+
+namespace cm {
+
+constexpr uint64_t kArenaCapacity = 4096ull * 4096ull;  // src/index/arena.rs:47-50,101
+constexpr uint32_t kMaxLayer = 31;                      // src/index/lockfree_hnsw.rs:43
+constexpr uint64_t kEmptyEntry = ~0ull;                 // src/index/lockfree_hnsw.rs:46
+constexpr float kF32Epsilon = 1.1920929e-7f;
+
+// f32::total_cmp as an unsigned key (src/index/mod.rs:37-52).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t total_key(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+void set_error(const std::string& msg);  // thread-local, read by cm_last_error()
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-side HNSW graph in the flat layout the device consumes.
+//   layer 0 : nbr0[n][cap0] + deg0[n]                  (cap0 = 2M)
+//   layer>0 : only nodes with top_layer >= 1 own lists. upper_base[v] is the slot of v's layer-1 list in
+//             nbr_up[slot][capU] / deg_up[slot] (capU = M); layer l lives at slot upper_base[v] + l - 1.
+// ---------------------------------------------------------------------------------------------------------
+struct Graph {
+  uint32_t cap0 = 0, capU = 0;
+  uint64_t n = 0;
+  std::vector<uint8_t> top_layer;    // [n]
+  std::vector<uint32_t> nbr0;        // [n * cap0]
+  std::vector<uint32_t> deg0;        // [n]
+  std::vector<uint32_t> upper_base;  // [n], CM_NO_ID when top_layer == 0
+  std::vector<uint32_t> nbr_up;      // [slots * capU]
+  std::vector<uint32_t> deg_up;      // [slots]
+  uint64_t entry = kEmptyEntry;      // (top_layer << 32) | id
+  bool built = false;
+
+  const uint32_t* list(uint32_t v, uint32_t layer, uint32_t* deg) const {
+    if (layer == 0) {
+      *deg = deg0[v];
+      return &nbr0[(uint64_t)v * cap0];
+    }
+    uint32_t slot = upper_base[v] + layer - 1;
+    *deg = deg_up[slot];
+    return &nbr_up[(uint64_t)slot * capU];
+  }
+};
+
+// Build `g` over the preprocessed rows x[n][dim] following LockFreeHnsw::insert. See hnsw_build.cpp.
+void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed, int threads,
+                 Graph* g);
+int check_graph_invariants(const Graph& g);
+
+// Host metric kernels (same arithmetic as src/metric.rs; see metric_host.h).
+void preprocess_row(const float* v, uint32_t n, float* out);
+
+// ---------------------------------------------------------------------------------------------------------
+// Snapshot records (src/types.rs) as parsed by snapshot.cpp.
+// ---------------------------------------------------------------------------------------------------------
+struct SnapshotMemory {
+  std::string id;
+  uint64_t data_offset;  // into SnapshotData::vectors (floats)
+  uint64_t ts_secs;
+  uint32_t ts_nanos;
+  float importance;
+  std::string context;
+  float decay_rate;
+  std::vector<std::string> relationships;
+  uint32_t access_count;
+  uint64_t last_access_secs;
+  uint32_t last_access_nanos;
+};
+struct SnapshotData {
+  cm_config config;
+  std::vector<SnapshotMemory> memories;
+  std::vector<float> vectors;  // memories.size() * config.dimensions, file order
+};
+// Returns CM_OK or the status load_snapshot would map to; message via set_error().
+cm_status read_snapshot(const char* path, SnapshotData* out);
+cm_status validate_config(const cm_config& c);
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident index (filled by cm_index_upload; consumed by the kernels).
+// ---------------------------------------------------------------------------------------------------------
+struct DeviceIndex {
+  int device = -1;
+  uint64_t n = 0;
+  uint32_t dim = 0;
+  uint32_t dim_pad = 0;       // fp32 row stride in floats (multiple of 8 -> 32-byte aligned rows)
+  float* x32 = nullptr;       // [n][dim_pad] preprocessed rows, zero padded
+  void* xbf16 = nullptr;      // [n_pad][k_pad] bf16 copy for the tensor-core scan
+  uint64_t n_pad = 0;         // rows padded to the scan's tile height
+  uint32_t k_pad = 0;         // columns padded to a multiple of 64
+  uint8_t* deleted = nullptr; // [n]
+  uint64_t* ts_secs = nullptr;
+  uint32_t* ts_nanos = nullptr;
+  float* decay = nullptr;
+  // graph
+  bool has_graph = false;
+  uint32_t cap0 = 0, capU = 0;
+  uint32_t* nbr0 = nullptr;
+  uint32_t* deg0 = nullptr;
+  uint32_t* upper_base = nullptr;
+  uint32_t* nbr_up = nullptr;
+  uint32_t* deg_up = nullptr;
+  uint32_t entry_id = 0, entry_top = 0;
+  bool has_entry = false;
+  uint64_t live = 0;
+  int sm_count = 0;
+};
+
+}  // namespace cm
+
+// The opaque ABI type.
+struct cm_index {
+  cm_config config{};
+  uint64_t n = 0;
+  uint32_t dim = 0;
+  std::vector<float> x;             // [n][dim] preprocessed rows (host copy: graph build + upload source)
+  std::vector<uint8_t> deleted;     // [n]
+  std::vector<uint64_t> ts_secs;    // [n]
+  std::vector<uint32_t> ts_nanos;   // [n]
+  std::vector<float> decay;         // [n]
+  std::vector<std::string> ext_ids; // snapshot-loaded only
+  uint64_t live = 0;
+  cm::Graph graph;
+  uint32_t shard_rank = 0, shard_count = 1;
+  int exact_engine = 0;
+  bool uploaded = false;
+  cm::DeviceIndex dev;
+  void* workspace_pool = nullptr;   // cm::WorkspacePool*, owned (see api.cu)
+};

@@ -1,0 +1,410 @@
+// hnsw_build.cpp — host-side HNSW construction for the device index.
+//
+// The reference snapshot carries no graph (src/persistence.rs:4-6,114-119: "The index is rebuilt on load"),
+// so the engine has to construct one before it has anything to flatten. This builder follows
+// `LockFreeHnsw::insert` (src/index/lockfree_hnsw.rs:375-449) — layer draw (:126-132), greedy descent
+// (:196-201), per-layer `search_layer(ef_construction)` (:140-194), Algorithm-4 `select_diverse` with
+// keepPruned backfill (:205-240), `add_backlink` with overflow re-selection (:246-280), `raise_entry`
+// (:351-371) — but works directly in the flat padded-CSR arrays the GPU consumes (cm::Graph), with epoch
+// visited arrays and reusable heaps instead of per-call HashSet/BinaryHeap allocations, four distance
+// chains in flight per query, and per-node spinlocks instead of COW lists + epoch GC when threads > 1.
+//
+// threads == 1 gives the reference's deterministic single-threaded graph (ticket == handle); threads > 1
+// mirrors its concurrent build: correct, but linkage depends on interleaving (:21-26).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <thread>
+
+#include "cm_internal.h"
+#include "metric_host.h"
+
+namespace cm {
+namespace {
+
+inline uint64_t splitmix64(uint64_t x) {  // src/index/lockfree_hnsw.rs:71-77
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+inline uint32_t draw_layer(uint64_t seed, uint64_t ticket, double ml) {  // :126-132
+  uint64_t bits = splitmix64(seed ^ ticket);
+  double u = 1.0 - (double)(bits >> 11) / 9007199254740992.0;
+  double v = -std::log(u) * ml;
+  uint64_t l = (uint64_t)v;
+  return (uint32_t)std::min<uint64_t>(l, kMaxLayer);
+}
+
+// (TotalF32, u32) tuples packed so that u64 order == tuple order.
+inline uint64_t pack(float d, uint32_t id) { return ((uint64_t)total_key(d) << 32) | id; }
+inline uint32_t key_id(uint64_t k) { return (uint32_t)k; }
+inline uint32_t key_dist(uint64_t k) { return (uint32_t)(k >> 32); }
+inline float key_float(uint64_t k) {
+  uint32_t t = key_dist(k);
+  uint32_t b = (t & 0x80000000u) ? (t & 0x7FFFFFFFu) : ~t;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+struct Builder;
+
+struct Scratch {  // per-thread, reused across inserts
+  std::vector<uint32_t> visited;
+  uint32_t epoch = 0;
+  std::vector<uint64_t> frontier;  // min-heap (std::greater)
+  std::vector<uint64_t> best;      // max-heap (std::less)
+  std::vector<uint64_t> cands;     // search_layer output, ascending
+  std::vector<uint32_t> entry_points;
+  std::vector<uint32_t> nbuf;      // neighbor-list copy + unvisited ids
+  std::vector<float> dbuf;
+  std::vector<uint64_t> sel;
+  std::vector<uint32_t> rej, result;
+  std::vector<std::vector<uint32_t>> selected_per_layer;
+  std::vector<uint64_t> with_d;
+
+  void next_epoch(uint64_t n) {
+    if (visited.size() != n) visited.assign(n, 0), epoch = 0;
+    if (++epoch == 0) {
+      std::fill(visited.begin(), visited.end(), 0);
+      epoch = 1;
+    }
+  }
+  bool visit(uint32_t id) {  // HashSet::insert: true when newly inserted
+    if (visited[id] == epoch) return false;
+    visited[id] = epoch;
+    return true;
+  }
+};
+
+struct Builder {
+  const float* x;
+  uint64_t n;
+  uint32_t dim;
+  uint32_t M, efC, cap0, capU;
+  Graph* g;
+  bool mt;
+  std::unique_ptr<std::atomic<uint8_t>[]> locks;
+  std::atomic<uint64_t> entry{kEmptyEntry};
+
+  const float* row(uint32_t id) const { return x + (uint64_t)id * dim; }
+  uint32_t cap(uint32_t layer) const { return layer == 0 ? cap0 : capU; }  // :117-123
+
+  void lock(uint32_t id) {
+    if (!mt) return;
+    while (locks[id].exchange(1, std::memory_order_acquire)) {
+      while (locks[id].load(std::memory_order_relaxed)) _mm_pause();
+    }
+  }
+  void unlock(uint32_t id) {
+    if (mt) locks[id].store(0, std::memory_order_release);
+  }
+
+  uint32_t* list_ptr(uint32_t v, uint32_t layer, uint32_t** deg) {
+    if (layer == 0) {
+      *deg = &g->deg0[v];
+      return &g->nbr0[(uint64_t)v * cap0];
+    }
+    uint32_t slot = g->upper_base[v] + layer - 1;
+    *deg = &g->deg_up[slot];
+    return &g->nbr_up[(uint64_t)slot * capU];
+  }
+
+  // Snapshot a neighbor list (NeighborList::load, src/index/neighbors.rs:48-57) into s.nbuf[0..deg).
+  uint32_t load_list(uint32_t v, uint32_t layer, Scratch& s) {
+    uint32_t* deg;
+    lock(v);
+    uint32_t* l = list_ptr(v, layer, &deg);
+    uint32_t d = *deg;
+    if (s.nbuf.size() < 2 * (size_t)cap0 + 8) s.nbuf.resize(2 * (size_t)cap0 + 8);
+    std::memcpy(s.nbuf.data(), l, d * sizeof(uint32_t));
+    unlock(v);
+    return d;
+  }
+
+  // src/index/lockfree_hnsw.rs:140-194. Result in s.cands (ascending (dist,id)).
+  void search_layer(const float* q, const uint32_t* eps, size_t n_eps, size_t ef, uint32_t layer, Scratch& s) {
+    s.next_epoch(n);
+    s.frontier.clear();
+    s.best.clear();
+    auto fpush = [&](uint64_t k) {
+      s.frontier.push_back(k);
+      std::push_heap(s.frontier.begin(), s.frontier.end(), std::greater<uint64_t>());
+    };
+    auto bpush = [&](uint64_t k) {
+      s.best.push_back(k);
+      std::push_heap(s.best.begin(), s.best.end());
+    };
+    auto bpop = [&]() {
+      std::pop_heap(s.best.begin(), s.best.end());
+      s.best.pop_back();
+    };
+    for (size_t i = 0; i < n_eps; ++i) {
+      uint32_t ep = eps[i];
+      if (layer > g->top_layer[ep] || !s.visit(ep)) continue;
+      uint64_t k = pack(dist_prepared(row(ep), q, dim), ep);
+      fpush(k);
+      bpush(k);
+    }
+    while (s.best.size() > ef) bpop();
+
+    while (!s.frontier.empty()) {
+      std::pop_heap(s.frontier.begin(), s.frontier.end(), std::greater<uint64_t>());
+      uint64_t cur = s.frontier.back();
+      s.frontier.pop_back();
+      if (!s.best.empty() && s.best.size() >= ef && key_dist(cur) > key_dist(s.best.front())) break;
+      uint32_t deg = load_list(key_id(cur), layer, s);
+      // Keep the not-yet-visited neighbors, in list order (visited.insert happens before the distance).
+      uint32_t m = 0;
+      uint32_t* fresh = s.nbuf.data() + cap0 + 4;
+      for (uint32_t j = 0; j < deg; ++j) {
+        uint32_t nb = s.nbuf[j];
+        if (s.visit(nb)) {
+          fresh[m++] = nb;
+          _mm_prefetch((const char*)row(nb), _MM_HINT_T0);
+        }
+      }
+      if (s.dbuf.size() < m + 4) s.dbuf.resize(m + 4);
+      uint32_t j = 0;
+      for (; j + 4 <= m; j += 4) {
+        const float* rows[4] = {row(fresh[j]), row(fresh[j + 1]), row(fresh[j + 2]), row(fresh[j + 3])};
+        dist_prepared_x4(q, rows, dim, &s.dbuf[j]);
+      }
+      for (; j < m; ++j) s.dbuf[j] = dist_prepared(row(fresh[j]), q, dim);
+      // Admission is sequential in list order against the evolving worst (strict, distance only).
+      for (j = 0; j < m; ++j) {
+        uint64_t k = pack(s.dbuf[j], fresh[j]);
+        bool admit = s.best.size() < ef || key_dist(k) < key_dist(s.best.front());
+        if (admit) {
+          fpush(k);
+          bpush(k);
+          if (s.best.size() > ef) bpop();
+        }
+      }
+    }
+    s.cands.assign(s.best.begin(), s.best.end());
+    std::sort(s.cands.begin(), s.cands.end());
+  }
+
+  uint32_t descend(const float* q, uint32_t ep, uint32_t layer, Scratch& s) {  // :196-201
+    search_layer(q, &ep, 1, 1, layer, s);
+    return s.cands.empty() ? ep : key_id(s.cands[0]);
+  }
+
+  // :205-240. cands ascending; result in s.result.
+  void select_diverse(const uint64_t* cands, size_t nc, size_t m, Scratch& s) {
+    s.sel.clear();
+    s.rej.clear();
+    for (size_t i = 0; i < nc; ++i) {
+      if (s.sel.size() >= m) break;
+      uint32_t cand = key_id(cands[i]);
+      float dq = key_float(cands[i]);
+      bool diverse = true;
+      for (uint64_t ch : s.sel) {
+        float dc = dist_prepared(row(cand), row(key_id(ch)), dim);
+        if (!(dq < dc)) {  // raw f32 `<` (:225)
+          diverse = false;
+          break;
+        }
+      }
+      if (diverse)
+        s.sel.push_back(cands[i]);
+      else
+        s.rej.push_back(cand);
+    }
+    s.result.clear();
+    for (uint64_t k : s.sel) s.result.push_back(key_id(k));
+    for (uint32_t r : s.rej) {
+      if (s.result.size() >= m) break;
+      s.result.push_back(r);
+    }
+  }
+
+  void add_backlink(uint32_t from, uint32_t to, uint32_t layer, Scratch& s) {  // :246-280
+    uint32_t* deg;
+    lock(from);
+    uint32_t* l = list_ptr(from, layer, &deg);
+    uint32_t d = *deg, c = cap(layer);
+    for (uint32_t j = 0; j < d; ++j)
+      if (l[j] == to) {
+        unlock(from);
+        return;
+      }
+    if (d < c) {
+      l[d] = to;
+      *deg = d + 1;
+      unlock(from);
+      return;
+    }
+    s.with_d.clear();
+    for (uint32_t j = 0; j < d; ++j) s.with_d.push_back(pack(dist_prepared(row(l[j]), row(from), dim), l[j]));
+    s.with_d.push_back(pack(dist_prepared(row(to), row(from), dim), to));
+    std::sort(s.with_d.begin(), s.with_d.end());
+    select_diverse(s.with_d.data(), s.with_d.size(), c, s);
+    std::memcpy(l, s.result.data(), s.result.size() * sizeof(uint32_t));
+    *deg = (uint32_t)s.result.size();
+    unlock(from);
+  }
+
+  void raise_entry(uint32_t id, uint32_t top) {  // :351-371
+    uint64_t cur = entry.load(std::memory_order_acquire);
+    for (;;) {
+      bool replace = cur == kEmptyEntry || top > (uint32_t)(cur >> 32);
+      if (!replace) return;
+      if (entry.compare_exchange_weak(cur, ((uint64_t)top << 32) | id, std::memory_order_acq_rel,
+                                      std::memory_order_acquire))
+        return;
+    }
+  }
+
+  void insert(uint32_t id, Scratch& s) {  // :375-449
+    const float* q = row(id);
+    uint32_t top = g->top_layer[id];
+    uint64_t e = entry.load(std::memory_order_acquire);
+    if (e == kEmptyEntry) {
+      uint64_t expected = kEmptyEntry;
+      if (entry.compare_exchange_strong(expected, ((uint64_t)top << 32) | id, std::memory_order_acq_rel,
+                                        std::memory_order_acquire))
+        return;
+      e = expected;
+    }
+    uint32_t entry_id = (uint32_t)e, entry_top = (uint32_t)(e >> 32);
+    uint32_t ep = entry_id;
+    for (uint32_t layer = entry_top; layer > top; --layer) ep = descend(q, ep, layer, s);
+
+    s.entry_points.assign(1, ep);
+    uint32_t start = std::min(top, entry_top);
+    if (s.selected_per_layer.size() < (size_t)start + 1) s.selected_per_layer.resize(start + 1);
+    for (uint32_t layer = start + 1; layer-- > 0;) {
+      search_layer(q, s.entry_points.data(), s.entry_points.size(), efC, layer, s);
+      select_diverse(s.cands.data(), s.cands.size(), M, s);
+      s.selected_per_layer[layer] = s.result;
+      s.entry_points.clear();
+      for (uint64_t k : s.cands) s.entry_points.push_back(key_id(k));
+    }
+    lock(id);
+    for (uint32_t layer = 0; layer <= start; ++layer) {
+      uint32_t* deg;
+      uint32_t* l = list_ptr(id, layer, &deg);
+      const auto& sel = s.selected_per_layer[layer];
+      std::memcpy(l, sel.data(), sel.size() * sizeof(uint32_t));
+      *deg = (uint32_t)sel.size();
+    }
+    unlock(id);
+    for (uint32_t layer = start + 1; layer-- > 0;) {
+      // A private copy: add_backlink reuses s.result.
+      std::vector<uint32_t>& sel = s.selected_per_layer[layer];
+      for (size_t j = 0; j < sel.size(); ++j) add_backlink(sel[j], id, layer, s);
+    }
+    raise_entry(id, top);
+  }
+};
+
+}  // namespace
+
+void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed, int threads,
+                 Graph* g) {
+  g->n = n;
+  g->cap0 = (uint32_t)(p.max_connections * 2);
+  g->capU = (uint32_t)p.max_connections;
+  g->top_layer.assign(n, 0);
+  g->upper_base.assign(n, CM_NO_ID);
+  double ml = 1.0 / std::log((double)p.max_connections);  // :104
+  uint64_t slots = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t t = draw_layer(seed, i, ml);  // ticket == handle under in-order insertion
+    g->top_layer[i] = (uint8_t)t;
+    if (t > 0) {
+      g->upper_base[i] = (uint32_t)slots;
+      slots += t;
+    }
+  }
+  g->nbr0.assign(n * g->cap0, CM_NO_ID);
+  g->deg0.assign(n, 0);
+  g->nbr_up.assign(slots * g->capU, CM_NO_ID);
+  g->deg_up.assign(slots, 0);
+  g->entry = kEmptyEntry;
+
+  Builder b;
+  b.x = x;
+  b.n = n;
+  b.dim = dim;
+  b.M = (uint32_t)p.max_connections;
+  b.efC = (uint32_t)p.ef_construction;
+  b.cap0 = g->cap0;
+  b.capU = g->capU;
+  b.g = g;
+  if (threads < 1) threads = 1;
+  b.mt = threads > 1;
+  if (b.mt) {
+    b.locks.reset(new std::atomic<uint8_t>[n]);
+    for (uint64_t i = 0; i < n; ++i) b.locks[i].store(0, std::memory_order_relaxed);
+  }
+  if (n > 0) {
+    // The first insert (and a short serial prefix that seeds the upper layers) runs on this thread.
+    uint64_t serial = b.mt ? std::min<uint64_t>(n, 256) : n;
+    {
+      Scratch s;
+      for (uint64_t i = 0; i < serial; ++i) b.insert((uint32_t)i, s);
+    }
+    if (serial < n) {
+      std::atomic<uint64_t> next{serial};
+      std::vector<std::thread> ts;
+      for (int t = 0; t < threads; ++t)
+        ts.emplace_back([&] {
+          Scratch s;
+          for (;;) {
+            uint64_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n) break;
+            b.insert((uint32_t)i, s);
+          }
+        });
+      for (auto& t : ts) t.join();
+    }
+  }
+  g->entry = b.entry.load();
+  g->built = true;
+}
+
+// src/index/lockfree_hnsw.rs:295-347 on the flat layout. 0 == sound.
+int check_graph_invariants(const Graph& g) {
+  uint64_t total = g.n;
+  if (g.entry != kEmptyEntry) {
+    uint32_t eid = (uint32_t)g.entry, etop = (uint32_t)(g.entry >> 32);
+    if (eid >= total) return 1;
+    if (g.top_layer[eid] < etop) return 2;
+  }
+  std::vector<uint32_t> seen;
+  for (uint64_t id = 0; id < total; ++id) {
+    for (uint32_t layer = 0; layer <= g.top_layer[id]; ++layer) {
+      uint32_t deg;
+      const uint32_t* l = g.list((uint32_t)id, layer, &deg);
+      if (deg > (layer == 0 ? g.cap0 : g.capU)) return 3;
+      seen.assign(l, l + deg);
+      std::sort(seen.begin(), seen.end());
+      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return 6;
+      for (uint32_t j = 0; j < deg; ++j) {
+        if (l[j] == id) return 4;
+        if (l[j] >= total) return 5;
+        if (g.top_layer[l[j]] < layer) return 7;
+      }
+    }
+  }
+  return 0;
+}
+
+void preprocess_row(const float* v, uint32_t n, float* out) {  // src/metric.rs:208-214
+  float s = 0.0f;
+  for (uint32_t i = 0; i < n; ++i) s += v[i] * v[i];
+  float norm = std::sqrt(s);
+  if (norm <= kF32Epsilon) {
+    if (out != v) std::memcpy(out, v, (size_t)n * sizeof(float));
+    return;
+  }
+  for (uint32_t i = 0; i < n; ++i) out[i] = v[i] / norm;
+}
+
+}  // namespace cm

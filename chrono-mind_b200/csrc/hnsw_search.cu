@@ -1,0 +1,399 @@
+// hnsw_search.cu — K3: batched HNSW search, one CTA per query.
+//
+// Replaces `LockFreeHnsw::search` (src/index/lockfree_hnsw.rs:469-495) and `search_layer` (:140-194) for a
+// batch of prepared queries over the frozen, flattened graph (padded CSR, see cm::DeviceIndex):
+//   greedy descent through layers entry_top..1 with ef = 1, then the layer-0 beam with ef candidates.
+//
+// How the reference's two heaps map onto a GPU:
+//   * `best` (max-heap, cap ef) is a SORTED list of u64 keys (TotalF32 distance << 32 | handle << 1 | expanded)
+//     in shared memory. `frontier` needs no storage: every admitted-but-unexpanded node that could still be
+//     popped is exactly an unexpanded entry of `best` (a node evicted from `best` is >= worst and would hit the
+//     `dist > worst` break), so "pop the frontier" == "first unexpanded list entry" and the loop ends when none
+//     is left. Per expansion the <=32 fresh neighbors are merged into the list by rank (each key computes its
+//     position in the union), which equals the reference's sequential admit/evict except when two different
+//     nodes have bit-identical distances at the admission boundary (the reference compares distance only,
+//     strictly; see DESIGN.md "Known deviations").
+//   * `visited` (HashSet<u32>) is an open-addressing table in shared memory, tagged with an 8-bit epoch so it
+//     never has to be cleared between layers or queries. Membership is exact. When a query would crowd the
+//     table past 3/4 the CTA restarts that query on a larger per-CTA table in global memory.
+//   * distance_prepared is evaluated bit-exactly: thread (n, j) of the CTA owns SIMD lane j of neighbor n,
+//     i.e. the reference's 8-lane FMA chain over elements j, j+8, ... (src/metric.rs:129-147); an octet reads
+//     one 32-byte sector per step, then the reference's reduction order and scalar tail.
+//
+// Gather-bound: per expansion one 128-byte neighbor list and up to 32 rows of dim*4 bytes.
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace cm {
+
+constexpr int HN_THREADS = 256;
+
+struct HnswKernelArgs {
+  const float* x;
+  uint32_t ldx, dim;
+  const uint32_t* nbr0;
+  const uint32_t* upper_base;
+  const uint32_t* nbr_up;
+  uint32_t cap0, capU;
+  const uint8_t* deleted;
+  uint32_t entry_id, entry_top;
+  const float* q;
+  uint32_t nq, ldq, ef;
+  uint32_t degenerate;  // query length != dim: every distance is 2.0 (src/metric.rs:220-222)
+  uint32_t* pool_ids;
+  float* pool_dist;
+  unsigned long long* counters;  // [0] dist_evals [1] expansions [2] list_entries [3] global-table restarts [4] failures
+  uint32_t* work_counter;
+  uint32_t hash_bits;      // shared-memory table
+  uint32_t* gtable;        // [gridDim.x] slabs of 1 << ghash_bits entries
+  uint32_t ghash_bits;
+};
+
+struct HnShared {
+  unsigned long long cand[32];
+  uint32_t fresh[32];
+  uint32_t list_count;
+  uint32_t fresh_count;
+  int cur_pos;
+  uint32_t cur_id;
+  uint32_t query;
+  uint32_t visited_count;
+  uint32_t overflow;
+  uint32_t epoch;
+  unsigned long long ctr_evals, ctr_exp, ctr_entries;
+};
+
+struct VisitedTable {
+  uint32_t* slots;
+  uint32_t bits;
+};
+
+__device__ __forceinline__ uint32_t key_handle(unsigned long long key) { return ((uint32_t)key) >> 1; }
+__device__ __forceinline__ unsigned long long make_key(float d, uint32_t id) {
+  return ((unsigned long long)total_key(d) << 32) | ((unsigned long long)id << 1);
+}
+
+// HashSet::insert — true when `id` was not present. Called by the lanes of warp 0 concurrently. The caller
+// keeps the load below 3/4, so the probe always ends.
+__device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t tag, uint32_t id) {
+  const uint32_t mask = (1u << t.bits) - 1;
+  uint32_t want = tag | id;
+  uint32_t h = (id * 2654435761u) >> (32 - t.bits);
+  for (;;) {
+    uint32_t old = t.slots[h];
+    if (old == want) return false;
+    if ((old & 0xFF000000u) != tag) {  // empty, or left over from another epoch: claim it
+      uint32_t prev = atomicCAS(&t.slots[h], old, want);
+      if (prev == old) return true;
+      if (prev == want) return false;
+      continue;  // another lane took the slot for a different id of this epoch: look at it again
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// distance_prepared(x[id], q) by one octet; every lane of the octet returns the same bits.
+__device__ __forceinline__ float octet_distance(const HnswKernelArgs& a, const float* qs, uint32_t id, uint32_t j,
+                                                bool active) {
+  const uint32_t body = a.dim & ~7u;
+  const float* xr = a.x + (uint64_t)id * a.ldx;
+  float acc = 0.0f;
+  if (active && !a.degenerate) {
+#pragma unroll 8
+    for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(__ldg(xr + e), qs[e], acc);
+  }
+  float sum = octet_hsum(acc);
+  if (active && !a.degenerate)
+    for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(__ldg(xr + e), qs[e]));
+  return a.degenerate ? 2.0f : clamp02(__fsub_rn(1.0f, sum));
+}
+
+// One search_layer call over shared state. `lists` holds two ping-pong buffers of `ef_cap` keys; returns which
+// one holds the result (ascending). All threads of the CTA call this.
+__device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const float* qs, unsigned long long* lists,
+                                uint32_t ef_cap, const VisitedTable& vt, uint32_t ef, uint32_t layer, uint32_t ep) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_slot = tid >> 3, j = tid & 7;
+  const uint32_t cap = layer == 0 ? a.cap0 : a.capU;
+  const uint32_t table_size = 1u << vt.bits;
+  const uint32_t limit = (table_size >> 1) + (table_size >> 2);
+  int buf = 0;
+
+  // A fresh visited set per call (:148): bump the epoch; clear the table when the 8-bit tag wraps.
+  if (tid == 0) {
+    sh->epoch += 1;
+    sh->visited_count = 0;
+  }
+  __syncthreads();
+  if (sh->epoch == 256) {
+    for (uint32_t i = tid; i < table_size; i += HN_THREADS) vt.slots[i] = 0;
+    __syncthreads();
+    if (tid == 0) sh->epoch = 1;
+    __syncthreads();
+  }
+  const uint32_t tag = sh->epoch << 24;
+
+  // Entry point: pushed to both heaps (:152-160).
+  if (tid == 0) {
+    visited_insert(vt, tag, ep);
+    sh->visited_count = 1;
+  }
+  {
+    float d = octet_distance(a, qs, ep, j, n_slot == 0);
+    if (tid == 0) {
+      lists[0] = make_key(d, ep);
+      sh->list_count = 1;
+      sh->ctr_evals += 1;
+    }
+  }
+  __syncthreads();
+
+  for (;;) {
+    unsigned long long* L = lists + (size_t)buf * ef_cap;
+    // pop: first unexpanded entry of the ascending list == nearest frontier element (:165)
+    if (warp == 0) {
+      uint32_t cnt = sh->list_count;
+      int pos = -1;
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        uint32_t i = base + lane;
+        bool un = i < cnt && !(L[i] & 1ull);
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, un);
+        if (m) {
+          pos = (int)(base + __ffs(m) - 1);
+          break;
+        }
+      }
+      if (lane == 0) {
+        sh->cur_pos = pos;
+        if (pos >= 0) {
+          sh->cur_id = key_handle(L[pos]);
+          L[pos] |= 1ull;
+          sh->ctr_exp += 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (sh->cur_pos < 0 || sh->overflow) break;
+    const uint32_t cur = sh->cur_id;
+    const uint32_t* nlist = layer == 0 ? a.nbr0 + (uint64_t)cur * a.cap0
+                                       : a.nbr_up + (uint64_t)(__ldg(a.upper_base + cur) + layer - 1) * a.capU;
+
+    for (uint32_t c0 = 0; c0 < cap; c0 += 32) {
+      // visited filter in list order (:174-177), warp 0
+      if (warp == 0) {
+        bool room = sh->visited_count + 32 <= limit;
+        uint32_t i = c0 + lane;
+        uint32_t nb = i < cap ? __ldg(nlist + i) : CM_NO_ID_DEV;
+        bool present = nb != CM_NO_ID_DEV;
+        bool is_new = room && present && visited_insert(vt, tag, nb);
+        uint32_t pm = __ballot_sync(0xFFFFFFFFu, present);
+        uint32_t nm = __ballot_sync(0xFFFFFFFFu, is_new);
+        if (is_new) sh->fresh[__popc(nm & ((1u << lane) - 1))] = nb;
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t m = __popc(nm);
+          sh->fresh_count = m;
+          sh->visited_count += m;
+          sh->ctr_entries += __popc(pm);
+          sh->ctr_evals += m;
+          if (!room) sh->overflow = 1;
+        }
+      }
+      __syncthreads();
+      const uint32_t m = sh->fresh_count;
+      if (sh->overflow) break;  // uniform: written before the barrier
+      if (m == 0) {
+        __syncthreads();
+        continue;
+      }
+      // distances (:181): thread (n_slot, j) = SIMD lane j of fresh neighbor n_slot
+      {
+        const bool active = n_slot < m;
+        const uint32_t nb = active ? sh->fresh[n_slot] : 0;
+        float d = octet_distance(a, qs, nb, j, active);
+        if (active && j == 0) sh->cand[n_slot] = make_key(d, nb);
+      }
+      __syncthreads();
+      // admit + evict (:182-189) as a merge by rank into the other buffer
+      {
+        const uint32_t cnt = sh->list_count;
+        unsigned long long* Lsrc = lists + (size_t)buf * ef_cap;
+        unsigned long long* Ldst = lists + (size_t)(buf ^ 1) * ef_cap;
+        for (uint32_t i = tid; i < cnt + m; i += HN_THREADS) {
+          unsigned long long key = i < cnt ? Lsrc[i] : sh->cand[i - cnt];
+          uint32_t pos = 0;
+          for (uint32_t c = 0; c < m; ++c) pos += sh->cand[c] < key;
+          if (i < cnt) {
+            pos += i;
+          } else {  // list keys below `key`: binary search (keys are unique)
+            uint32_t lo = 0, hi = cnt;
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (Lsrc[mid] < key)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            pos += lo;
+          }
+          if (pos < ef) Ldst[pos] = key;
+        }
+        __syncthreads();
+        if (tid == 0) sh->list_count = min(ef, cnt + m);
+        buf ^= 1;
+        __syncthreads();
+      }
+    }
+    if (sh->overflow) break;
+  }
+  return buf;
+}
+
+__global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t ef_cap = a.ef;
+  float* qs = reinterpret_cast<float*>(smem_raw);
+  size_t off = ((size_t)a.dim * 4 + 15) & ~(size_t)15;
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(smem_raw + off);
+  off += (size_t)2 * ef_cap * 8;
+  uint32_t* stable = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off += (size_t)4 << a.hash_bits;
+  HnShared* sh = reinterpret_cast<HnShared*>(smem_raw + ((off + 15) & ~(size_t)15));
+
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < (1u << a.hash_bits); i += HN_THREADS) stable[i] = 0;
+  if (tid == 0) {
+    sh->epoch = 0;
+    sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = 0;
+  }
+  __syncthreads();
+
+  for (;;) {
+    if (tid == 0) sh->query = atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const uint32_t qi = sh->query;
+    if (qi >= a.nq) break;
+    for (uint32_t e = tid; e < a.dim; e += HN_THREADS) qs[e] = a.degenerate ? 0.0f : a.q[(uint64_t)qi * a.ldq + e];
+
+    bool use_global = false;
+    int b = 0;
+    for (;;) {
+      VisitedTable vt;
+      if (use_global) {
+        vt.slots = a.gtable + ((size_t)blockIdx.x << a.ghash_bits);
+        vt.bits = a.ghash_bits;
+        for (uint32_t i = tid; i < (1u << vt.bits); i += HN_THREADS) vt.slots[i] = 0;
+      } else {
+        vt.slots = stable;
+        vt.bits = a.hash_bits;
+      }
+      if (tid == 0) sh->overflow = 0;
+      __syncthreads();
+
+      uint32_t ep = a.entry_id;
+      for (uint32_t layer = a.entry_top; layer >= 1 && !sh->overflow; --layer) {  // descend_layer (:196-201)
+        int bb = search_layer_dev(a, sh, qs, lists, ef_cap, vt, 1, layer, ep);
+        ep = key_handle(lists[(size_t)bb * ef_cap]);
+        __syncthreads();
+      }
+      if (!sh->overflow) b = search_layer_dev(a, sh, qs, lists, ef_cap, vt, a.ef, 0, ep);
+      __syncthreads();
+      if (!sh->overflow) break;
+      if (use_global) {  // cannot happen for sane ef; reported, never silent
+        if (tid == 0) atomicAdd(&a.counters[4], 1ull);
+        if (tid == 0) sh->list_count = 0;
+        __syncthreads();
+        break;
+      }
+      use_global = true;
+      if (tid == 0) atomicAdd(&a.counters[3], 1ull);
+    }
+    if (use_global) {  // the shared table missed epochs while the global one was in use: start it over
+      for (uint32_t i = tid; i < (1u << a.hash_bits); i += HN_THREADS) stable[i] = 0;
+      if (tid == 0) sh->epoch = 0;
+      __syncthreads();
+    }
+    const unsigned long long* L = lists + (size_t)b * ef_cap;
+
+    // tombstone filter on the final list only (:488-492), order preserved; pad to ef.
+    if (tid < 32) {
+      uint32_t cnt = sh->list_count, outp = 0;
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        uint32_t i = base + tid;
+        unsigned long long key = i < cnt ? L[i] : 0;
+        uint32_t id = key_handle(key);
+        bool keep = i < cnt && !(a.deleted && a.deleted[id]);
+        uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+        if (keep) {
+          uint32_t o = outp + __popc(km & ((1u << tid) - 1));
+          a.pool_ids[(uint64_t)qi * a.ef + o] = id;
+          a.pool_dist[(uint64_t)qi * a.ef + o] = key_to_float((uint32_t)(key >> 32));
+        }
+        outp += __popc(km);
+      }
+      for (uint32_t o = outp + tid; o < a.ef; o += 32) {
+        a.pool_ids[(uint64_t)qi * a.ef + o] = CM_NO_ID_DEV;
+        a.pool_dist[(uint64_t)qi * a.ef + o] = __int_as_float(0x7F800000);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && a.counters) {
+    atomicAdd(&a.counters[0], sh->ctr_evals);
+    atomicAdd(&a.counters[1], sh->ctr_exp);
+    atomicAdd(&a.counters[2], sh->ctr_entries);
+  }
+}
+
+static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits) {
+  return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + ((size_t)4 << hash_bits) + 16 + sizeof(HnShared);
+}
+
+cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid) {
+  size_t smem = hnsw_smem_bytes(ix.dim, ef, hash_bits);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k_hnsw_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hnsw_search, HN_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  *grid = (unsigned)ix.sm_count * per_sm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& l, cudaStream_t s) {
+  if (l.nq == 0) return cudaSuccess;
+  HnswKernelArgs a;
+  a.x = ix.x32;
+  a.ldx = ix.dim_pad;
+  a.dim = ix.dim;
+  a.nbr0 = ix.nbr0;
+  a.upper_base = ix.upper_base;
+  a.nbr_up = ix.nbr_up;
+  a.cap0 = ix.cap0;
+  a.capU = ix.capU;
+  a.deleted = ix.deleted;
+  a.entry_id = ix.entry_id;
+  a.entry_top = ix.entry_top;
+  a.q = l.q;
+  a.nq = l.nq;
+  a.ldq = l.ldq;
+  a.ef = l.ef;
+  a.degenerate = l.degenerate;
+  a.pool_ids = l.pool_ids;
+  a.pool_dist = l.pool_dist;
+  a.counters = l.counters;
+  a.work_counter = l.work_counter;
+  a.hash_bits = l.hash_bits;
+  a.gtable = l.gtable;
+  a.ghash_bits = l.ghash_bits;
+  cudaError_t e = cudaMemsetAsync(l.work_counter, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  unsigned grid = l.grid < l.nq ? l.grid : l.nq;
+  k_hnsw_search<<<grid, HN_THREADS, hnsw_smem_bytes(ix.dim, l.ef, l.hash_bits), s>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace cm

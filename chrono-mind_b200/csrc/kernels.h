@@ -1,0 +1,68 @@
+// kernels.h — launchers of the CUDA kernels (defined in the .cu files of this directory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cm_internal.h"
+
+namespace cm {
+
+void count_launch();  // bumps the process-wide and the thread-local launch counters
+
+// K0 — CosineDistance::preprocess per row (src/metric.rs:208-214). out may alias x when ld_in == ld_out.
+// Columns [dim, ld_out) of out are zeroed. bad_row (optional, device u32 preset to UINT32_MAX) receives the
+// smallest row index holding a non-finite component (validate_query, src/store.rs:386-390).
+cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, float* out,
+                                   uint32_t ld_out, uint32_t* bad_row, cudaStream_t s);
+
+// fp32 -> bf16 copy of prepared rows into the tensor-core scan layout [n_pad][k_pad] (zero padded).
+cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
+                           uint32_t k_pad, cudaStream_t s);
+
+// distance_prepared for n row pairs (src/metric.rs:219-224).
+cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
+                                 cudaStream_t s);
+
+// fp32 exact scan, CUDA cores, bit-exact to dot_avx2: D[qi][row] = distance_prepared(x[row], q[qi]).
+cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
+                              uint32_t ldx, float* D, uint64_t ldD, cudaStream_t s);
+cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
+
+// k smallest (distance, handle) per row of D, tombstones dropped.
+cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
+                                    uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, cudaStream_t s);
+
+// K5 — shard merge (src/index/sharded_rwlock.rs:81-94).
+cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
+                              uint32_t out_len, uint32_t* out_ids, float* out_dist, cudaStream_t s);
+
+// K4 — rerank tail of ChronoMind::search (src/store.rs:327-344, 395-415).
+cudaError_t launch_rerank(const uint32_t* pool_ids, const float* pool_dist, uint32_t nq, uint32_t pool, uint32_t k,
+                          const uint64_t* ts_secs, const uint32_t* ts_nanos, const float* decay, float w, float base,
+                          uint64_t now_secs, uint32_t now_nanos, uint32_t* out_ids, float* out_score,
+                          float* out_dist, cudaStream_t s);
+
+// K3 — batched HNSW search (src/index/lockfree_hnsw.rs:140-194, 469-495). q: prepared queries [nq][ldq].
+// Writes the tombstone-filtered candidate pool, ascending (distance, handle): pool_ids/pool_dist [nq][ef]
+// padded with CM_NO_ID / +inf.
+struct HnswLaunch {
+  const float* q;
+  uint32_t nq, ldq, ef;
+  uint32_t degenerate;       // query length != dim: all distances are 2.0
+  uint32_t* pool_ids;
+  float* pool_dist;
+  unsigned long long* counters;  // device, 8 x u64: dist_evals, expansions, list_entries, gtable restarts, failures
+  uint32_t* work_counter;    // device u32, zeroed by the launcher
+  uint32_t hash_bits;        // shared-memory visited table = 1 << hash_bits entries
+  uint32_t* gtable;          // per-CTA overflow tables in global memory, grid << ghash_bits entries
+  uint32_t ghash_bits;
+  unsigned grid;             // from hnsw_grid_size()
+};
+cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid);
+cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& a, cudaStream_t s);
+
+// K1/K2 — tcgen05 bf16 scan + fp32 rescore (scan_tc.cu).
+struct ScanTcWorkspace;
+cudaError_t scan_tc_supported(const DeviceIndex& ix);
+
+}  // namespace cm

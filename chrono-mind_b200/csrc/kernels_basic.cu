@@ -1,0 +1,426 @@
+// kernels_basic.cu — CUDA-core kernels of the read path: preprocess (K0), the bit-exact fp32 scan, top-k
+// select, shard merge (K5), temporal rerank (K4) and the metric surface.
+//
+// All of this is HBM/ALU work on CUDA cores (no GEMM shape is forced onto it); the tensor-core scan lives
+// in scan_tc.cu and the graph traversal in hnsw_search.cu.
+#include <cuda_bf16.h>
+
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace cm {
+
+// ---------------------------------------------------------------------------------------------------------
+// K0 preprocess — CosineDistance::preprocess (src/metric.rs:208-214).
+// One warp owns 32 rows. Tiles of 32x32 floats are staged through shared memory so that global reads are
+// coalesced while each lane still walks ITS row sequentially: s += x*x with a separately rounded multiply and
+// add, exactly like the reference's scalar `map(|x| x * x).sum()`.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_preprocess_rows(const float* __restrict__ x, uint64_t n, uint32_t dim,
+                                                        uint32_t ld_in, float* __restrict__ out, uint32_t ld_out,
+                                                        uint32_t* bad_row) {
+  __shared__ float tile[32][33];
+  __shared__ float norms[32];
+  const uint32_t lane = threadIdx.x;
+  const uint64_t row0 = (uint64_t)blockIdx.x * 32;
+  float s = 0.0f;
+  for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
+    for (uint32_t r = 0; r < 32; ++r) {
+      uint64_t row = row0 + r;
+      uint32_t c = c0 + lane;
+      float v = (row < n && c < dim) ? x[row * ld_in + c] : 0.0f;
+      // validate_query (src/store.rs:386-390): remember the first row with a NaN/Inf component.
+      if (bad_row && !isfinite(v)) atomicMin(bad_row, (uint32_t)row);
+      tile[r][lane] = v;
+    }
+    __syncwarp();
+    uint32_t lim = min(32u, dim - c0);
+    for (uint32_t c = 0; c < lim; ++c) {
+      float v = tile[lane][c];
+      s = __fadd_rn(s, __fmul_rn(v, v));
+    }
+    __syncwarp();
+  }
+  norms[lane] = __fsqrt_rn(s);
+  __syncwarp();
+  for (uint32_t r = 0; r < 32; ++r) {
+    uint64_t row = row0 + r;
+    if (row >= n) break;
+    float nr = norms[r];
+    bool degenerate = nr <= 1.1920929e-7f;  // f32::EPSILON: left unchanged
+    for (uint32_t c = lane; c < ld_out; c += 32) {
+      float v = 0.0f;
+      if (c < dim) {
+        v = x[row * ld_in + c];
+        if (!degenerate) v = __fdiv_rn(v, nr);
+      }
+      out[row * ld_out + c] = v;
+    }
+  }
+}
+
+cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, float* out,
+                                   uint32_t ld_out, uint32_t* bad_row, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  // In-place use is only safe when the strides match (each row is fully read before it is written by the
+  // same warp: reads happen in the first loop, writes in the second).
+  k_preprocess_rows<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(x, n, dim, ld_in, out, ld_out, bad_row);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 -> bf16 (round to nearest even) into the scan layout.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_to_bf16(const float* __restrict__ x, uint64_t n, uint32_t dim, uint32_t ld_in,
+                          __nv_bfloat16* __restrict__ out, uint64_t n_pad, uint32_t k_pad) {
+  uint64_t total = n_pad * (uint64_t)(k_pad / 2);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t row = i / (k_pad / 2);
+    uint32_t c = (uint32_t)(i % (k_pad / 2)) * 2;
+    float a = 0.0f, b = 0.0f;
+    if (row < n) {
+      if (c < dim) a = x[row * ld_in + c];
+      if (c + 1 < dim) b = x[row * ld_in + c + 1];
+    }
+    reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
+  }
+}
+
+cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
+                           uint32_t k_pad, cudaStream_t s) {
+  if (n_pad == 0) return cudaSuccess;
+  k_to_bf16<<<148 * 8, 256, 0, s>>>(x, n, dim, ld_in, (__nv_bfloat16*)out, n_pad, k_pad);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// distance_prepared on row pairs (src/metric.rs:219-224): one lane-octet per pair; lane j carries the
+// reference's SIMD lane j (elements j, j+8, ...), then the reference's reduction order and scalar tail.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_distance(const float* __restrict__ a, const float* __restrict__ b,
+                                                       uint64_t n, uint32_t dim, uint32_t ld, float* __restrict__ out) {
+  uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  uint32_t j = threadIdx.x & 7;
+  bool valid = pair < n;
+  uint64_t p = valid ? pair : 0;
+  const float* pa = a + p * ld;
+  const float* pb = b + p * ld;
+  uint32_t body = dim & ~7u;
+  float acc = 0.0f;
+  for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(pa[e], pb[e], acc);
+  float sum = octet_hsum(acc);
+  for (uint32_t e = body; e < dim; ++e) sum = __fadd_rn(sum, __fmul_rn(pa[e], pb[e]));
+  if (valid && j == 0) out[pair] = dim == 0 ? 2.0f : clamp02(__fsub_rn(1.0f, sum));
+}
+
+cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
+                                 cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint64_t threads = n * 8;
+  k_pair_distance<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, b, n, dim, ld, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 exact scan (CUDA cores), bit-exact to the reference's dot_avx2.
+//
+// CTA = 8 warps, 16 queries x 256 rows. The 16 queries sit in shared memory transposed (qs[e][qi]) so one
+// lane fetches the 16 query values of its element with four LDS.128. A warp covers 4 rows x 8 SIMD lanes
+// per pass: lane (r, j) streams x[row][8t + j] (the octet reads one 32-byte sector per step) and keeps 16
+// accumulators — the reference's lane-j partial sum for each of the 16 queries — so every x value is reused
+// 16 times from a register.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int EX_QT = 16;
+constexpr int EX_ROWS = 256;
+
+__global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
+                                                    const float* __restrict__ x, uint64_t n, uint32_t dim,
+                                                    uint32_t ldx, float* __restrict__ D, uint64_t ldD) {
+  extern __shared__ __align__(16) float qs[];  // [body][16]
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t j = lane & 7, rsub = lane >> 3;
+  const uint32_t body = dim & ~7u;
+  const uint32_t q0 = blockIdx.y * EX_QT;
+
+  for (uint32_t idx = tid; idx < body * EX_QT; idx += 256) {
+    uint32_t e = idx / EX_QT, qi = idx % EX_QT;
+    uint32_t qq = q0 + qi;
+    qs[idx] = qq < nq ? q[(uint64_t)qq * ldq + e] : 0.0f;
+  }
+  __syncthreads();
+
+  const uint64_t row_base = (uint64_t)blockIdx.x * EX_ROWS;
+  for (uint32_t pass = 0; pass < EX_ROWS / 32; ++pass) {
+    uint64_t row = row_base + pass * 32 + warp * 4 + rsub;
+    bool valid = row < n;
+    const float* xr = x + (valid ? row : 0) * ldx;
+    float acc[EX_QT];
+#pragma unroll
+    for (int i = 0; i < EX_QT; ++i) acc[i] = 0.0f;
+#pragma unroll 4
+    for (uint32_t e = j; e < body; e += 8) {
+      float xv = __ldg(xr + e);
+      const float4* qp = reinterpret_cast<const float4*>(qs + (size_t)e * EX_QT);
+      float4 a = qp[0], b = qp[1], c = qp[2], d = qp[3];
+      acc[0] = __fmaf_rn(xv, a.x, acc[0]);
+      acc[1] = __fmaf_rn(xv, a.y, acc[1]);
+      acc[2] = __fmaf_rn(xv, a.z, acc[2]);
+      acc[3] = __fmaf_rn(xv, a.w, acc[3]);
+      acc[4] = __fmaf_rn(xv, b.x, acc[4]);
+      acc[5] = __fmaf_rn(xv, b.y, acc[5]);
+      acc[6] = __fmaf_rn(xv, b.z, acc[6]);
+      acc[7] = __fmaf_rn(xv, b.w, acc[7]);
+      acc[8] = __fmaf_rn(xv, c.x, acc[8]);
+      acc[9] = __fmaf_rn(xv, c.y, acc[9]);
+      acc[10] = __fmaf_rn(xv, c.z, acc[10]);
+      acc[11] = __fmaf_rn(xv, c.w, acc[11]);
+      acc[12] = __fmaf_rn(xv, d.x, acc[12]);
+      acc[13] = __fmaf_rn(xv, d.y, acc[13]);
+      acc[14] = __fmaf_rn(xv, d.z, acc[14]);
+      acc[15] = __fmaf_rn(xv, d.w, acc[15]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < EX_QT; ++qi) {
+      float sum = octet_hsum(acc[qi]);
+      uint32_t qq = q0 + qi;
+      if (body < dim && qq < nq) {
+        const float* qrow = q + (uint64_t)qq * ldq;
+        for (uint32_t e = body; e < dim; ++e) sum = __fadd_rn(sum, __fmul_rn(xr[e], qrow[e]));
+      }
+      if ((qi & 7) == (int)j && valid && qq < nq) D[(uint64_t)qq * ldD + row] = clamp02(__fsub_rn(1.0f, sum));
+    }
+  }
+}
+
+cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
+                              uint32_t ldx, float* D, uint64_t ldD, cudaStream_t s) {
+  if (nq == 0 || n == 0) return cudaSuccess;
+  size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_exact_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // D rows are indexed by the query's position inside this launch.
+  dim3 grid((unsigned)((n + EX_ROWS - 1) / EX_ROWS), (nq + EX_QT - 1) / EX_QT);
+  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void k_fill(float* p, uint64_t n, float v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_fill<<<148 * 4, 256, 0, s>>>(p, n, v);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Top-k select: the k smallest (TotalF32 distance, handle) tuples of one row of D per CTA — the stable
+// `sort_by(total_cmp)` + `take(k)` of tests/recall_test.rs:77-78 / tests/property_test.rs:206 without sorting
+// the row. Threshold filter + shared-memory candidate buffer + bitonic flushes.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t SEL_THREADS = 256;
+constexpr uint32_t SEL_BUF = 2048;
+constexpr uint32_t SEL_STEP = SEL_THREADS * 4;
+
+struct SelState {
+  unsigned long long tau;
+  uint32_t cnt;
+};
+
+// Sort keys[0 .. kp+cnt) (padded with MAX to a power of two), keep the first kp, refresh tau = k-th key.
+__device__ __forceinline__ void select_flush(unsigned long long* keys, uint32_t kp, uint32_t k, SelState* st) {
+  __syncthreads();
+  uint32_t total = kp + st->cnt;
+  uint32_t P = next_pow2(total);
+  for (uint32_t i = total + threadIdx.x; i < P; i += blockDim.x) keys[i] = kKeyMax;
+  block_bitonic_sort(keys, P);
+  if (threadIdx.x == 0) {
+    st->cnt = 0;
+    st->tau = keys[k - 1];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* __restrict__ D, uint64_t ldD, uint64_t n,
+                                                                  const uint8_t* __restrict__ deleted, uint32_t k,
+                                                                  uint32_t kp, uint32_t* __restrict__ ids,
+                                                                  float* __restrict__ dist, uint32_t out_ld) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // next_pow2(kp + SEL_BUF)
+  __shared__ SelState st;
+  const float* row = D + (uint64_t)blockIdx.x * ldD;
+  for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) keys[i] = kKeyMax;
+  if (threadIdx.x == 0) {
+    st.cnt = 0;
+    st.tau = kKeyMax;
+  }
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += SEL_STEP) {
+    unsigned long long tau = st.tau;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint64_t i = base + c * SEL_THREADS + threadIdx.x;
+      if (i < n) {
+        unsigned long long key = pack_key(row[i], (uint32_t)i);
+        if (key < tau && !(deleted && deleted[i])) {
+          uint32_t slot = atomicAdd(&st.cnt, 1u);
+          keys[kp + slot] = key;
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t pending = st.cnt;  // read between two barriers: no thread is appending
+    __syncthreads();
+    if (pending > SEL_BUF - SEL_STEP) select_flush(keys, kp, k, &st);
+  }
+  select_flush(keys, kp, k, &st);
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    unsigned long long key = keys[i];
+    bool ok = key != kKeyMax;
+    ids[(uint64_t)blockIdx.x * out_ld + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    dist[(uint64_t)blockIdx.x * out_ld + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  }
+}
+
+cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
+                                    uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  uint32_t kp = next_pow2(k < 32 ? 32 : k);
+  size_t smem = (size_t)next_pow2(kp + SEL_BUF) * sizeof(unsigned long long);
+  k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5 shard merge — ShardedRwLockHnsw::search's gather step (src/index/sharded_rwlock.rs:81-94): concat the
+// per-shard lists, sort by (distance, global handle), truncate. global = local * n_shards + shard.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_merge_topk(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
+                                                    uint32_t n_shards, uint32_t nq, uint32_t len, uint32_t out_len,
+                                                    uint32_t P, uint32_t* __restrict__ out_ids,
+                                                    float* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // P >= n_shards * len
+  const uint32_t qi = blockIdx.x;
+  const uint32_t total = n_shards * len;
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = kKeyMax;
+    if (i < total) {
+      uint32_t sh = i / len, jj = i % len;
+      uint64_t o = ((uint64_t)sh * nq + qi) * len + jj;
+      uint32_t local = ids[o];
+      if (local != CM_NO_ID_DEV) key = pack_key(dist[o], local * n_shards + sh);
+    }
+    keys[i] = key;
+  }
+  block_bitonic_sort(keys, P);
+  for (uint32_t i = threadIdx.x; i < out_len; i += blockDim.x) {
+    unsigned long long key = i < P ? keys[i] : kKeyMax;
+    bool ok = key != kKeyMax;
+    out_ids[(uint64_t)qi * out_len + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    out_dist[(uint64_t)qi * out_len + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  }
+}
+
+cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
+                              uint32_t out_len, uint32_t* out_ids, float* out_dist, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  uint32_t P = next_pow2(n_shards * len < 32 ? 32 : n_shards * len);
+  size_t smem = (size_t)P * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_merge_topk<<<nq, 256, smem, s>>>(ids, dist, n_shards, nq, len, out_len, P, out_ids, out_dist);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4 temporal rerank — ChronoMind::search's tail (src/store.rs:327-344) with combined_score (:395-415).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float combined_score_dev(float distance, unsigned long long ts_secs, uint32_t ts_nanos,
+                                                    float decay_rate, unsigned long long now_secs,
+                                                    uint32_t now_nanos, float w, float base_decay_rate) {
+  // now.duration_since(ts).unwrap_or_default()
+  unsigned long long dsecs = 0;
+  uint32_t dnanos = 0;
+  bool later = (now_secs > ts_secs) || (now_secs == ts_secs && now_nanos >= ts_nanos);
+  if (later) {
+    dsecs = now_secs - ts_secs;
+    if (now_nanos >= ts_nanos) {
+      dnanos = now_nanos - ts_nanos;
+    } else {
+      dsecs -= 1;
+      dnanos = now_nanos + 1000000000u - ts_nanos;
+    }
+  }
+  // Duration::as_secs_f32 = secs as f32 + nanos as f32 / 1e9
+  float age_secs = __fadd_rn(__ull2float_rn(dsecs), __fdiv_rn(__uint2float_rn(dnanos), 1.0e9f));
+  float age_hours = __fdiv_rn(age_secs, 3600.0f);
+  float rate = decay_rate > 0.0f ? decay_rate : base_decay_rate;
+  // f32::exp: evaluated in double and rounded once (correctly rounded fp32 result).
+  float temporal_relevance = (float)exp((double)__fmul_rn(-rate, age_hours));
+  float geo = __fmul_rn(__fsub_rn(1.0f, w), __fdiv_rn(distance, 2.0f));
+  float tmp = __fmul_rn(w, __fsub_rn(1.0f, temporal_relevance));
+  return __fadd_rn(geo, tmp);
+}
+
+__global__ void __launch_bounds__(128) k_rerank(const uint32_t* __restrict__ pool_ids, const float* __restrict__ pool_dist,
+                                                uint32_t pool, uint32_t P, uint32_t k,
+                                                const unsigned long long* __restrict__ ts_secs,
+                                                const uint32_t* __restrict__ ts_nanos, const float* __restrict__ decay,
+                                                float w, float base, unsigned long long now_secs, uint32_t now_nanos,
+                                                uint32_t* __restrict__ out_ids, float* __restrict__ out_score,
+                                                float* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // P
+  const uint64_t qo = (uint64_t)blockIdx.x * pool;
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = kKeyMax;
+    if (i < pool) {
+      uint32_t id = pool_ids[qo + i];
+      if (id != CM_NO_ID_DEV) {
+        float sc = combined_score_dev(pool_dist[qo + i], ts_secs[id], ts_nanos[id], decay[id], now_secs, now_nanos, w, base);
+        // Stable sort by score: the pool rank breaks ties (pool is ascending (distance, handle)).
+        key = ((unsigned long long)total_key(sc) << 32) | i;
+      }
+    }
+    keys[i] = key;
+  }
+  block_bitonic_sort(keys, P);
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    unsigned long long key = i < P ? keys[i] : kKeyMax;
+    bool ok = key != kKeyMax;
+    uint32_t rank = (uint32_t)key;
+    uint64_t o = (uint64_t)blockIdx.x * k + i;
+    out_ids[o] = ok ? pool_ids[qo + rank] : CM_NO_ID_DEV;
+    out_score[o] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+    if (out_dist) out_dist[o] = ok ? pool_dist[qo + rank] : __int_as_float(0x7F800000);
+  }
+}
+
+cudaError_t launch_rerank(const uint32_t* pool_ids, const float* pool_dist, uint32_t nq, uint32_t pool, uint32_t k,
+                          const uint64_t* ts_secs, const uint32_t* ts_nanos, const float* decay, float w, float base,
+                          uint64_t now_secs, uint32_t now_nanos, uint32_t* out_ids, float* out_score,
+                          float* out_dist, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  uint32_t P = next_pow2(pool < 32 ? 32 : pool);
+  k_rerank<<<nq, 128, (size_t)P * 8, s>>>(pool_ids, pool_dist, pool, P, k, (const unsigned long long*)ts_secs, ts_nanos,
+                                          decay, w, base, now_secs, now_nanos, out_ids, out_score, out_dist);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace cm

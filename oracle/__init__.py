@@ -73,6 +73,9 @@ def lib():
     sig("orc_hnsw_top_layer", C.c_uint32, [vp, C.c_uint32])
     sig("orc_hnsw_neighbors", C.c_uint32, [vp, C.c_uint32, C.c_uint32, _u32p, C.c_uint32])
     sig("orc_hnsw_vector", None, [vp, C.c_uint32, _f32p])
+    sig("orc_hnsw_import", None,
+        [vp, _f32p, C.c_uint64, C.c_uint64, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint32, _u32p,
+         C.c_uint64, vp])
     sig("orc_hnsw_search", C.c_uint64, [vp, _f32p, C.c_uint64, C.c_uint64, _u32p, _f32p, C.c_uint64, vp])
     sig("orc_hnsw_search_batch", None,
         [vp, _f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _f32p, vp, C.c_int, vp])
@@ -211,6 +214,19 @@ class OracleHnsw:
         lib().orc_hnsw_vector(self._h, handle, out)
         return out
 
+    def import_graph(self, x_prepared, graph: dict, deleted=None):
+        """Adopt a graph read by `read_graph_sidecar` over already-preprocessed rows."""
+        x = _f32(x_prepared)
+        dptr = None
+        if deleted is not None:
+            deleted = np.ascontiguousarray(deleted, dtype=np.uint8)
+            dptr = deleted.ctypes.data_as(C.c_void_p)
+        g = graph
+        nbr_up = g["nbr_up"] if g["nbr_up"].size else np.zeros(1, np.uint32)
+        deg_up = g["deg_up"] if g["deg_up"].size else np.zeros(1, np.uint32)
+        lib().orc_hnsw_import(self._h, x, x.shape[0], x.shape[1], g["top_layer"], g["nbr0"], g["cap0"], g["deg0"],
+                              g["upper_base"], nbr_up, g["capU"], deg_up, g["entry"], dptr)
+
     def search(self, q, ef, counters=None):
         """VectorIndex::search -> list of (handle, distance), ascending."""
         q = _f32(q).ravel()
@@ -285,3 +301,22 @@ def sharded_merge(ids, dists, out_len):
     od = np.empty((nq, out_len), dtype=np.float32)
     lib().orc_sharded_merge(ids, dists, s, nq, ln, out_len, oi, od)
     return oi, od
+
+
+def read_graph_sidecar(path) -> dict:
+    """Parse the engine's graph sidecar ("CMGRAPH1", layout in chrono-mind_b200/csrc/api.cu) with numpy."""
+    with open(path, "rb") as f:
+        blob = f.read()
+    assert blob[:8] == b"CMGRAPH1"
+    n, = np.frombuffer(blob, np.uint64, 1, 8)
+    cap0, capU = np.frombuffer(blob, np.uint32, 2, 16)
+    entry, slots = np.frombuffer(blob, np.uint64, 2, 24)
+    n, cap0, capU, entry, slots = int(n), int(cap0), int(capU), int(entry), int(slots)
+    o = 40
+    out = {"n": n, "cap0": cap0, "capU": capU, "entry": entry}
+    for name, dt, cnt in (("top_layer", np.uint8, n), ("deg0", np.uint32, n), ("nbr0", np.uint32, n * cap0),
+                          ("upper_base", np.uint32, n), ("deg_up", np.uint32, slots),
+                          ("nbr_up", np.uint32, slots * capU)):
+        out[name] = np.frombuffer(blob, dt, cnt, o).copy()
+        o += cnt * np.dtype(dt).itemsize
+    return out

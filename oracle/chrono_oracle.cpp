@@ -588,6 +588,34 @@ void orc_hnsw_vector(void* h, uint32_t id, float* out) {
   std::memcpy(out, g->nodes[id].vector.data(), g->nodes[id].vector.size() * 4);
 }
 
+// Adopt an already-built graph (flat layout written by the engine's graph sidecar) so that the oracle's
+// search_layer/search run over exactly the graph the GPU searches ("same snapshot graph" parity):
+// rows are ALREADY preprocess()ed; nbr0[n][cap0]/deg0[n]; upper lists of node v (top_layer t >= 1) at slots
+// upper_base[v] .. upper_base[v]+t-1 of nbr_up[slot][capU]/deg_up[slot]. Replaces the index content.
+void orc_hnsw_import(void* h, const float* x, uint64_t n, uint64_t dim, const uint8_t* top_layer, const uint32_t* nbr0,
+                     uint32_t cap0, const uint32_t* deg0, const uint32_t* upper_base, const uint32_t* nbr_up,
+                     uint32_t capU, const uint32_t* deg_up, uint64_t entry, const uint8_t* deleted) {
+  Hnsw* g = (Hnsw*)h;
+  g->nodes.clear();
+  g->live = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    Node nd;
+    nd.vector.assign(x + i * dim, x + (i + 1) * dim);
+    nd.top_layer = top_layer[i];
+    nd.deleted = deleted && deleted[i];
+    nd.layers.resize(nd.top_layer + 1);
+    nd.layers[0].assign(nbr0 + i * cap0, nbr0 + i * cap0 + deg0[i]);
+    for (size_t l = 1; l <= nd.top_layer; ++l) {
+      uint64_t slot = (uint64_t)upper_base[i] + l - 1;
+      nd.layers[l].assign(nbr_up + slot * capU, nbr_up + slot * capU + deg_up[slot]);
+    }
+    if (!nd.deleted) g->live++;
+    g->nodes.push_back(std::move(nd));
+  }
+  g->entry = entry;
+  g->layer_ticket = n;
+}
+
 // VectorIndex::search (src/index/mod.rs:70-72). Writes up to `cap` pairs;
 // returns the number of results. counters (optional): [dist_evals, expansions, list_entries].
 uint64_t orc_hnsw_search(void* h, const float* q, uint64_t len, uint64_t ef, uint32_t* ids, float* dists,

@@ -1,0 +1,206 @@
+"""CPU-side tests of the product's host runtime (no GPU compute): ABI surface, snapshot reader, graph builder
+against the oracle, sidecar round trip, and "no CPU fallback" behaviour."""
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import snapshot_codec as sc
+import chronomind_b200 as cb
+from chronomind_b200 import datasets
+from chronomind_b200.engine import ABI, ChronoMindB200, CmError, default_config, native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "chronomind_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = native()
+    for name in declared:
+        assert hasattr(L, name), "library does not export %s" % name
+    assert declared == set(ABI), "engine.py's ABI table and the header disagree: %s" % (declared ^ set(ABI))
+
+
+def test_default_config_matches_reference():            # src/config.rs:73-85,27-35
+    c = default_config()
+    assert (c.dimensions, c.max_memories, c.max_relationships) == (768, 100_000, 50)
+    assert (c.index.max_connections, c.index.ef_construction, c.index.ef_search) == (16, 200, 50)
+    assert abs(c.base_decay_rate - 0.1) < 1e-7 and abs(c.temporal_weight - 0.3) < 1e-7
+    assert native().cm_metric_name() == b"cosine"       # src/metric.rs:201-203
+
+
+def test_config_validation_errors():                    # src/config.rs:97-143
+    x = np.zeros((4, 8), np.float32)
+    for kw in ({"max_connections": 1}, {"ef_construction": 4}, {"ef_search": 0}, {"temporal_weight": 1.5},
+               {"base_decay_rate": 0.0}, {"max_memories": 0}, {"similarity_threshold": 1.0}):
+        with pytest.raises(CmError) as e:
+            ChronoMindB200.from_matrix(x, default_config(**kw))
+        assert e.value.kind == "Config"
+
+
+def test_rows_are_preprocessed_like_the_reference():    # src/metric.rs:208-214
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-50, 50, (37, 13)).astype(np.float32)
+    x[5] = 0.0
+    st = ChronoMindB200.from_matrix(x, default_config(dimensions=13))
+    want = oracle.preprocess_rows(x)
+    got = np.stack([st.vector(i) for i in range(37)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert len(st) == 37 and st.slots == 37 and st.dim == 13
+
+
+def test_search_without_upload_fails_loudly():
+    st = ChronoMindB200.from_matrix(np.eye(4, dtype=np.float32), default_config(dimensions=4))
+    with pytest.raises(CmError) as e:
+        st.search_exact(np.ones((1, 4), np.float32), 1)
+    assert e.value.kind == "Cuda"                       # no CPU path behind the ABI
+
+
+def _graphs_equal(st, orc, n):
+    assert st.entry() == orc.entry()
+    for i in range(n):
+        t = st.top_layer(i)
+        assert t == orc.top_layer(i)
+        for l in range(t + 1):
+            assert np.array_equal(st.neighbors(i, l), orc.neighbors(i, l)), (i, l)
+
+
+@pytest.mark.parametrize("n,dim,M,efc,seed", [(600, 32, 16, 200, 0xC0FFEE), (400, 6, 4, 16, 7), (300, 768, 16, 100, 5),
+                                              (250, 11, 8, 32, 99)])
+def test_single_thread_build_equals_oracle_graph(n, dim, M, efc, seed):
+    """threads == 1 must reproduce `LockFreeHnsw::insert`'s deterministic graph (lockfree_hnsw.rs:555-573)."""
+    rng = np.random.default_rng(seed)
+    x = datasets.unit_vectors(rng, n, dim)
+    cfg = default_config(dimensions=dim, max_connections=M, ef_construction=efc)
+    st = ChronoMindB200.from_matrix(x, cfg).build_graph(seed, threads=1)
+    assert st.check_invariants() == 0
+    orc = oracle.OracleHnsw(M, efc, 50, seed)
+    orc.insert_matrix(x)
+    _graphs_equal(st, orc, n)
+
+
+def test_multi_thread_build_is_sound_and_searchable(tmp_path):
+    """Concurrent build: invariants hold and the oracle's CPU search over THAT graph meets the recall gate
+    (stress_test.rs:41-175 semantics: invariants + recall >= 0.90 at ef = 100)."""
+    data, queries = datasets.embedding_dataset(3000, 50, 0xBEEF, dim=64, intrinsic=8)
+    cfg = default_config(dimensions=64, ef_construction=100)
+    st = ChronoMindB200.from_matrix(data, cfg).build_graph(11, threads=4)
+    assert st.check_invariants() == 0
+    p = str(tmp_path / "g.cmgraph")
+    st.save_graph(p)
+    g = oracle.read_graph_sidecar(p)
+    orc = oracle.OracleHnsw(16, 100, 50, 11)
+    orc.import_graph(oracle.preprocess_rows(data), g)
+    assert orc.check_invariants() == 0
+    got, _, _, _ = orc.search_batch(queries, 100, 10)
+    exp, _ = oracle.brute_force(data, queries, 10, mode="distance")
+    rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(got, exp)])
+    assert rec >= 0.90
+    # sidecar round trip
+    st2 = ChronoMindB200.from_matrix(data, cfg).load_graph(p)
+    assert st2.entry() == st.entry()
+    for i in (0, 17, 2999):
+        assert np.array_equal(st2.neighbors(i, 0), st.neighbors(i, 0))
+    with pytest.raises(CmError):
+        ChronoMindB200.from_matrix(data[:100], cfg).load_graph(p)     # wrong index
+
+
+def _sample_memories(n=20, dim=4):
+    return [sc.Memory(id="m%d" % i, data=[float(i), i + 1.0, i + 2.0, i + 3.0][:dim], ts_secs=1_700_000_000 + i,
+                      ts_nanos=5 * i, importance=i / 20.0, context="even" if i % 2 == 0 else "odd",
+                      decay_rate=0.05 * (i % 3), relationships=["m0"] if i % 4 == 0 else [],
+                      last_access_secs=1_700_000_100 + i) for i in range(n)]
+
+
+def test_snapshot_reader_matches_codec(tmp_path):       # src/persistence.rs:73-123
+    cfg = sc.Config(dimensions=4, temporal_weight=0.5)
+    mems = _sample_memories()
+    p = str(tmp_path / "s.chrono")
+    sc.write_snapshot(p, cfg, mems)
+    st = ChronoMindB200.from_snapshot(p)
+    assert st.slots == 20 and len(st) == 20 and st.dim == 4
+    c = st.config
+    assert c.dimensions == 4 and abs(c.temporal_weight - 0.5) < 1e-7 and c.index.ef_construction == 200
+    for i, m in enumerate(mems):
+        assert st.external_id(i) == m.id
+        assert np.array_equal(st.vector(i), oracle.preprocess(m.data))
+
+
+def test_snapshot_duplicate_id_tombstones_older_handle(tmp_path):   # src/store.rs:252-262
+    mems = _sample_memories(6)
+    mems.append(sc.Memory(id="m2", data=[9.0, 9.0, 9.0, 1.0]))
+    p = str(tmp_path / "dup.chrono")
+    sc.write_snapshot(p, sc.Config(dimensions=4), mems)
+    st = ChronoMindB200.from_snapshot(p)
+    assert st.slots == 7 and len(st) == 6
+    assert not st.remove(2)                              # already tombstoned by the replacement
+    assert st.remove(6) and not st.remove(6)
+
+
+def test_snapshot_errors_map_to_reference_variants(tmp_path):       # tests/persistence_test.rs:59-150
+    def load(b):
+        p = str(tmp_path / "x.bin")
+        open(p, "wb").write(b)
+        return ChronoMindB200.from_snapshot(p)
+    good = sc.encode_snapshot(sc.Config(dimensions=4), _sample_memories())
+    for blob, kind, needle in ((b"definitely not a chronomind snapshot", "InvalidSnapshot", "magic"),
+                               (b"CHR", "InvalidSnapshot", "short"),
+                               (b"CHRONO1" + bytes([99]), "InvalidSnapshot", "99")):
+        with pytest.raises(CmError) as e:
+            load(blob)
+        assert e.value.kind == kind and needle in str(e.value)
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0xFF
+    with pytest.raises(CmError) as e:
+        load(bytes(bad))
+    assert e.value.kind == "InvalidSnapshot" and "checksum" in str(e.value)
+    with pytest.raises(CmError) as e:
+        ChronoMindB200.from_snapshot(str(tmp_path / "does_not_exist.chrono"))
+    assert e.value.kind == "Io"
+    # truncated body with a fixed-up CRC -> Serialization (bincode error)
+    body = good[12:-9]
+    import zlib
+    with pytest.raises(CmError) as e:
+        load(good[:8] + struct.pack("<I", zlib.crc32(body)) + body)
+    assert e.value.kind == "Serialization"
+    # Config::validate / Memory::validate on load
+    with pytest.raises(CmError) as e:
+        load(sc.encode_snapshot(sc.Config(dimensions=4, temporal_weight=2.0), _sample_memories()))
+    assert e.value.kind == "Config"
+    with pytest.raises(CmError) as e:
+        load(sc.encode_snapshot(sc.Config(dimensions=5), _sample_memories()))
+    assert e.value.kind == "InvalidDimensions"
+    m = _sample_memories()
+    m[3].data[1] = float("nan")
+    with pytest.raises(CmError) as e:
+        load(sc.encode_snapshot(sc.Config(dimensions=4), m))
+    assert e.value.kind == "InvalidVector"
+    m = _sample_memories()
+    m[3].importance = 1.5
+    with pytest.raises(CmError) as e:
+        load(sc.encode_snapshot(sc.Config(dimensions=4), m))
+    assert e.value.kind == "InvalidImportance"
+    with pytest.raises(CmError) as e:
+        load(sc.encode_snapshot(sc.Config(dimensions=4, max_memories=5), _sample_memories()))
+    assert e.value.kind == "CapacityExceeded"
+
+
+def test_snapshot_empty_store(tmp_path):
+    p = str(tmp_path / "e.chrono")
+    sc.write_snapshot(p, sc.Config(dimensions=3), [])
+    st = ChronoMindB200.from_snapshot(p)
+    assert st.slots == 0 and len(st) == 0
+
+
+def test_attr_validation():
+    st = ChronoMindB200.from_matrix(np.eye(3, dtype=np.float32), default_config(dimensions=3))
+    with pytest.raises(CmError):
+        st.set_attrs(decay_rate=np.array([0.1, -1.0, 0.0], np.float32))    # src/types.rs:112-118
+    st.set_attrs(deleted=np.array([0, 1, 0], np.uint8))
+    assert len(st) == 2 and st.slots == 3
