@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of the batched exact search (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload exact|hnsw]
+
+One "step" = one pass of the hot path over one 10,000-query batch against the 1,000,000 x 768 cosine corpus
+(k = 10, recall@10 = 1.0 by construction: the scan is exact). N > 1 (launched under torchrun, one rank per GPU)
+shards the corpus by vector id (global = local * N + rank, src/index/sharded_rwlock.rs:54-66), every rank scans
+its shard for the whole batch, the per-shard top-k lists are all-gathered over NCCL and merged on the device
+("scaling": "strong": the corpus is fixed, per-GPU work shrinks with N).
+
+`--impl reference` times the reference algorithm's CPU form of the same path (the oracle's brute-force scan —
+the Rust crate cannot be built in this image) on the host cores, on a bounded query sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS = 1_000_000
+DIM = 768
+N_QUERIES = 10_000
+K = 10
+SEED = 0x5EED
+QUERY_BATCHES = 4          # distinct query batches rotated through the steps
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_data(n_rows, n_queries_total):
+    from chronomind_b200 import datasets
+    t0 = time.time()
+    rng = np.random.default_rng(SEED)
+    basis = datasets.unit_vectors(rng, 16, DIM)
+    corpus = datasets.embedding_rows(rng, basis, n_rows)
+    queries = datasets.embedding_rows(np.random.default_rng(SEED ^ 0xFACE), basis, n_queries_total)
+    log("[bench] synthetic embedding-like data: corpus %s queries %s in %.1fs" % (corpus.shape, queries.shape, time.time() - t0))
+    return corpus, queries
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+def cpu_reference(corpus_prepared, queries, threads, sample_queries, steps=1, warmup=0):
+    """The reference algorithm's CPU scan (oracle brute force, tests/property_test.rs:201-206 arithmetic) on a bounded
+    query sample with all host threads; queries split statically (benches/comparison.rs:125-139). Returns
+    (qps, seconds per sample)."""
+    import oracle
+    q = np.ascontiguousarray(queries[:sample_queries])
+    for _ in range(warmup):
+        oracle.brute_force(corpus_prepared, q, K, mode="prepared", threads=threads)
+    best = None
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        oracle.brute_force(corpus_prepared, q, K, mode="prepared", threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)          # best_qps, benches/external.rs:118-124
+    return sample_queries / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    threads = os.cpu_count() or 1
+    n_rows, nq = args.rows, args.queries
+    corpus, queries = make_data(n_rows, nq)
+    t0 = time.time()
+    prepared = _preprocess_mt(corpus, threads)      # the index stores preprocess()ed rows
+    log("[bench] reference: preprocess %.1fs" % (time.time() - t0))
+    sample = min(args.cpu_sample or 2 * threads, nq)
+    t_all = []
+    for _ in range(args.warmup):
+        cpu_reference(prepared, queries, threads, sample)
+    for s in range(args.steps):
+        q = queries[(s * sample) % max(1, nq - sample):][:sample]
+        t0 = time.perf_counter()
+        oracle.brute_force(prepared, np.ascontiguousarray(q), K, mode="prepared", threads=threads)
+        t_all.append(time.perf_counter() - t0)
+    total = sum(t_all)
+    qps = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": qps,
+        "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "exact brute-force kNN %dx%d cosine, %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, nq, K),
+                   "recall_at_10": 1.0, "engine": "CPU scan of the reference algorithm (oracle port, AVX2+FMA)"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "%d queries per step x %d steps against the full %d x %d corpus" % (sample, args.steps, n_rows, DIM)},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _preprocess_mt(corpus, threads):
+    import oracle
+    return oracle.preprocess_rows(corpus, threads=threads)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="corpus rows (default: the metric's 1,000,000)")
+    ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 fp32 CUDA-core scan, 2 tcgen05 scan + rescore")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0: 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from chronomind_b200 import engine
+    from chronomind_b200.engine import ChronoMindB200, default_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    n_rows, nq = args.rows, args.queries
+    corpus, queries_all = make_data(n_rows, nq * QUERY_BATCHES)
+    shard = np.ascontiguousarray(corpus[rank::world]) if world > 1 else corpus
+    t0 = time.time()
+    st = ChronoMindB200.from_matrix(shard, default_config(dimensions=DIM)).set_shard(rank, world).upload(local_rank)
+    st.set_exact_engine(args.engine)
+    log("[bench] rank %d: index of %d rows resident on cuda:%d in %.1fs" % (rank, len(st), local_rank, time.time() - t0))
+
+    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(QUERY_BATCHES)]
+    q_dev = [q.to(dev) for q in q_host]
+    ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    if world > 1:
+        ids_g = torch.empty((world, nq, K), dtype=torch.int32, device=dev)
+        dist_g = torch.empty((world, nq, K), dtype=torch.float32, device=dev)
+    out_ids_host = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    out_dist_host = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+
+    def step_device(i):
+        """Inputs resident in HBM; result stays on the device."""
+        st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_l, dist_l)
+        if world > 1:
+            dist.all_gather_into_tensor(ids_g, ids_l)
+            dist.all_gather_into_tensor(dist_g, dist_l)
+            return engine.merge_topk_cuda(ids_g, dist_g, K)
+        return ids_l, dist_l
+
+    def step_e2e(i):
+        """Public API with HOST buffers: H2D of the query batch and D2H of the result inside the step."""
+        if world == 1:
+            return st.search_exact(q_host[i % QUERY_BATCHES].numpy(), K)
+        qd = q_host[i % QUERY_BATCHES].to(dev, non_blocking=True)
+        st.search_exact_cuda(qd, K, ids_l, dist_l)
+        dist.all_gather_into_tensor(ids_g, ids_l)
+        dist.all_gather_into_tensor(dist_g, dist_l)
+        mi, md = engine.merge_topk_cuda(ids_g, dist_g, K)
+        out_ids_host.copy_(mi, non_blocking=True)
+        out_dist_host.copy_(md, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_ids_host, out_dist_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    engine.profile_enable(True)
+    engine.profile_read()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        res = step_device(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = engine.launch_count() - launches0
+    kernel_ms, kernel_n = engine.profile_read()
+    engine.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- end-to-end through the host-buffer API -----------------------------------------------------------------
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = step_e2e(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        counters = engine.last_counters()
+        tc = bool(counters.get("rescored", 0)) or args.engine == 2
+        flops_per_launch = 2.0 * nq * (n_rows / world) * DIM * args.steps / max(kernel_n, 1)
+        kern_avg_ms = kernel_ms / max(kernel_n, 1)
+        achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
+                    "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback of B200_PROFILING.md"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            import oracle
+            threads = os.cpu_count() or 1
+            sample = args.cpu_sample or 2 * threads
+            t0 = time.time()
+            prepared = _preprocess_mt(corpus, threads)
+            qps, secs = cpu_reference(prepared, queries_all, threads, sample, steps=2)
+            # parity spot check on the sample while we have both sides
+            wi, wd = oracle.brute_force(prepared, queries_all[:sample], K, mode="prepared", threads=threads)
+            gi, gd = st.search_exact(queries_all[:sample], K) if world == 1 else (None, None)
+            parity = None if gi is None else bool(np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)))
+            cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                   "sample": "%d of the %d queries against the full %dx%d corpus, best of 2 passes (%.1fs each)"
+                             % (sample, nq, n_rows, DIM, secs), "parity_on_sample": parity}
+            log("[bench] cpu baseline in %.1fs" % (time.time() - t0))
+        line = {
+            "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": nq * args.steps / (ms * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if tc else "f32", "data": "synthetic",
+            "config": {"workload": "exact brute-force kNN %dx%d cosine, %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, nq, K),
+                       "recall_at_10": 1.0, "engine": "tcgen05 bf16 scan + fp32 rescore" if tc else "fp32 CUDA-core scan",
+                       "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
+                       "l2": "inputs larger than L2: %.2f GB corpus streamed per step; %d query batches rotated" % (n_rows * DIM * 4 / 1e9, QUERY_BATCHES)},
+            "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4,
+                    "d2h_bytes_per_step": nq * K * 8},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

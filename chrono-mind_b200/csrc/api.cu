@@ -38,6 +38,29 @@ static cm_status cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// ---- roofline instrumentation (cm_profile_*) ---------------------------------------------------------------
+static std::atomic<int> g_profile{0};
+static std::mutex g_profile_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
+struct ProfileScope {  // brackets one dominant-kernel launch with events on its stream
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  explicit ProfileScope(cudaStream_t stream) : s(stream) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+      a = b = nullptr;
+      return;
+    }
+    cudaEventRecord(a, s);
+  }
+  ~ProfileScope() {
+    if (!a) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> g(g_profile_mu);
+    g_profile_events.emplace_back(a, b);
+  }
+};
+
 // ---- device buffers ----------------------------------------------------------------------------------------
 struct DevBuf {
   void* p = nullptr;
@@ -190,8 +213,10 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
     uint32_t nb = std::min<uint32_t>((uint32_t)qb, nq - q0);
     if (pq.degenerate)
       CM_CUDA(launch_fill(D, (uint64_t)nb * ldD, 2.0f, s));
-    else
+    else {
+      ProfileScope prof(s);
       CM_CUDA(launch_exact_dist(pq.qn + (size_t)q0 * pq.ld, nb, pq.ld, d.x32, d.n, d.dim, d.dim_pad, D, ldD, s));
+    }
     CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, d.deleted, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, k, s));
   }
   tl_counters.dist_evals += (uint64_t)nq * d.n;
@@ -232,7 +257,10 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   l.gtable = ws->gtable.as<uint32_t>();
   l.ghash_bits = kGHashBits;
   l.grid = grid;
-  CM_CUDA(launch_hnsw_search(d, l, s));
+  {
+    ProfileScope prof(s);
+    CM_CUDA(launch_hnsw_search(d, l, s));
+  }
   return CM_OK;
 }
 
@@ -328,6 +356,29 @@ uint64_t cm_launch_count(void) { return g_launches.load(); }
 cm_status cm_last_counters(cm_counters* out) {
   if (!out) return fail(CM_ERR_INVALID_ARGUMENT, "null out");
   *out = tl_counters;
+  return CM_OK;
+}
+
+cm_status cm_profile_enable(int on) {
+  g_profile.store(on ? 1 : 0);
+  return CM_OK;
+}
+cm_status cm_profile_read(float* kernel_ms, uint32_t* kernel_launches) {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+  {
+    std::lock_guard<std::mutex> g(g_profile_mu);
+    evs.swap(g_profile_events);
+  }
+  float total = 0.0f;
+  for (auto& e : evs) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess)
+      total += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  if (kernel_ms) *kernel_ms = total;
+  if (kernel_launches) *kernel_launches = (uint32_t)evs.size();
   return CM_OK;
 }
 

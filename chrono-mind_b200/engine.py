@@ -89,6 +89,8 @@ ABI = {
     "cm_metric_name": (C.c_char_p, []),
     "cm_set_exact_engine": (_i, [_vp, _i]),
     "cm_last_counters": (_i, [C.POINTER(Counters)]),
+    "cm_profile_enable": (_i, [_i]),
+    "cm_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(_u32)]),
     "cm_launch_count": (_u64, []),
     "cm_last_error": (C.c_char_p, []),
     "cm_version": (C.c_char_p, []),
@@ -124,6 +126,17 @@ def last_counters() -> dict:
     c = Counters()
     native().cm_last_counters(C.byref(c))
     return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+
+def profile_enable(on: bool):
+    native().cm_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """(summed device ms of the bracketed dominant-kernel launches, their count) since the last read."""
+    ms, n = C.c_float(0), C.c_uint32(0)
+    native().cm_profile_read(C.byref(ms), C.byref(n))
+    return float(ms.value), int(n.value)
 
 
 def launch_count() -> int:

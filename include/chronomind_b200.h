@@ -209,6 +209,11 @@ const char* cm_metric_name(void);
  * CUDA-core scan, 2 = force the tcgen05 scan + fp32 rescore. */
 cm_status cm_set_exact_engine(cm_index* idx, int engine);
 cm_status cm_last_counters(cm_counters* out); /* thread-local */
+/* Roofline instrumentation: when enabled, the search calls bracket their dominant kernel (the scan for the exact
+ * path, the traversal for the HNSW path) with CUDA events on the launching stream. cm_profile_read waits for
+ * the recorded events, returns their summed device time and count since the last read, and clears them. */
+cm_status cm_profile_enable(int on);
+cm_status cm_profile_read(float* kernel_ms, uint32_t* kernel_launches);
 uint64_t cm_launch_count(void);               /* process-wide count of kernels launched by this library */
 const char* cm_last_error(void);              /* thread-local message of the last failing call */
 const char* cm_version(void);

@@ -53,6 +53,7 @@ def lib():
     sig("orc_dot_scalar", C.c_float, [_f32p, _f32p, C.c_uint64])
     sig("orc_dot_avx2", C.c_float, [_f32p, _f32p, C.c_uint64])
     sig("orc_preprocess", None, [_f32p, C.c_uint64, _f32p])
+    sig("orc_preprocess_rows", None, [_f32p, C.c_uint64, C.c_uint64, _f32p, C.c_int])
     sig("orc_distance_prepared", C.c_float, [_f32p, C.c_uint64, _f32p, C.c_uint64])
     sig("orc_distance", C.c_float, [_f32p, C.c_uint64, _f32p, C.c_uint64])
     sig("orc_distance_scalar", C.c_float, [_f32p, C.c_uint64, _f32p, C.c_uint64])
@@ -107,12 +108,11 @@ def preprocess(v) -> np.ndarray:
     return out
 
 
-def preprocess_rows(x) -> np.ndarray:
+def preprocess_rows(x, threads=1) -> np.ndarray:
     x = _f32(x)
     out = np.empty_like(x)
-    L = lib()
-    for i in range(x.shape[0]):
-        L.orc_preprocess(x[i], x.shape[1], out[i])
+    if x.shape[0]:
+        lib().orc_preprocess_rows(x, x.shape[0], x.shape[1], out, threads)
     return out
 
 

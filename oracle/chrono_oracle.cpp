@@ -526,6 +526,10 @@ uint32_t orc_total_key(float f) { return total_key(f); }
 float orc_dot_scalar(const float* a, const float* b, uint64_t n) { return dot_scalar(a, b, n); }
 float orc_dot_avx2(const float* a, const float* b, uint64_t n) { return dot_avx2(a, b, n); }
 void orc_preprocess(const float* v, uint64_t n, float* out) { preprocess(v, n, out); }
+// preprocess() for every row of a row-major matrix (rows are independent; `threads` splits them statically).
+void orc_preprocess_rows(const float* x, uint64_t n, uint64_t dim, float* out, int threads) {
+  parallel_for(n, threads, [&](size_t i) { preprocess(x + i * dim, dim, out + i * dim); });
+}
 float orc_distance_prepared(const float* a, uint64_t na, const float* b, uint64_t nb) {
   return distance_prepared(a, na, b, nb);
 }

