@@ -11,12 +11,14 @@
 
 #include "cm_internal.h"
 #include "kernels.h"
+#include "scan_tc.h"
 
 namespace cm {
 
 // ---- errors / counters -----------------------------------------------------------------------------------
 static thread_local std::string tl_error;
 static thread_local cm_counters tl_counters;
+static thread_local bool tl_used_tc = false;  // the last exact search on this thread ran the tensor-core scan
 static std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string& msg) { tl_error = msg; }
@@ -45,8 +47,8 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
 struct ProfileScope {  // brackets one dominant-kernel launch with events on its stream
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t s;
-  explicit ProfileScope(cudaStream_t stream) : s(stream) {
-    if (!g_profile.load(std::memory_order_relaxed)) return;
+  explicit ProfileScope(cudaStream_t stream, bool enabled = true) : s(stream) {
+    if (!enabled || !g_profile.load(std::memory_order_relaxed)) return;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
       a = b = nullptr;
       return;
@@ -91,10 +93,13 @@ struct DevBuf {
 // Scratch for one in-flight search call. Calls on different host threads take different workspaces.
 struct Workspace {
   DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable;
+  DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
   cudaStream_t stream = nullptr;  // host-buffer variants
   unsigned hnsw_grid = 0;
   void release() {
-    for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable}) b->release();
+    for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qbf16,
+                      &tc_state, &cand, &qflag})
+      b->release();
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -136,6 +141,11 @@ struct WorkspaceLease {
 
 constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited table: 128 Ki entries
 constexpr size_t kDistWorkspaceBytes = 1ull << 30;  // fp32 scan: distance block [QB][n] floats
+constexpr uint32_t kCandCap = 2048;            // tensor-core scan: candidate slots per query
+constexpr uint32_t kFlagCap = 64;              // queries per call the in-stream fp32 fallback can absorb
+// ws->small layout (bytes): 0 HNSW counters (8 x u64) | 64 rescored_total u64 | 72 flag_count u32 |
+// 128 work_counter u32 | 192 bad_row u32 | 256 flag_list (kFlagCap x u32)
+constexpr size_t kSmallBytes = 256 + kFlagCap * 4;
 
 static void free_device(DeviceIndex& d) {
   if (d.device < 0) return;
@@ -193,6 +203,83 @@ static cm_status prepare_queries(const cm_index* idx, Workspace* ws, const float
   return CM_OK;
 }
 
+// fp32 CUDA-core scan in query blocks: D[QB][n] then select. qmap/active_count route the fallback of the
+// tensor-core scan (only the first *active_count rows of q are live; results land in row qmap[i]).
+static cm_status exact_topk_fp32(const cm_index* idx, Workspace* ws, const float* qn, uint32_t ldq, bool degenerate,
+                                 uint32_t nq, uint32_t k, uint32_t* ids, float* dist, const uint32_t* qmap,
+                                 const uint32_t* active_count, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  uint64_t ldD = (d.n + 3) & ~3ull;
+  uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
+  qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
+  if (qmap) qb = ((uint64_t)nq + 15) & ~15ull;  // the fallback runs as one block
+  CM_CUDA(ws->D.ensure(qb * ldD * sizeof(float)));
+  float* D = ws->D.as<float>();
+  for (uint32_t q0 = 0; q0 < nq; q0 += (uint32_t)qb) {
+    uint32_t nb = std::min<uint32_t>((uint32_t)qb, nq - q0);
+    if (degenerate) {
+      CM_CUDA(launch_fill(D, (uint64_t)nb * ldD, 2.0f, s));
+    } else {
+      ProfileScope prof(qmap ? nullptr : s, qmap == nullptr);
+      CM_CUDA(launch_exact_dist(qn + (size_t)q0 * ldq, nb, ldq, d.x32, d.n, d.dim, d.dim_pad, D, ldD, active_count, s));
+    }
+    CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, d.deleted, k, qmap ? ids : ids + (size_t)q0 * k,
+                                    qmap ? dist : dist + (size_t)q0 * k, k, qmap, active_count, s));
+  }
+  return CM_OK;
+}
+
+// tcgen05 bf16 scan + exact fp32 rescore (+ in-stream fp32 fallback for flagged queries). See scan_tc.cu.
+static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
+                               uint32_t* ids, float* dist, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  const uint32_t nq_pad = scan_tc_pad_queries(nq);
+  tl_used_tc = true;
+  CM_CUDA(ws->qbf16.ensure((size_t)nq_pad * d.k_pad * 2));
+  CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
+  CM_CUDA(ws->cand.ensure((size_t)nq_pad * kCandCap * 8));
+  CM_CUDA(ws->small.ensure(kSmallBytes));
+  CM_CUDA(ws->qflag.ensure((size_t)kFlagCap * d.dim_pad * 4));
+  uint32_t* tau_key = ws->tc_state.as<uint32_t>();
+  uint32_t* cand_cnt = tau_key + nq_pad;
+  uint8_t* small = ws->small.as<uint8_t>();
+  CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
+  CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));
+  CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, s));
+  ScanTcLaunch sl;
+  sl.q_bf16 = ws->qbf16.p;
+  sl.nq = nq;
+  sl.k = k;
+  sl.tau_key = tau_key;
+  sl.cand_cnt = cand_cnt;
+  sl.cand = ws->cand.as<unsigned long long>();
+  sl.cap = kCandCap;
+  {
+    ProfileScope prof(s);
+    CM_CUDA(launch_scan_tc(d, sl, s));
+  }
+  RescoreLaunch rl;
+  rl.qn = pq.qn;
+  rl.ldq = pq.ld;
+  rl.nq = nq;
+  rl.k = k;
+  rl.tau_key = tau_key;
+  rl.cand_cnt = cand_cnt;
+  rl.cand = sl.cand;
+  rl.cap = kCandCap;
+  rl.ids = ids;
+  rl.dist = dist;
+  rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
+  rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
+  rl.flag_list = reinterpret_cast<uint32_t*>(small + 256);
+  rl.flag_cap = kFlagCap;
+  CM_CUDA(launch_rescore(d, rl, s));
+  // Flagged queries (candidate overflow / too few survivors): exact fp32 scan, in stream, no host round trip.
+  CM_CUDA(launch_gather_rows(pq.qn, pq.ld, rl.flag_list, rl.flag_count, kFlagCap, ws->qflag.as<float>(), s));
+  return exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
+                         rl.flag_count, s);
+}
+
 // Exact top-`k` by (distance, handle) into ids/dist [nq][k] (device).
 static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
                             uint32_t* ids, float* dist, cudaStream_t s) {
@@ -203,24 +290,13 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
     CM_CUDA(launch_fill(dist, (uint64_t)nq * k, INFINITY, s));
     return CM_OK;
   }
-  // fp32 CUDA-core scan in query blocks: D[QB][n] then select.
-  uint64_t ldD = (d.n + 3) & ~3ull;
-  uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
-  qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
-  CM_CUDA(ws->D.ensure(qb * ldD * sizeof(float)));
-  float* D = ws->D.as<float>();
-  for (uint32_t q0 = 0; q0 < nq; q0 += (uint32_t)qb) {
-    uint32_t nb = std::min<uint32_t>((uint32_t)qb, nq - q0);
-    if (pq.degenerate)
-      CM_CUDA(launch_fill(D, (uint64_t)nb * ldD, 2.0f, s));
-    else {
-      ProfileScope prof(s);
-      CM_CUDA(launch_exact_dist(pq.qn + (size_t)q0 * pq.ld, nb, pq.ld, d.x32, d.n, d.dim, d.dim_pad, D, ldD, s));
-    }
-    CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, d.deleted, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, k, s));
-  }
   tl_counters.dist_evals += (uint64_t)nq * d.n;
-  return CM_OK;
+  bool tc_ok = !pq.degenerate && scan_tc_supported(d, k);
+  bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && nq >= 64 && d.n >= 8192);
+  if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
+    return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 64 and a bf16 copy of the corpus");
+  if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s);
+  return exact_topk_fp32(idx, ws, pq.qn, pq.ld, pq.degenerate, nq, k, ids, dist, nullptr, nullptr, s);
 }
 
 // HNSW candidate pool [nq][ef] (tombstones filtered, ascending) into ws->pool_*.
@@ -240,7 +316,7 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   unsigned grid = 0;
   cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid);
   if (ge != cudaSuccess) return fail(CM_ERR_INVALID_ARGUMENT, "ef / dim too large for the HNSW kernel's shared memory");
-  CM_CUDA(ws->small.ensure(256));
+  CM_CUDA(ws->small.ensure(kSmallBytes));
   CM_CUDA(ws->gtable.ensure(((size_t)grid << kGHashBits) * 4));
   CM_CUDA(cudaMemsetAsync(ws->small.p, 0, 160, s));  // counters + work counter (bad_row at 192 is the caller's)
   HnswLaunch l;
@@ -328,6 +404,16 @@ static cm_status search_temporal_dev_impl(const cm_index* idx, Workspace* ws, co
   CM_CUDA(launch_rerank(ws->pool_ids.as<uint32_t>(), ws->pool_dist.as<float>(), nq, ef, k, d.ts_secs, d.ts_nanos,
                         d.decay, w, base, now_secs, now_nanos, ids, score, dist, s));
   return CM_OK;
+}
+
+static void fetch_scan_counters(Workspace* ws) {
+  if (!ws->small.p) return;
+  unsigned long long r = 0;
+  uint32_t f = 0;
+  if (cudaMemcpy(&r, ws->small.as<uint8_t>() + 64, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (cudaMemcpy(&f, ws->small.as<uint8_t>() + 72, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  tl_counters.rescored += r;
+  tl_counters.fallback_queries += f;
 }
 
 static void fetch_hnsw_counters(Workspace* ws) {
@@ -552,6 +638,11 @@ cm_status cm_index_upload(cm_index* idx, int device) {
     CM_CUDA(cudaMemcpy2D(d.x32, (size_t)d.dim_pad * 4, idx->x.data(), (size_t)d.dim * 4, (size_t)d.dim * 4, n,
                          cudaMemcpyHostToDevice));
   }
+  // bf16 copy for the tensor-core scan, padded to whole tiles (zero rows/columns score 0 and are masked by id).
+  d.n_pad = scan_tc_pad_rows(std::max<uint64_t>(n, 1));
+  d.k_pad = scan_tc_pad_k(d.dim);
+  CM_CUDA(cudaMalloc(&d.xbf16, d.n_pad * d.k_pad * 2));
+  CM_CUDA(launch_to_bf16(d.x32, n, d.dim, d.dim_pad, d.xbf16, d.n_pad, d.k_pad, nullptr));
   CM_CUDA(cudaMalloc(&d.deleted, rows));
   CM_CUDA(cudaMalloc(&d.ts_secs, rows * 8));
   CM_CUDA(cudaMalloc(&d.ts_nanos, rows * 4));
@@ -822,6 +913,7 @@ cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint
   WorkspaceLease lease(idx);
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
+  tl_used_tc = false;
   st = search_exact_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, hc.ids_dev, hc.a_dev, hc.s);
   if (st != CM_OK) return st;
   size_t ob = (size_t)nq * k * 4;
@@ -830,6 +922,20 @@ cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint
     CM_CUDA(cudaMemcpyAsync(dist, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
   }
   CM_CUDA(cudaStreamSynchronize(hc.s));
+  if (tl_used_tc) {
+    fetch_scan_counters(lease.ws);
+    if (tl_counters.fallback_queries > kFlagCap) {
+      // More queries needed the fp32 fallback than the in-stream path absorbs: redo the batch on the fp32 engine.
+      PreparedQueries pq;
+      pq.qn = lease.ws->qn.as<float>();
+      pq.ld = idx->dev.dim_pad;
+      st = exact_topk_fp32(idx, lease.ws, pq.qn, pq.ld, false, nq, k, hc.ids_dev, hc.a_dev, nullptr, nullptr, hc.s);
+      if (st != CM_OK) return st;
+      CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+      CM_CUDA(cudaMemcpyAsync(dist, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+      CM_CUDA(cudaStreamSynchronize(hc.s));
+    }
+  }
   return CM_OK;
 }
 
@@ -878,7 +984,7 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
   WorkspaceLease lease(idx);
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
-  CM_CUDA(lease.ws->small.ensure(256));
+  CM_CUDA(lease.ws->small.ensure(kSmallBytes));
   uint32_t* bad_row = lease.ws->small.as<uint32_t>() + 48;  // offset 192
   CM_CUDA(cudaMemsetAsync(bad_row, 0xFF, 4, hc.s));
   st = search_temporal_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, ef_search, w, base, now_secs, now_nanos, exact,

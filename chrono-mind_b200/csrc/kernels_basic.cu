@@ -138,8 +138,14 @@ constexpr int EX_ROWS = 256;
 
 __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
                                                     const float* __restrict__ x, uint64_t n, uint32_t dim,
-                                                    uint32_t ldx, float* __restrict__ D, uint64_t ldD) {
+                                                    uint32_t ldx, float* __restrict__ D, uint64_t ldD,
+                                                    const uint32_t* __restrict__ active_count) {
   extern __shared__ __align__(16) float qs[];  // [body][16]
+  if (active_count) {
+    uint32_t ac = *active_count;
+    if (blockIdx.y * EX_QT >= ac) return;
+    nq = min(nq, ac);
+  }
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t j = lane & 7, rsub = lane >> 3;
   const uint32_t body = dim & ~7u;
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
 }
 
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
-                              uint32_t ldx, float* D, uint64_t ldD, cudaStream_t s) {
+                              uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, cudaStream_t s) {
   if (nq == 0 || n == 0) return cudaSuccess;
   size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -208,7 +214,22 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
   }
   // D rows are indexed by the query's position inside this launch.
   dim3 grid((unsigned)((n + EX_ROWS - 1) / EX_ROWS), (nq + EX_QT - 1) / EX_QT);
-  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD);
+  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, uint32_t ld, const uint32_t* __restrict__ list,
+                              const uint32_t* __restrict__ count, uint32_t cap, float* __restrict__ dst) {
+  uint32_t c = min(*count, cap);
+  if (blockIdx.x >= c) return;
+  const float* s = src + (uint64_t)list[blockIdx.x] * ld;
+  float* d = dst + (uint64_t)blockIdx.x * ld;
+  for (uint32_t e = threadIdx.x; e < ld; e += blockDim.x) d[e] = s[e];
+}
+cudaError_t launch_gather_rows(const float* src, uint32_t ld, const uint32_t* list, const uint32_t* count,
+                               uint32_t cap, float* dst, cudaStream_t s) {
+  k_gather_rows<<<cap, 128, 0, s>>>(src, ld, list, count, cap, dst);
   count_launch();
   return cudaGetLastError();
 }
@@ -254,9 +275,13 @@ __device__ __forceinline__ void select_flush(unsigned long long* keys, uint32_t 
 __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* __restrict__ D, uint64_t ldD, uint64_t n,
                                                                   const uint8_t* __restrict__ deleted, uint32_t k,
                                                                   uint32_t kp, uint32_t* __restrict__ ids,
-                                                                  float* __restrict__ dist, uint32_t out_ld) {
+                                                                  float* __restrict__ dist, uint32_t out_ld,
+                                                                  const uint32_t* __restrict__ qmap,
+                                                                  const uint32_t* __restrict__ active_count) {
   extern __shared__ __align__(16) unsigned long long keys[];  // next_pow2(kp + SEL_BUF)
   __shared__ SelState st;
+  if (active_count && blockIdx.x >= *active_count) return;
+  const uint32_t out_row = qmap ? qmap[blockIdx.x] : blockIdx.x;
   const float* row = D + (uint64_t)blockIdx.x * ldD;
   for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) keys[i] = kKeyMax;
   if (threadIdx.x == 0) {
@@ -286,17 +311,18 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
   for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
     unsigned long long key = keys[i];
     bool ok = key != kKeyMax;
-    ids[(uint64_t)blockIdx.x * out_ld + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
-    dist[(uint64_t)blockIdx.x * out_ld + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+    ids[(uint64_t)out_row * out_ld + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    dist[(uint64_t)out_row * out_ld + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
   }
 }
 
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
-                                    uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, cudaStream_t s) {
+                                    uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, const uint32_t* qmap,
+                                    const uint32_t* active_count, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint32_t kp = next_pow2(k < 32 ? 32 : k);
   size_t smem = (size_t)next_pow2(kp + SEL_BUF) * sizeof(unsigned long long);
-  k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld);
+  k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld, qmap, active_count);
   count_launch();
   return cudaGetLastError();
 }

@@ -1,0 +1,41 @@
+// scan_tc.h — launch interface of the tcgen05 scan (K1) and the fp32 rescore (K2). See scan_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cm_internal.h"
+
+namespace cm {
+
+uint64_t scan_tc_pad_rows(uint64_t n);        // corpus rows padded to the X tile height (256)
+uint32_t scan_tc_pad_queries(uint32_t nq);    // queries padded to the Q tile height (128)
+uint32_t scan_tc_pad_k(uint32_t dim);         // columns padded to the K block (64)
+bool scan_tc_supported(const DeviceIndex& ix, uint32_t k);
+
+struct ScanTcLaunch {
+  const void* q_bf16;        // [pad_queries(nq)][k_pad] bf16, zero padded
+  uint32_t nq, k;
+  uint32_t* tau_key;         // [pad_queries(nq)] zeroed
+  uint32_t* cand_cnt;        // [pad_queries(nq)] zeroed
+  unsigned long long* cand;  // [pad_queries(nq)][cap]
+  uint32_t cap;
+};
+cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s);
+
+struct RescoreLaunch {
+  const float* qn;           // prepared fp32 queries [nq][ldq]
+  uint32_t ldq, nq, k;
+  const uint32_t* tau_key;
+  const uint32_t* cand_cnt;
+  const unsigned long long* cand;
+  uint32_t cap;
+  uint32_t* ids;             // [nq][k]
+  float* dist;               // [nq][k]
+  uint32_t* flag_count;      // zeroed; queries that must be re-run through the fp32 scan
+  uint32_t* flag_list;       // [flag_cap]
+  uint32_t flag_cap;
+  unsigned long long* rescored_total;
+};
+cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaStream_t s);
+
+}  // namespace cm

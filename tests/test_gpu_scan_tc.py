@@ -1,0 +1,84 @@
+"""Tensor-core exact scan (tcgen05 bf16 scan + exact fp32 rescore), forced with engine = 2, against the oracle:
+the result must be the EXACT top-k — ids bit-exact, distances bit-identical — not a bf16 approximation."""
+import numpy as np
+import pytest
+
+import oracle
+from chronomind_b200 import datasets
+from chronomind_b200.engine import NO_ID, ChronoMindB200, default_config, last_counters
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def store(data, deleted=None, engine=2):
+    st = ChronoMindB200.from_matrix(data, default_config(dimensions=data.shape[1]), deleted=deleted)
+    return st.upload(0).set_exact_engine(engine)
+
+
+@pytest.mark.parametrize("n,nq,dim,k,kind", [(20000, 300, 768, 10, "emb"), (20000, 300, 768, 10, "uni"),
+                                             (5000, 77, 100, 10, "uni"), (33000, 129, 768, 32, "emb"),
+                                             (4097, 1, 64, 1, "uni"), (9000, 500, 32, 64, "uni"),
+                                             (3000, 40, 771, 10, "emb")])
+def test_tc_scan_is_exact(n, nq, dim, k, kind):
+    if kind == "emb":
+        data, q = datasets.embedding_dataset(n, nq, 0xBEEF + n, dim=dim)
+    else:
+        data, q = datasets.uniform_dataset(n, nq, dim, 0xC0FFEE + n)
+    st = store(data)
+    ids, d = st.search_exact(q, k)
+    c = last_counters()
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data, threads=8), q, k, mode="prepared", threads=8)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(bits(d), bits(wd))
+    assert c["rescored"] >= nq * min(k, n)               # the tensor-core path actually ran
+    assert c["fallback_queries"] == 0
+
+
+def test_tc_scan_tombstones_duplicates_and_short_rows():
+    rng = np.random.default_rng(12)
+    data = datasets.unit_vectors(rng, 6000, 96)
+    data[100:140] = data[50]                            # 41 identical rows: ties resolved by handle
+    dele = (rng.uniform(size=6000) < 0.3).astype(np.uint8)
+    dele[50] = 1
+    q = np.vstack([data[50:51], datasets.unit_vectors(rng, 70, 96)])
+    st = store(data, dele)
+    ids, d = st.search_exact(q, 20)
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 20, mode="prepared", deleted=dele)
+    assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+    assert not dele[ids[ids != NO_ID]].any()
+    # fewer live rows than k: padded
+    small = datasets.unit_vectors(rng, 9000, 16)
+    dele = np.ones(9000, np.uint8)
+    dele[[5, 77, 8000]] = 0
+    st = store(small, dele)
+    ids, d = st.search_exact(datasets.unit_vectors(rng, 64, 16), 10)
+    assert np.all(np.sort(ids[:, :3], axis=1) == np.array([5, 77, 8000])) and np.all(ids[:, 3:] == NO_ID)
+
+
+def test_tc_scan_nonfinite_query_falls_back_to_fp32():
+    """A NaN query yields NaN scores on the tensor cores (nothing passes the threshold): K2 flags the query and the
+    in-stream fp32 scan reproduces the reference's result for it; the other queries are unaffected."""
+    rng = np.random.default_rng(3)
+    data = datasets.unit_vectors(rng, 9000, 64)
+    q = datasets.unit_vectors(rng, 70, 64)
+    q[13, 5] = np.nan
+    st = store(data)
+    ids, d = st.search_exact(q, 10)
+    c = last_counters()
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 10, mode="prepared")
+    assert c["fallback_queries"] == 1
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(bits(d), bits(wd))
+
+
+def test_auto_engine_matches_forced_engines():
+    data, q = datasets.embedding_dataset(12000, 128, 5)
+    a = store(data, engine=0).search_exact(q, 10)
+    b = store(data, engine=1).search_exact(q, 10)
+    c = store(data, engine=2).search_exact(q, 10)
+    for x in (b, c):
+        assert np.array_equal(a[0], x[0]) and np.array_equal(bits(a[1]), bits(x[1]))
