@@ -141,8 +141,8 @@ struct WorkspaceLease {
 
 constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited table: 128 Ki entries
 constexpr size_t kDistWorkspaceBytes = 1ull << 30;  // fp32 scan: distance block [QB][n] floats
-constexpr uint32_t kCandCap = 2048;            // tensor-core scan: candidate slots per query
-constexpr uint32_t kFlagCap = 64;              // queries per call the in-stream fp32 fallback can absorb
+constexpr uint32_t kFlagCap = 1024;            // queries per call the in-stream fp32 fallback can absorb
+constexpr uint32_t kFlagChunk = 64;            // ... in fp32 scans of this many queries (empty chunks exit at once)
 // ws->small layout (bytes): 0 HNSW counters (8 x u64) | 64 rescored_total u64 | 72 flag_count u32 |
 // 128 work_counter u32 | 192 bad_row u32 | 256 flag_list (kFlagCap x u32)
 constexpr size_t kSmallBytes = 256 + kFlagCap * 4;
@@ -172,6 +172,12 @@ static void parallel_rows(uint64_t n, F f) {
     });
   }
   for (auto& t : ts) t.join();
+}
+
+static bool row_is_finite(const float* v, uint32_t dim) {
+  float acc = 0.0f;
+  for (uint32_t e = 0; e < dim; ++e) acc += v[e] * 0.0f;  // NaN/Inf poison the sum; vectorises
+  return acc == 0.0f;
 }
 
 static uint32_t hash_bits_for(uint32_t ef) {
@@ -212,7 +218,7 @@ static cm_status exact_topk_fp32(const cm_index* idx, Workspace* ws, const float
   uint64_t ldD = (d.n + 3) & ~3ull;
   uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
   qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
-  if (qmap) qb = ((uint64_t)nq + 15) & ~15ull;  // the fallback runs as one block
+  if (qmap) qb = std::min<uint64_t>(qb, kFlagChunk);  // fallback: small chunks, the ones past *active_count exit at once
   CM_CUDA(ws->D.ensure(qb * ldD * sizeof(float)));
   float* D = ws->D.as<float>();
   for (uint32_t q0 = 0; q0 < nq; q0 += (uint32_t)qb) {
@@ -221,10 +227,10 @@ static cm_status exact_topk_fp32(const cm_index* idx, Workspace* ws, const float
       CM_CUDA(launch_fill(D, (uint64_t)nb * ldD, 2.0f, s));
     } else {
       ProfileScope prof(qmap ? nullptr : s, qmap == nullptr);
-      CM_CUDA(launch_exact_dist(qn + (size_t)q0 * ldq, nb, ldq, d.x32, d.n, d.dim, d.dim_pad, D, ldD, active_count, s));
+      CM_CUDA(launch_exact_dist(qn + (size_t)q0 * ldq, nb, ldq, d.x32, d.n, d.dim, d.dim_pad, D, ldD, active_count, q0, s));
     }
     CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, d.deleted, k, qmap ? ids : ids + (size_t)q0 * k,
-                                    qmap ? dist : dist + (size_t)q0 * k, k, qmap, active_count, s));
+                                    qmap ? dist : dist + (size_t)q0 * k, k, qmap ? qmap + q0 : nullptr, active_count, q0, s));
   }
   return CM_OK;
 }
@@ -237,7 +243,8 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   tl_used_tc = true;
   CM_CUDA(ws->qbf16.ensure((size_t)nq_pad * d.k_pad * 2));
   CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
-  CM_CUDA(ws->cand.ensure((size_t)nq_pad * kCandCap * 8));
+  const uint32_t cap = scan_tc_cand_cap(k);
+  CM_CUDA(ws->cand.ensure((size_t)nq_pad * cap * 8));
   CM_CUDA(ws->small.ensure(kSmallBytes));
   CM_CUDA(ws->qflag.ensure((size_t)kFlagCap * d.dim_pad * 4));
   uint32_t* tau_key = ws->tc_state.as<uint32_t>();
@@ -253,7 +260,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   sl.tau_key = tau_key;
   sl.cand_cnt = cand_cnt;
   sl.cand = ws->cand.as<unsigned long long>();
-  sl.cap = kCandCap;
+  sl.cap = cap;
   {
     ProfileScope prof(s);
     CM_CUDA(launch_scan_tc(d, sl, s));
@@ -266,7 +273,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   rl.tau_key = tau_key;
   rl.cand_cnt = cand_cnt;
   rl.cand = sl.cand;
-  rl.cap = kCandCap;
+  rl.cap = cap;
   rl.ids = ids;
   rl.dist = dist;
   rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
@@ -291,10 +298,12 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
     return CM_OK;
   }
   tl_counters.dist_evals += (uint64_t)nq * d.n;
-  bool tc_ok = !pq.degenerate && scan_tc_supported(d, k);
+  // Rows with NaN/Inf components order by f32::total_cmp in the reference; the threshold select cannot
+  // reproduce that, so such an index always takes the fp32 scan.
+  bool tc_ok = !pq.degenerate && idx->all_finite && scan_tc_supported(d, k);
   bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && nq >= 64 && d.n >= 8192);
   if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
-    return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 64 and a bf16 copy of the corpus");
+    return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 64 and a corpus without NaN/Inf components");
   if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s);
   return exact_topk_fp32(idx, ws, pq.qn, pq.ld, pq.degenerate, nq, k, ids, dist, nullptr, nullptr, s);
 }
@@ -512,7 +521,13 @@ cm_status cm_index_from_matrix(const float* x, uint64_t n, uint32_t dim, const c
   cm_index* idx = new_index(c, n, dim);
   idx->x.resize(n * (uint64_t)dim);
   float* dst = idx->x.data();
-  parallel_rows(n, [=](uint64_t i) { preprocess_row(x + i * dim, dim, dst + i * dim); });
+  std::atomic<bool> finite{true};
+  std::atomic<bool>* fin = &finite;
+  parallel_rows(n, [=](uint64_t i) {
+    preprocess_row(x + i * dim, dim, dst + i * dim);
+    if (!row_is_finite(dst + i * dim, dim)) fin->store(false, std::memory_order_relaxed);
+  });
+  idx->all_finite = finite.load();
   *out = idx;
   return CM_OK;
 }
@@ -531,7 +546,13 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   idx->x.resize(n * (uint64_t)dim);
   const float* src = snap.vectors.data();
   float* dst = idx->x.data();
-  parallel_rows(n, [=](uint64_t i) { preprocess_row(src + i * dim, dim, dst + i * dim); });
+  std::atomic<bool> finite{true};
+  std::atomic<bool>* fin = &finite;
+  parallel_rows(n, [=](uint64_t i) {
+    preprocess_row(src + i * dim, dim, dst + i * dim);
+    if (!row_is_finite(dst + i * dim, dim)) fin->store(false, std::memory_order_relaxed);
+  });
+  idx->all_finite = finite.load();
   idx->ext_ids.resize(n);
   // Replay ChronoMind::insert's handle bookkeeping (src/store.rs:226-264): a repeated id publishes the new
   // handle and tombstones the one it replaces; capacity counts distinct ids.

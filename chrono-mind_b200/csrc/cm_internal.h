@@ -141,6 +141,7 @@ struct cm_index {
   std::vector<float> decay;         // [n]
   std::vector<std::string> ext_ids; // snapshot-loaded only
   uint64_t live = 0;
+  bool all_finite = true;           // no NaN/Inf component in any stored row (gate of the tensor-core scan)
   cm::Graph graph;
   uint32_t shard_rank = 0, shard_count = 1;
   int exact_engine = 0;

@@ -24,16 +24,18 @@ cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uin
                                  cudaStream_t s);
 
 // fp32 exact scan, CUDA cores, bit-exact to dot_avx2: D[qi][row] = distance_prepared(x[row], q[qi]).
-// active_count (optional, device): only the first *active_count queries are computed.
+// active_count (optional, device): query i of this launch is computed only when active_base + i < *active_count.
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
-                              uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, cudaStream_t s);
+                              uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
+                              cudaStream_t s);
 cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
 
 // k smallest (distance, handle) per row of D, tombstones dropped.
-// qmap/active_count (optional, device): row b of D belongs to output row qmap[b]; rows >= *active_count are skipped.
+// qmap/active_count (optional, device): row b of D belongs to output row qmap[b]; rows with
+// active_base + b >= *active_count are skipped.
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
                                     uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, const uint32_t* qmap,
-                                    const uint32_t* active_count, cudaStream_t s);
+                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s);
 
 // K5 — shard merge (src/index/sharded_rwlock.rs:81-94).
 cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,

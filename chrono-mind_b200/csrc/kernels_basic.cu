@@ -139,10 +139,12 @@ constexpr int EX_ROWS = 256;
 __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
                                                     const float* __restrict__ x, uint64_t n, uint32_t dim,
                                                     uint32_t ldx, float* __restrict__ D, uint64_t ldD,
-                                                    const uint32_t* __restrict__ active_count) {
+                                                    const uint32_t* __restrict__ active_count,
+                                                    uint32_t active_base) {
   extern __shared__ __align__(16) float qs[];  // [body][16]
   if (active_count) {
     uint32_t ac = *active_count;
+    ac = ac > active_base ? ac - active_base : 0;
     if (blockIdx.y * EX_QT >= ac) return;
     nq = min(nq, ac);
   }
@@ -202,7 +204,8 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
 }
 
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
-                              uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, cudaStream_t s) {
+                              uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
+                              cudaStream_t s) {
   if (nq == 0 || n == 0) return cudaSuccess;
   size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -214,7 +217,7 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
   }
   // D rows are indexed by the query's position inside this launch.
   dim3 grid((unsigned)((n + EX_ROWS - 1) / EX_ROWS), (nq + EX_QT - 1) / EX_QT);
-  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count);
+  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base);
   count_launch();
   return cudaGetLastError();
 }
@@ -277,10 +280,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
                                                                   uint32_t kp, uint32_t* __restrict__ ids,
                                                                   float* __restrict__ dist, uint32_t out_ld,
                                                                   const uint32_t* __restrict__ qmap,
-                                                                  const uint32_t* __restrict__ active_count) {
+                                                                  const uint32_t* __restrict__ active_count,
+                                                                  uint32_t active_base) {
   extern __shared__ __align__(16) unsigned long long keys[];  // next_pow2(kp + SEL_BUF)
   __shared__ SelState st;
-  if (active_count && blockIdx.x >= *active_count) return;
+  if (active_count && active_base + blockIdx.x >= *active_count) return;
   const uint32_t out_row = qmap ? qmap[blockIdx.x] : blockIdx.x;
   const float* row = D + (uint64_t)blockIdx.x * ldD;
   for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) keys[i] = kKeyMax;
@@ -318,11 +322,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
 
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
                                     uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, const uint32_t* qmap,
-                                    const uint32_t* active_count, cudaStream_t s) {
+                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint32_t kp = next_pow2(k < 32 ? 32 : k);
   size_t smem = (size_t)next_pow2(kp + SEL_BUF) * sizeof(unsigned long long);
-  k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld, qmap, active_count);
+  k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld, qmap, active_count,
+                                                   active_base);
   count_launch();
   return cudaGetLastError();
 }

@@ -3,29 +3,43 @@
 // Replaces the all-pairs loop of the reference's brute force (tests/recall_test.rs:70-79,
 // tests/property_test.rs:201-206, src/store.rs:362-376) for large batches:
 //
-//   K1  scan_tc_kernel   S = Q · Xᵀ in bf16 on tcgen05 (fp32 accumulators in TMEM, operands staged by TMA into
-//                        128B-swizzled shared memory). S is never written: the epilogue warps read each
-//                        accumulator tile straight out of TMEM and keep, per query, only the rows whose bf16
-//                        score can still be among the exact top-k (threshold select, see below).
-//   K2  rescore_kernel   the few surviving rows per query are re-scored with the reference's exact fp32
-//                        arithmetic (dot_avx2 order, src/metric.rs:129-147) and sorted by (distance, handle).
+//   K1  scan_tc_kernel   S = Q · Xᵀ in bf16 on tcgen05 (cta_group::2: one 256x256 tile per CTA PAIR, fp32
+//                        accumulators in TMEM, operands staged by TMA into 128B-swizzled shared memory). S is
+//                        never written: the epilogue warps read each accumulator tile straight out of TMEM and
+//                        keep, per query, only the rows whose bf16 score can still be among the exact top-k
+//                        (threshold select, see below).
+//   K2  rescore_kernel   per query: tighten the candidate set with the now-known k-th best bf16 score, re-score
+//                        the few survivors with the reference's exact fp32 arithmetic (dot_avx2 order,
+//                        src/metric.rs:129-147) and sort by (distance, handle).
 //
 // Why the result is EXACT (not "bf16-approximate"): let e_r be the fp32 reference dot of row r and s_r the
 // tensor-core bf16 score, |s_r - e_r| <= eps for unit vectors (bf16 rounding of both operands: 2·2^-9 relative
-// per product, Cauchy-Schwarz => <= 2^-8 absolute; eps = kEps adds slack for accumulation order). The k-th
-// largest s is <= (k-th largest e) + eps, so every row of the exact top-k has s_r >= s_(k) - 2·eps. The
-// epilogue's threshold tau_q is always a LOWER bound of s_(k) - 2·eps (it is derived from k scores actually
-// seen for that query), so no row of the exact top-k is ever filtered. K2 then orders the survivors with the
-// exact arithmetic. If a query's candidate buffer overflows, or fewer than k candidates survive (NaN/Inf data),
+// per product, Cauchy-Schwarz => <= 2^-8 absolute; kEps adds slack for accumulation order). With s_(k) / e_(k)
+// the k-th largest score over the live rows: the k rows of largest s have e >= s_(k) - eps, so
+// e_(k) >= s_(k) - eps, so every row of the exact top-k (e_r >= e_(k)) has s_r >= s_(k) - 2·eps.
+//   * K1's threshold tau_q is always a LOWER bound of s_(k) - 2·eps: it is the k-th best of k scores of distinct
+//     live rows actually seen for that query, minus 2·eps, and only ever grows (atomicMax). Every row with
+//     s_r >= tau_q (final) is therefore in the candidate list, which contains the whole bf16 top-k.
+//   * K2 reads s_(k) off the candidate list (its k-th largest key), keeps s_r >= s_(k) - 2·eps and orders those
+//     with the exact arithmetic.
+// If a query's candidate buffer overflows, or fewer than min(k, live) candidates survive (NaN/Inf queries),
 // K2 flags the query and it is re-run through the fp32 scan — never silently degraded.
 //
-// Kernel organisation (one CTA per SM, persistent, 8 warps):
-//   warp 0  TMA producer     (one lane)  — 4-stage ring of {Q tile 128x64, X tile 256x64} bf16, 48 KB per stage
-//   warp 1  MMA issuer       (one lane)  — tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, 4 per stage
-//   warp 2  TMEM allocator               — 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4-7 epilogue (128 threads)     — thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time
-// Work unit = (query tile m, strip of kStripTiles X tiles), ordered m-fastest so that the CTAs in flight stream
-// the same few MB of X at the same time (X is read from HBM once per strip and hit in L2 by the other query tiles).
+// Kernel organisation (persistent, one CTA per SM, clusters of 2 = one CTA pair per TPC, 8 warps per CTA):
+//   warp 0  TMA producer (one lane, both CTAs) — ring of {Q tile 128x64, X tile 128x64} bf16, 32 KB per stage
+//           per CTA; the pair's loads all complete on the LEADER's full barrier
+//   warp 1  MMA issuer   (one lane, leader CTA only) — tcgen05.mma.cta_group::2.kind::f16, M=256 N=256 K=16:
+//           CTA r supplies Q rows [128r, 128r+128) and X rows [128r, 128r+128) of the tile and receives the
+//           accumulator rows of ITS queries against all 256 X rows
+//   warp 2  TMEM allocator — 512 columns = two 128x256 fp32 accumulators (double buffered) per CTA
+//   warps 4-7 epilogue (128 threads) — thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time
+// Operand traffic: each CTA fetches 32 KB per 2·128·256·64 FLOP (128 FLOP/B, vs 85 for a 1-CTA 128x256 tile),
+// which is what keeps the L2->SM path (≈6.3 KB/clk chip-wide) below the tensor pipe's demand.
+//
+// Work unit = (query tile pair m, corpus split s): the pair scans tiles [s·T/S, (s+1)·T/S) for its 256 queries,
+// so a thread's running top-k covers a long row range and its threshold converges after a few tiles. Units are
+// ordered m-fastest: the clusters in flight stream the same corpus splits at the same time (X comes from HBM
+// once per split and is hit in L2 by the other query tiles).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -37,17 +51,38 @@
 
 namespace cm {
 
-constexpr uint32_t BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr uint32_t kStages = 4, kAccStages = 2;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t BM = 128;        // query rows per CTA (TMEM lanes)
+constexpr uint32_t PAIR_M = 256;    // query rows per CTA pair (UMMA M)
+constexpr uint32_t BN = 256;        // corpus rows per tile (UMMA N)
+constexpr uint32_t BN_HALF = 128;   // corpus rows each CTA stages
+constexpr uint32_t BK = 64, UMMA_K = 16;
+constexpr uint32_t kMaxStages = 6, kAccStages = 2;
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN_HALF * BK * 2;
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kStripTiles = 16;
 constexpr uint32_t kThreads = 256;
-constexpr float kEps = 0.0042f;  // >= 2^-8 + accumulation slack; margin is 2 * kEps
+constexpr uint32_t kSlotChunk = 8;  // candidate slots reserved per atomic
+constexpr float kEps = 0.0042f;     // >= 2^-8 + accumulation slack; margin is 2 * kEps
+constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of THIS CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -55,8 +90,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrive on a barrier of any CTA of the cluster (shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 // Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -76,10 +112,13 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+// TMA load issued by either CTA of a pair into ITS OWN shared memory; the bytes are accounted on `bar_cluster`
+// (a shared::cluster address — the leader's full barrier).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int32_t c0,
+                                                 int32_t c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -102,16 +141,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __device__ __forceinline__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] · B[smem]ᵀ over the CTA pair; issued by one thread of the leader CTA.
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// When every MMA issued so far has retired: arrive (count 1) on the barrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -128,32 +173,68 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct ScanArgs {
-  uint32_t nq, m_tiles, n_tiles, k_blocks, k;
-  uint32_t strip_begin, strip_end;  // this launch covers strips [strip_begin, strip_end)
+  uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, stages;
   uint64_t n;
   const uint8_t* deleted;
-  uint32_t* tau_key;             // [m_tiles*128] ordered-uint threshold per query (0 = none yet)
-  uint32_t* cand_cnt;            // [m_tiles*128]
-  unsigned long long* cand;      // [m_tiles*128][cap]  (ordered score key << 32 | row)
+  uint32_t* tau_key;             // [m_pairs*256] ordered-uint threshold per query (0 = none yet)
+  uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
+  unsigned long long* cand;      // [m_pairs*256][cap]  (ordered score key << 32 | row); 0 = unused slot
   uint32_t cap;
 };
 
-// Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists | barriers | tmem ptr
+// Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists [k][128] | barriers | tmem ptr.
+// Both CTAs of a pair use the same offsets (the MMA descriptors and multicast commits rely on it).
 struct ScanSmemTail {
-  unsigned long long full[kStages], empty[kStages], tmem_full[kAccStages], tmem_empty[kAccStages];
+  unsigned long long full[kMaxStages], empty[kMaxStages], tmem_full[kAccStages], tmem_empty[kAccStages];
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+// Running top-k (k largest scores) of one thread, unsorted, strided by 128 in shared memory.
+struct LocalTopK {
+  float* list;
+  uint32_t k, filled, min_pos;
+  float kth;  // smallest of the k entries once filled == k
+  __device__ __forceinline__ void rescan() {
+    kth = list[0];
+    min_pos = 0;
+    for (uint32_t j = 1; j < k; ++j) {
+      float v = list[j * 128];
+      if (v < kth) kth = v, min_pos = j;
+    }
+  }
+  // returns true when the k-th best changed
+  __device__ __forceinline__ bool insert(float s) {
+    if (filled < k) {
+      list[filled * 128] = s;
+      if (++filled == k) {
+        rescan();
+        return true;
+      }
+      return false;
+    }
+    if (s > kth) {
+      list[min_pos * 128] = s;
+      rescan();
+      return true;
+    }
+    return false;
+  }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves the slack).
+  // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves the slack). The
+  // dynamic window starts at the same offset in both CTAs of the pair, so the carve-up matches.
   uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  float* lists = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [k][128]
-  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(tiles + kStages * kStageBytes + (size_t)a.k * 128 * 4);
+  float* lists = reinterpret_cast<float*>(tiles + a.stages * kStageBytes);  // [k][128]
+  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(tiles + a.stages * kStageBytes + (size_t)a.k * 128 * 4);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t units = (a.strip_end - a.strip_begin) * a.m_tiles;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t units = a.m_pairs * a.splits;
+  const uint32_t kStages = a.stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -161,41 +242,46 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&tail->full[s]), 1);
-      mbar_init(smem_u32(&tail->empty[s]), 1);
+      mbar_init(smem_u32(&tail->full[s]), 1);    // leader's producer: arrive.expect_tx for the pair's bytes
+      mbar_init(smem_u32(&tail->empty[s]), 1);   // one multicast commit per use
     }
     for (uint32_t s = 0; s < kAccStages; ++s) {
-      mbar_init(smem_u32(&tail->tmem_full[s]), 1);
-      mbar_init(smem_u32(&tail->tmem_empty[s]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&tail->tmem_full[s]), 1);   // one multicast commit per tile
+      mbar_init(smem_u32(&tail->tmem_empty[s]), 8);  // leader's copy: 4 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
                  "r"(kTmemCols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA lands
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer =========================================================================================
+    // ===== TMA producer (both CTAs) =============================================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t m = u % a.m_tiles, strip = a.strip_begin + u / a.m_tiles;
-        const uint32_t t0 = strip * kStripTiles, t1 = min(a.n_tiles, t0 + kStripTiles);
+      for (uint32_t u = cluster_id; u < units; u += n_clusters) {
+        const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
+        const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+        const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        const int32_t q_row = (int32_t)(m * PAIR_M + rank * BM);
         for (uint32_t t = t0; t < t1; ++t) {
+          const int32_t x_row = (int32_t)(t * BN + rank * BN_HALF);
           for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
             mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
-            const uint32_t bar = smem_u32(&tail->full[stage]);
-            mbar_expect_tx(bar, kStageBytes);
+            const uint32_t bar_local = smem_u32(&tail->full[stage]);
+            if (rank == 0) mbar_expect_tx(bar_local, 2 * kStageBytes);  // both CTAs' Q and X tiles
+            const uint32_t bar = map_to_cta(bar_local, 0);
             const uint32_t sa = smem_u32(tiles + stage * kStageBytes);
-            tma_load_2d(sa, &map_q, bar, (int32_t)(kb * BK), (int32_t)(m * BM));
-            tma_load_2d(sa + kStageBytesA, &map_x, bar, (int32_t)(kb * BK), (int32_t)(t * BN));
+            tma_load_2d_pair(sa, &map_q, bar, (int32_t)(kb * BK), q_row);
+            tma_load_2d_pair(sa + kStageBytesA, &map_x, bar, (int32_t)(kb * BK), x_row);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -205,15 +291,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer ===========================================================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    // ===== MMA issuer (leader CTA) ==============================================================================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR_M, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t strip = a.strip_begin + u / a.m_tiles;
-        const uint32_t t0 = strip * kStripTiles, t1 = min(a.n_tiles, t0 + kStripTiles);
+      for (uint32_t u = cluster_id; u < units; u += n_clusters) {
+        const uint32_t sp = u / a.m_pairs;
+        const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+        const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
         for (uint32_t t = t0; t < t1; ++t) {
-          mbar_wait(smem_u32(&tail->tmem_empty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
+          mbar_wait(smem_u32(&tail->tmem_empty[acc]), acc_phase ^ 1);  // both epilogues drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
@@ -224,10 +311,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
             for (uint32_t kk = 0; kk < BK / UMMA_K; ++kk) {
               // advancing 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 start field
-              umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+              umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
             }
-            umma_commit(smem_u32(&tail->empty[stage]));  // frees the smem stage when these MMAs retire
-            if (kb + 1 == a.k_blocks) umma_commit(smem_u32(&tail->tmem_full[acc]));
+            umma_commit_pair(smem_u32(&tail->empty[stage]));  // frees the stage in both CTAs when the MMAs retire
+            if (kb + 1 == a.k_blocks) umma_commit_pair(smem_u32(&tail->tmem_full[acc]));
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -242,33 +329,66 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===== epilogue: threshold select straight out of TMEM =======================================================
-    const uint32_t ew = warp & 3;              // TMEM lane quarter this warp may access
-    const uint32_t row_in_tile = ew * 32 + lane;
-    const uint32_t et = (warp - 4) * 32 + lane;  // 0..127 index into the per-thread lists
-    float* my_list = lists + et;               // my_list[i * 128]
-    const uint32_t k = a.k;
+    const uint32_t quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const uint32_t row_in_cta = quarter * 32 + lane;   // accumulator row == TMEM lane
+    LocalTopK top;
+    top.list = lists + row_in_cta;
+    top.k = a.k;
+    const uint32_t empty_bar0 = map_to_cta(smem_u32(&tail->tmem_empty[0]), 0);
+    const uint32_t empty_bar1 = map_to_cta(smem_u32(&tail->tmem_empty[1]), 0);
     uint32_t acc = 0, acc_phase = 0;
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-      const uint32_t m = u % a.m_tiles, strip = a.strip_begin + u / a.m_tiles;
-      const uint32_t t0 = strip * kStripTiles, t1 = min(a.n_tiles, t0 + kStripTiles);
-      const uint32_t q = m * BM + row_in_tile;
+    for (uint32_t u = cluster_id; u < units; u += n_clusters) {
+      const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
+      const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+      const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+      const uint32_t q = m * PAIR_M + rank * BM + row_in_cta;
       const bool q_valid = q < a.nq;
-      // Per-strip local state: the k best scores this thread has seen that reached the emission threshold.
-      uint32_t filled = 0;
-      float local_kth = -INFINITY;   // k-th best of the local list once it holds k entries
-      uint32_t min_pos = 0;
-      float tau = INFINITY;          // emission threshold; +inf for padding queries (nothing passes)
+      unsigned long long* my_cand = a.cand + (uint64_t)q * a.cap;
+      // Per-unit state: the k best scores of this unit's rows, and a chunk of reserved candidate slots.
+      top.filled = 0;
+      top.min_pos = 0;
+      top.kth = -INFINITY;
+      uint32_t slot_next = 0, slots_left = 0;
       for (uint32_t t = t0; t < t1; ++t) {
+        float tau = INFINITY;  // padding queries: nothing passes
         if (q_valid) {
-          uint32_t tk = a.tau_key[q];
-          float g = tk ? key_to_float(tk) : -INFINITY;
-          tau = fmaxf(g, local_kth - 2.0f * kEps);
+          const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
+          const float g = tk ? key_to_float(tk) : -INFINITY;
+          tau = fmaxf(g, top.filled == top.k ? top.kth - 2.0f * kEps : -INFINITY);
         }
         mbar_wait(smem_u32(&tail->tmem_full[acc]), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((ew * 32) << 16) + acc * BN;
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * BN;
         const uint64_t row0 = (uint64_t)t * BN;
         bool improved = false;
+        // Cold start (no threshold yet): first build the running top-k from this tile WITHOUT emitting, so the
+        // main pass below emits ~k rows instead of all 256.
+        const bool cold = q_valid && tau == -INFINITY;
+        bool listed = false;  // this tile's rows are already in the running top-k
+        if (__any_sync(0xFFFFFFFFu, cold)) {
+#pragma unroll 1
+          for (uint32_t c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(taddr + c, r);
+            tmem_ld_wait();
+            if (cold) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float s = __uint_as_float(r[i]);
+                const uint64_t row = row0 + c + i;
+                if (s == s && row < a.n && !(a.deleted && a.deleted[row])) top.insert(s);
+              }
+            }
+          }
+          if (cold) {
+            listed = true;
+            if (top.filled == top.k) {
+              tau = top.kth - 2.0f * kEps;
+              improved = true;
+            }
+          }
+        }
 #pragma unroll 1
         for (uint32_t c = 0; c < BN; c += 32) {
           uint32_t r[32];
@@ -285,64 +405,64 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               if (s >= tau) {
                 const uint64_t row = row0 + c + i;
                 if (row < a.n && !(a.deleted && a.deleted[row])) {
-                  uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
-                  if (slot < a.cap) a.cand[(uint64_t)q * a.cap + slot] = ((unsigned long long)total_key(s) << 32) | (uint32_t)row;
-                  if (filled < k) {
-                    my_list[filled * 128] = s;
-                    ++filled;
-                    if (filled == k) {
-                      local_kth = my_list[0];
-                      min_pos = 0;
-                      for (uint32_t j = 1; j < k; ++j) {
-                        float v = my_list[j * 128];
-                        if (v < local_kth) local_kth = v, min_pos = j;
-                      }
-                      improved = true;
-                    }
-                  } else if (s > local_kth) {
-                    my_list[min_pos * 128] = s;
-                    local_kth = my_list[0];
-                    min_pos = 0;
-                    for (uint32_t j = 1; j < k; ++j) {
-                      float v = my_list[j * 128];
-                      if (v < local_kth) local_kth = v, min_pos = j;
-                    }
-                    improved = true;
+                  if (slots_left == 0) {
+                    slot_next = atomicAdd(&a.cand_cnt[q], kSlotChunk);
+                    slots_left = kSlotChunk;
                   }
-                  if (improved) tau = fmaxf(tau, local_kth - 2.0f * kEps);
+                  if (slot_next < a.cap) my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)row;
+                  ++slot_next;
+                  --slots_left;
+                  if (!listed && top.insert(s)) {
+                    improved = true;
+                    tau = fmaxf(tau, top.kth - 2.0f * kEps);
+                  }
                 }
               }
             }
           }
         }
-        // accumulator drained: hand it back to the MMA warp
+        // accumulator drained: hand it back to the MMA warp of the leader CTA
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[acc]));
+        if (lane == 0) mbar_arrive_cluster(acc ? empty_bar1 : empty_bar0);
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
         }
-        // publish the lower bound s_(k) - 2 eps for the other CTAs working on this query
-        if (improved && q_valid) atomicMax(&a.tau_key[q], total_key(local_kth - 2.0f * kEps));
+        // publish the lower bound s_(k) - 2 eps for the other clusters working on this query
+        if (improved && q_valid) atomicMax(&a.tau_key[q], total_key(top.kth - 2.0f * kEps));
+      }
+      // reserved but unused candidate slots: mark empty
+      while (slots_left) {
+        if (slot_next < a.cap) my_cand[slot_next] = 0ull;
+        ++slot_next;
+        --slots_left;
       }
     }
   }
 
+  // Neither CTA may exit (or free TMEM) while its peer can still multicast to / read from it.
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K2 rescore: one CTA per query. Keep the candidates whose bf16 score reaches the FINAL threshold, evaluate
-// distance_prepared exactly (octet per candidate, reference lane order), sort by (distance, handle).
+// K2 rescore: one CTA per query.
+//   1. keep the candidates whose bf16 score reaches the FINAL scan threshold (everything the scan emitted
+//      before the threshold converged drops out here);
+//   2. sort them by score, read s_(k) — the exact k-th best bf16 score over the live rows — and keep the
+//      prefix with s >= s_(k) - 2 eps;
+//   3. evaluate distance_prepared exactly for that prefix (octet per candidate, reference lane order) and
+//      sort by (distance, handle).
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t RS_THREADS = 256;
-constexpr uint32_t RS_MAX = 1024;  // survivors handled per query
+constexpr uint32_t RS_MAX = 4096;    // candidates above the final scan threshold handled per query
+constexpr uint32_t RS2_MAX = 1024;   // candidates re-scored per query
 
 struct RescoreArgs {
   const float* qn;
@@ -362,28 +482,43 @@ struct RescoreArgs {
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
-  __shared__ __align__(16) unsigned long long keys[RS_MAX];
-  __shared__ uint32_t surv[RS_MAX];
-  __shared__ uint32_t n_surv;
-  extern __shared__ __align__(16) float qs[];  // dim floats
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);          // [RS_MAX] ~(score key, row)
+  unsigned long long* dkeys = keys + RS_MAX;                                           // [RS2_MAX] (distance, row)
+  float* qs = reinterpret_cast<float*>(dkeys + RS2_MAX);                               // [dim]
+  __shared__ uint32_t n_surv, n_keep;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t cnt_raw = a.cand_cnt[q];
   const uint32_t cnt = min(cnt_raw, a.cap);
   const uint32_t tk = a.tau_key[q];
-  if (tid == 0) n_surv = 0;
+  if (tid == 0) n_surv = 0, n_keep = 0;
   for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.qn[(uint64_t)q * a.ldq + e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
-    unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
-    if ((uint32_t)(c >> 32) >= tk) {
+    const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
+    if (c != 0ull && (uint32_t)(c >> 32) >= tk) {
       uint32_t slot = atomicAdd(&n_surv, 1u);
-      if (slot < RS_MAX) surv[slot] = (uint32_t)c;
+      if (slot < RS_MAX) keys[slot] = ~c;  // ascending sort of ~c == descending score
     }
   }
   __syncthreads();
   const uint32_t ns = n_surv;
-  const uint64_t need = a.n_live < a.k ? a.n_live : a.k;
-  const bool bad = cnt_raw > a.cap || ns > RS_MAX || ns < need;
+  const uint32_t need = (uint32_t)(a.n_live < a.k ? a.n_live : a.k);
+  bool bad = cnt_raw > a.cap || ns > RS_MAX || ns < need;
+  uint32_t keep = 0;
+  if (!bad) {
+    const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
+    for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
+    block_bitonic_sort(keys, P);
+    // s_(k): the k-th largest bf16 score (all of the bf16 top-k are in the list, see the header comment)
+    uint32_t thr = 0;  // ns < k only when fewer than k rows are live: keep everything
+    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - 2.0f * kEps);
+    for (uint32_t i = tid; i < ns; i += RS_THREADS)
+      if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);  // sorted: the kept set is a prefix
+    __syncthreads();
+    keep = n_keep;
+    bad = keep > RS2_MAX;
+  }
   if (bad) {
     if (tid == 0) {
       uint32_t slot = atomicAdd(a.flag_count, 1u);
@@ -397,15 +532,15 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     }
     return;
   }
-  const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
-  for (uint32_t i = tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
+  const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
+  for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
   __syncthreads();
   const uint32_t body = a.dim & ~7u;
   const uint32_t j = tid & 7, oct = tid >> 3;
-  for (uint32_t base = 0; base < ns; base += RS_THREADS / 8) {
+  for (uint32_t base = 0; base < keep; base += RS_THREADS / 8) {
     uint32_t i = base + oct;
-    bool active = i < ns;
-    uint32_t row = active ? surv[i] : 0;
+    bool active = i < keep;
+    uint32_t row = active ? (uint32_t)(~keys[i]) : 0;
     const float* xr = a.x + (uint64_t)row * a.ldx;
     float acc = 0.0f;
     if (active) {
@@ -415,17 +550,17 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     float sum = octet_hsum(acc);
     if (active) {
       for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(__ldg(xr + e), qs[e]));
-      if (j == 0) keys[i] = pack_key(clamp02(__fsub_rn(1.0f, sum)), row);
+      if (j == 0) dkeys[i] = pack_key(clamp02(__fsub_rn(1.0f, sum)), row);
     }
   }
-  block_bitonic_sort(keys, P);
+  block_bitonic_sort(dkeys, P2);
   for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
-    unsigned long long key = i < P ? keys[i] : kKeyMax;
+    unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
     bool ok = key != kKeyMax;
     a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
     a.dist[(uint64_t)q * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
   }
-  if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)ns);
+  if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)keep);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -462,47 +597,54 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 }
 
 uint64_t scan_tc_pad_rows(uint64_t n) { return (n + BN - 1) / BN * BN; }
-uint32_t scan_tc_pad_queries(uint32_t nq) { return (nq + BM - 1) / BM * BM; }
+uint32_t scan_tc_pad_queries(uint32_t nq) { return (nq + PAIR_M - 1) / PAIR_M * PAIR_M; }
 uint32_t scan_tc_pad_k(uint32_t dim) { return (dim + BK - 1) / BK * BK; }
+uint32_t scan_tc_cand_cap(uint32_t k) { return k <= 16 ? 4096u : 8192u; }
 
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
   return ix.xbf16 != nullptr && k >= 1 && k <= 64 && encode_fn() != nullptr;
+}
+
+// Corpus splits per query-tile pair: minimise waves x (tiles per unit + a few tiles of pipeline fill / cold start).
+static uint32_t pick_splits(uint32_t m_pairs, uint32_t n_tiles, uint32_t clusters) {
+  uint32_t best = 1;
+  uint64_t best_cost = ~0ull;
+  for (uint32_t s = 1; s <= std::min<uint32_t>(n_tiles, 128); ++s) {
+    uint64_t tiles_per = (n_tiles + s - 1) / s;
+    uint64_t waves = ((uint64_t)m_pairs * s + clusters - 1) / clusters;
+    uint64_t cost = waves * (tiles_per + 3);
+    if (cost < best_cost) best_cost = cost, best = s;
+  }
+  return best;
 }
 
 cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s) {
   CUtensorMap map_q, map_x;
   const uint32_t nq_pad = scan_tc_pad_queries(l.nq);
   if (!make_map(&map_q, l.q_bf16, nq_pad, ix.k_pad, BM)) return cudaErrorInvalidValue;
-  if (!make_map(&map_x, ix.xbf16, ix.n_pad, ix.k_pad, BN)) return cudaErrorInvalidValue;
+  if (!make_map(&map_x, ix.xbf16, ix.n_pad, ix.k_pad, BN_HALF)) return cudaErrorInvalidValue;
+  const uint32_t clusters = (uint32_t)std::max(1, ix.sm_count / 2);
   ScanArgs a;
   a.nq = l.nq;
-  a.m_tiles = nq_pad / BM;
+  a.m_pairs = nq_pad / PAIR_M;
   a.n_tiles = (uint32_t)(ix.n_pad / BN);
   a.k_blocks = ix.k_pad / BK;
   a.k = l.k;
+  a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters);
   a.n = ix.n;
   a.deleted = ix.deleted;
   a.tau_key = l.tau_key;
   a.cand_cnt = l.cand_cnt;
   a.cand = l.cand;
   a.cap = l.cap;
-  size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 16;
-  cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 16;
+  a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
+  if (a.stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = fixed + (size_t)a.stages * kStageBytes;
+  cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
   if (e != cudaSuccess) return e;
-  const uint32_t strips = (a.n_tiles + kStripTiles - 1) / kStripTiles;
-  // Launch 1 warms the per-query thresholds on the first strip only (one unit per query tile), so that the
-  // strips of launch 2 — many of which run concurrently for the same queries — start with a real threshold
-  // instead of each emitting its own cold-start candidates.
-  a.strip_begin = 0;
-  a.strip_end = 1;
-  unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ix.sm_count, (uint64_t)a.m_tiles);
-  scan_tc_kernel<<<grid, kThreads, smem, s>>>(map_q, map_x, a);
-  count_launch();
-  e = cudaGetLastError();
-  if (e != cudaSuccess || strips == 1) return e;
-  a.strip_begin = 1;
-  a.strip_end = strips;
-  grid = (unsigned)std::min<uint64_t>((uint64_t)ix.sm_count, (uint64_t)(strips - 1) * a.m_tiles);
+  const uint32_t units = a.m_pairs * a.splits;
+  const unsigned grid = 2u * std::min(clusters, units);  // whole CTA pairs (__cluster_dims__(2,1,1))
   scan_tc_kernel<<<grid, kThreads, smem, s>>>(map_q, map_x, a);
   count_launch();
   return cudaGetLastError();
@@ -529,7 +671,15 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.flag_list = l.flag_list;
   a.flag_cap = l.flag_cap;
   a.rescored_total = l.rescored_total;
-  rescore_kernel<<<l.nq, RS_THREADS, (size_t)ix.dim * 4, s>>>(a);
+  const size_t smem = (size_t)(RS_MAX + RS2_MAX) * 8 + (size_t)ix.dim * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  rescore_kernel<<<l.nq, RS_THREADS, smem, s>>>(a);
   count_launch();
   return cudaGetLastError();
 }

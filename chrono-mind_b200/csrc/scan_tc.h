@@ -8,7 +8,8 @@
 namespace cm {
 
 uint64_t scan_tc_pad_rows(uint64_t n);        // corpus rows padded to the X tile height (256)
-uint32_t scan_tc_pad_queries(uint32_t nq);    // queries padded to the Q tile height (128)
+uint32_t scan_tc_pad_queries(uint32_t nq);    // queries padded to the Q tile-pair height (256)
+uint32_t scan_tc_cand_cap(uint32_t k);        // candidate slots per query
 uint32_t scan_tc_pad_k(uint32_t dim);         // columns padded to the K block (64)
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k);
 

@@ -11,7 +11,12 @@ pytestmark = pytest.mark.gpu
 
 
 def bits(a):
-    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+    """Bit patterns, with every NaN mapped to one pattern (x86 keeps the operand's NaN payload, CUDA returns the
+    canonical NaN; the reference only promises that NaN propagates, src/metric.rs:223)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
 
 
 def store(data, deleted=None, engine=2):
@@ -22,7 +27,8 @@ def store(data, deleted=None, engine=2):
 @pytest.mark.parametrize("n,nq,dim,k,kind", [(20000, 300, 768, 10, "emb"), (20000, 300, 768, 10, "uni"),
                                              (5000, 77, 100, 10, "uni"), (33000, 129, 768, 32, "emb"),
                                              (4097, 1, 64, 1, "uni"), (9000, 500, 32, 64, "uni"),
-                                             (3000, 40, 771, 10, "emb")])
+                                             (3000, 40, 771, 10, "emb"), (300000, 700, 64, 10, "uni"),
+                                             (200000, 257, 768, 10, "emb"), (150000, 520, 128, 50, "uni")])
 def test_tc_scan_is_exact(n, nq, dim, k, kind):
     if kind == "emb":
         data, q = datasets.embedding_dataset(n, nq, 0xBEEF + n, dim=dim)
@@ -82,3 +88,36 @@ def test_auto_engine_matches_forced_engines():
     c = store(data, engine=2).search_exact(q, 10)
     for x in (b, c):
         assert np.array_equal(a[0], x[0]) and np.array_equal(bits(a[1]), bits(x[1]))
+
+
+def test_tc_scan_full_size_matches_fp32_engine():
+    """BASELINE configs[1] size (1M x 768, k = 10): the tensor-core path must return exactly what the bit-exact
+    fp32 CUDA-core scan returns (itself checked against the oracle at oracle-sized cases), with no query routed
+    to the fallback; a 48-query slice is also checked against the oracle directly."""
+    rng = np.random.default_rng(0x5EED)
+    basis = datasets.unit_vectors(rng, 16, 768)
+    corpus = datasets.embedding_rows(rng, basis, 1_000_000)
+    q = datasets.embedding_rows(np.random.default_rng(99), basis, 2048)
+    st = ChronoMindB200.from_matrix(corpus, default_config(dimensions=768)).upload(0)
+    ia, da = st.set_exact_engine(2).search_exact(q, 10)
+    c = last_counters()
+    assert c["fallback_queries"] == 0 and c["rescored"] >= 2048 * 10
+    ib, db = st.set_exact_engine(1).search_exact(q, 10)
+    assert np.array_equal(ia, ib) and np.array_equal(bits(da), bits(db))
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(corpus, threads=16), q[:48], 10, mode="prepared", threads=16)
+    assert np.array_equal(ia[:48], wi) and np.array_equal(bits(da[:48]), bits(wd))
+    assert np.all(np.diff(da, axis=1) >= 0)          # ascending
+
+
+def test_tc_scan_more_flagged_queries_than_one_fallback_chunk():
+    """200 NaN queries (> one 64-query fallback chunk): every one of them is resolved by the in-stream fp32 scan."""
+    rng = np.random.default_rng(8)
+    data = datasets.unit_vectors(rng, 9000, 64)
+    q = datasets.unit_vectors(rng, 400, 64)
+    q[::2, 3] = np.nan
+    st = store(data)
+    ids, d = st.search_exact(q, 10)
+    c = last_counters()
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 10, mode="prepared")
+    assert c["fallback_queries"] == 200
+    assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
