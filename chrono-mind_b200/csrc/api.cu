@@ -252,7 +252,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   uint8_t* small = ws->small.as<uint8_t>();
   CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
   CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));
-  CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, s));
+  CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, nullptr, false, s));
   ScanTcLaunch sl;
   sl.q_bf16 = ws->qbf16.p;
   sl.nq = nq;
@@ -659,11 +659,6 @@ cm_status cm_index_upload(cm_index* idx, int device) {
     CM_CUDA(cudaMemcpy2D(d.x32, (size_t)d.dim_pad * 4, idx->x.data(), (size_t)d.dim * 4, (size_t)d.dim * 4, n,
                          cudaMemcpyHostToDevice));
   }
-  // bf16 copy for the tensor-core scan, padded to whole tiles (zero rows/columns score 0 and are masked by id).
-  d.n_pad = scan_tc_pad_rows(std::max<uint64_t>(n, 1));
-  d.k_pad = scan_tc_pad_k(d.dim);
-  CM_CUDA(cudaMalloc(&d.xbf16, d.n_pad * d.k_pad * 2));
-  CM_CUDA(launch_to_bf16(d.x32, n, d.dim, d.dim_pad, d.xbf16, d.n_pad, d.k_pad, nullptr));
   CM_CUDA(cudaMalloc(&d.deleted, rows));
   CM_CUDA(cudaMalloc(&d.ts_secs, rows * 8));
   CM_CUDA(cudaMalloc(&d.ts_nanos, rows * 4));
@@ -674,6 +669,11 @@ cm_status cm_index_upload(cm_index* idx, int device) {
     CM_CUDA(cudaMemcpy(d.ts_nanos, idx->ts_nanos.data(), n * 4, cudaMemcpyHostToDevice));
     CM_CUDA(cudaMemcpy(d.decay, idx->decay.data(), n * 4, cudaMemcpyHostToDevice));
   }
+  // bf16 copy for the tensor-core scan, padded to whole tiles; tombstoned and padding rows are NaN-masked.
+  d.n_pad = scan_tc_pad_rows(std::max<uint64_t>(n, 1));
+  d.k_pad = scan_tc_pad_k(d.dim);
+  CM_CUDA(cudaMalloc(&d.xbf16, d.n_pad * d.k_pad * 2));
+  CM_CUDA(launch_to_bf16(d.x32, n, d.dim, d.dim_pad, d.xbf16, d.n_pad, d.k_pad, n ? d.deleted : nullptr, true, nullptr));
   const Graph& g = idx->graph;
   d.has_graph = g.built;
   if (g.built) {

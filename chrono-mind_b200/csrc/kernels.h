@@ -16,8 +16,9 @@ cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uin
                                    uint32_t ld_out, uint32_t* bad_row, cudaStream_t s);
 
 // fp32 -> bf16 copy of prepared rows into the tensor-core scan layout [n_pad][k_pad] (zero padded).
+// mask_rows (corpus copies): tombstoned rows (deleted[row] != 0) and padding rows score NaN in the scan.
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
-                           uint32_t k_pad, cudaStream_t s);
+                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s);
 
 // distance_prepared for n row pairs (src/metric.rs:219-224).
 cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,

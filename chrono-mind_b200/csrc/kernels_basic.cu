@@ -70,10 +70,13 @@ cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uin
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fp32 -> bf16 (round to nearest even) into the scan layout.
+// fp32 -> bf16 (round to nearest even) into the scan layout. With mask_rows set (corpus copies), tombstoned
+// rows and the padding rows past n get a NaN in column 0: their tensor-core score is NaN, which never passes
+// a threshold (`s >= tau` is false) and is dropped by fmaxf — the scan needs no per-row liveness lookup.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_to_bf16(const float* __restrict__ x, uint64_t n, uint32_t dim, uint32_t ld_in,
-                          __nv_bfloat16* __restrict__ out, uint64_t n_pad, uint32_t k_pad) {
+                          __nv_bfloat16* __restrict__ out, uint64_t n_pad, uint32_t k_pad,
+                          const uint8_t* __restrict__ deleted, int mask_rows) {
   uint64_t total = n_pad * (uint64_t)(k_pad / 2);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t row = i / (k_pad / 2);
@@ -83,14 +86,15 @@ __global__ void k_to_bf16(const float* __restrict__ x, uint64_t n, uint32_t dim,
       if (c < dim) a = x[row * ld_in + c];
       if (c + 1 < dim) b = x[row * ld_in + c + 1];
     }
+    if (mask_rows && c == 0 && (row >= n || (deleted && deleted[row]))) a = __int_as_float(0x7FC00000);
     reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
   }
 }
 
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
-                           uint32_t k_pad, cudaStream_t s) {
+                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s) {
   if (n_pad == 0) return cudaSuccess;
-  k_to_bf16<<<148 * 8, 256, 0, s>>>(x, n, dim, ld_in, (__nv_bfloat16*)out, n_pad, k_pad);
+  k_to_bf16<<<148 * 8, 256, 0, s>>>(x, n, dim, ld_in, (__nv_bfloat16*)out, n_pad, k_pad, deleted, mask_rows ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }

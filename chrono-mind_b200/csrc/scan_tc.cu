@@ -90,9 +90,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// arrive on a barrier of any CTA of the cluster (shared::cluster address)
+// arrive on a barrier of any CTA of the cluster (shared::cluster address). CTA-scope release: what the
+// waiter consumes is TMEM, ordered by tcgen05.wait::ld + tcgen05.fence, not generic memory — a cluster-scope
+// release would drain every outstanding candidate store first (MEMBAR.ALL.GPU + ERRBAR).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 // Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -172,10 +174,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// r[i] for a run-time i without spilling r[] to local memory: a 5-level select tree (31 selects).
+__device__ __forceinline__ float pick32(const uint32_t (&r)[32], uint32_t i) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = (i & 1) ? r[2 * j + 1] : r[2 * j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c[j] = (i & 4) ? b[2 * j + 1] : b[2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) d[j] = (i & 8) ? c[2 * j + 1] : c[2 * j];
+  return __uint_as_float((i & 16) ? d[1] : d[0]);
+}
+
 struct ScanArgs {
   uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, stages;
-  uint64_t n;
-  const uint8_t* deleted;
   uint32_t* tau_key;             // [m_pairs*256] ordered-uint threshold per query (0 = none yet)
   uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
   unsigned long long* cand;      // [m_pairs*256][cap]  (ordered score key << 32 | row); 0 = unused slot
@@ -362,7 +376,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint64_t row0 = (uint64_t)t * BN;
         bool improved = false;
         // Cold start (no threshold yet): first build the running top-k from this tile WITHOUT emitting, so the
-        // main pass below emits ~k rows instead of all 256.
+        // main pass below emits ~k rows instead of all 256. Tombstoned and padding rows score NaN (see
+        // launch_to_bf16) and never enter a list or pass a threshold.
         const bool cold = q_valid && tau == -INFINITY;
         bool listed = false;  // this tile's rows are already in the running top-k
         if (__any_sync(0xFFFFFFFFu, cold)) {
@@ -376,8 +391,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float s = __uint_as_float(r[i]);
-                const uint64_t row = row0 + c + i;
-                if (s == s && row < a.n && !(a.deleted && a.deleted[row])) top.insert(s);
+                if (s == s) top.insert(s);
               }
             }
           }
@@ -389,36 +403,50 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
           }
         }
-#pragma unroll 1
-        for (uint32_t c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          __syncwarp();  // the slow path below diverges; tcgen05.ld is warp-collective
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
-          float mx = __uint_as_float(r[0]);
+        // Main pass, software pipelined: the next 32 columns are in flight while this chunk is filtered.
+        auto filter_chunk = [&](const uint32_t (&r)[32], uint32_t c) {
+          float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          if (mx >= tau) {
+          for (int i = 2; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));  // fmaxf drops NaN
+          if (mx >= tau) {  // rare: ~1e-4 of the scores reach a converged threshold
+            uint32_t mask = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float s = __uint_as_float(r[i]);
-              if (s >= tau) {
-                const uint64_t row = row0 + c + i;
-                if (row < a.n && !(a.deleted && a.deleted[row])) {
-                  if (slots_left == 0) {
-                    slot_next = atomicAdd(&a.cand_cnt[q], kSlotChunk);
-                    slots_left = kSlotChunk;
-                  }
-                  if (slot_next < a.cap) my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)row;
-                  ++slot_next;
-                  --slots_left;
-                  if (!listed && top.insert(s)) {
-                    improved = true;
-                    tau = fmaxf(tau, top.kth - 2.0f * kEps);
-                  }
+            for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[i]) >= tau) ? (1u << i) : 0u;
+            while (mask) {
+              const uint32_t i = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float s = pick32(r, i);
+              if (s >= tau) {  // tau may have risen inside this loop
+                if (slots_left == 0) {
+                  slot_next = atomicAdd(&a.cand_cnt[q], kSlotChunk);
+                  slots_left = kSlotChunk;
+                }
+                if (slot_next < a.cap)
+                  my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)(row0 + c + i);
+                ++slot_next;
+                --slots_left;
+                if (!listed && top.insert(s)) {
+                  improved = true;
+                  tau = fmaxf(tau, top.kth - 2.0f * kEps);
                 }
               }
             }
+          }
+        };
+        {
+          uint32_t ra[32], rb[32];
+          __syncwarp();
+          tmem_ld32(taddr, ra);
+#pragma unroll 1
+          for (uint32_t c = 0; c < BN; c += 64) {
+            tmem_ld_wait();
+            __syncwarp();  // filter_chunk diverges; tcgen05.ld is warp-collective
+            tmem_ld32(taddr + c + 32, rb);
+            filter_chunk(ra, c);
+            tmem_ld_wait();
+            __syncwarp();
+            if (c + 64 < BN) tmem_ld32(taddr + c + 64, ra);
+            filter_chunk(rb, c + 32);
           }
         }
         // accumulator drained: hand it back to the MMA warp of the leader CTA
@@ -631,8 +659,6 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.k_blocks = ix.k_pad / BK;
   a.k = l.k;
   a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters);
-  a.n = ix.n;
-  a.deleted = ix.deleted;
   a.tau_key = l.tau_key;
   a.cand_cnt = l.cand_cnt;
   a.cand = l.cand;
