@@ -139,6 +139,136 @@ def _preprocess_mt(corpus, threads):
     return oracle.preprocess_rows(corpus, threads=threads)
 
 
+def run_hnsw(args, rank, world, local_rank):
+    """BASELINE configs[2]: batched HNSW search (one CTA per query) + fused temporal rerank, w = 0.3, on the graph the
+    host builder constructs over the synthetic corpus (the snapshot carries no graph). value = queries/s
+    of `VectorIndex::search(q, ef)` + take(10) at --ef with recall@10 against the exact scan reported beside it."""
+    import torch
+    from chronomind_b200 import datasets, engine
+    from chronomind_b200.engine import ChronoMindB200, default_config
+    assert world == 1, "the hnsw workload is single-GPU in this round (the sharded exact path is --workload exact)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n_rows, nq = args.rows, args.queries
+    efs = sorted({int(e) for e in args.efs.split(",")} | {args.ef})
+    if args.data == "emb":
+        corpus, queries_all = make_data(n_rows, nq * 2)
+    else:
+        corpus, queries_all = datasets.uniform_dataset(n_rows, nq * 2, DIM, SEED)
+    now = (1_790_000_000, 0)
+    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, now[0])
+    cfg = default_config(dimensions=DIM, ef_construction=args.efc)
+    threads = os.cpu_count() or 1
+    st = ChronoMindB200.from_matrix(corpus, cfg, ts_s, ts_n, decay)
+    t0 = time.time()
+    st.build_graph(SEED, threads)
+    build_s = time.time() - t0
+    log("[bench] host graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
+        % (n_rows, args.efc, threads, build_s, n_rows / build_s, st.check_invariants()))
+    st.upload(local_rank)
+    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(2)]
+    q_dev = [q.to(dev) for q in q_host]
+    ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    truth = [st.search_exact_cuda(q, K)[0].cpu().numpy().view(np.uint32) for q in q_dev]   # exact ground truth
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+
+    def recall(got, want):
+        return float(np.mean([len(set(a) & set(b)) / K for a, b in zip(got.tolist(), want.tolist())]))
+
+    per_ef, head = {}, None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for ef in efs:
+        for i in range(args.warmup):
+            st.search_index_cuda(q_dev[i % 2], ef, K, ids_l, dist_l)
+        torch.cuda.synchronize()
+        engine.profile_enable(True)
+        engine.profile_read()
+        launches0 = engine.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            st.search_index_cuda(q_dev[(args.warmup + i) % 2], ef, K, ids_l, dist_l)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = engine.launch_count() - launches0
+        kernel_ms, kernel_n = engine.profile_read()
+        engine.profile_enable(False)
+        last = (args.warmup + args.steps - 1) % 2
+        got = ids_l.cpu().numpy().view(np.uint32)
+        # work counters (== the CPU oracle's at equal ef on the same graph: tests/test_gpu_parity.py) and the e2e leg
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            hid, hsc = st.search(q_host[i % 2].numpy(), K, now=now, ef_search=ef, temporal_weight=0.3)
+        e2e_s = time.perf_counter() - t0
+        st.search_index(q_host[last].numpy(), ef, K)
+        c = engine.last_counters()
+        bytes_per_batch = c["dist_evals"] * DIM * 4 + c["list_entries"] * 4 + nq * DIM * 4
+        kern_avg = kernel_ms / max(kernel_n, 1)
+        r = {"ef": ef, "qps": nq * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "recall_at_10": recall(got, truth[last]),
+             "dist_evals_per_query": c["dist_evals"] / nq, "expansions_per_query": c["expansions"] / nq,
+             "algorithmic_bytes_per_query": bytes_per_batch / nq, "kernel_ms_avg": kern_avg,
+             "achieved_gbs": bytes_per_batch / (kern_avg * 1e-3) / 1e9 if kern_avg > 0 else None,
+             "hbm_frac": bytes_per_batch / (kern_avg * 1e-3) / 1e9 / hbm_peak if kern_avg > 0 else None,
+             "temporal_e2e_qps": nq * args.steps / e2e_s, "gpu_launches": launches, "visited_table_restarts": c["fallback_queries"]}
+        per_ef[str(ef)] = r
+        log("[bench] hnsw ef=%d: %s" % (ef, json.dumps(r)))
+        if ef == args.ef:
+            head = r
+    clocks = sampler.stop()
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        import tempfile
+        t0 = time.time()
+        sample = args.cpu_sample or 64 * threads
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "graph.cmg")
+            st.save_graph(path)
+            g = oracle.read_graph_sidecar(path)
+        orc = oracle.OracleHnsw(16, args.efc, 50, SEED)
+        orc.import_graph(_preprocess_mt(corpus, threads), g)
+        qs = queries_all[:sample]
+        orc.search_batch(qs, args.ef, K, threads=threads)
+        best = None
+        for _ in range(3):                                   # best_qps (benches/external.rs:118-124)
+            t1 = time.perf_counter()
+            oi, od, _, octr = orc.search_batch(qs, args.ef, K, threads=threads)
+            dt = time.perf_counter() - t1
+            best = dt if best is None else min(best, dt)
+        gi, gd = st.search_index(qs, args.ef, K)
+        parity = bool(np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32)))
+        cpu = {"value": sample / best, "unit": "queries/s", "cores": threads, "kind": "port",
+               "sample": "%d queries, ef=%d, same graph (sidecar import), best of 3 passes (%.2fs each)" % (sample, args.ef, best),
+               "parity_on_sample": parity, "dist_evals_per_query": float(octr[0]) / sample}
+        log("[bench] cpu baseline in %.1fs: %s" % (time.time() - t0, cpu))
+    line = {
+        "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": head["qps"], "unit": "queries/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, ef=%d, M=16 efC=%d host-built graph "
+                               "(BASELINE configs[2]); temporal rerank w=0.3 in the e2e leg" % (n_rows, DIM, args.data, nq, K, args.ef, args.efc),
+                   "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build_s": build_s, "build_threads": threads,
+                   "l2": "3.07 GB fp32 corpus gathered at random: larger than L2; 2 query batches rotated"},
+        "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
+        "gpu_launches": head["gpu_launches"],
+        "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
+                     "traffic": None, "kernel": "k_hnsw_search", "kernel_ms_avg": head["kernel_ms_avg"],
+                     "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
+        "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +280,12 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 fp32 CUDA-core scan, 2 tcgen05 scan + rescore")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0: 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="exact", choices=["exact", "hnsw"],
+                    help="exact: BASELINE configs[1] (the metric's workload); hnsw: configs[2], batched HNSW + temporal rerank")
+    ap.add_argument("--ef", type=int, default=128, help="hnsw: the ef the headline value is quoted at")
+    ap.add_argument("--efs", default="64,128,200", help="hnsw: every ef measured (reported under config.per_ef)")
+    ap.add_argument("--efc", type=int, default=100, help="hnsw: ef_construction of the host-built graph")
+    ap.add_argument("--data", default="emb", choices=["emb", "uniform"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -157,6 +293,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "hnsw":
+        run_hnsw(args, rank, world, local_rank)
         return
 
     import torch
