@@ -300,7 +300,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from chronomind_b200 import engine
+    from chronomind_b200 import engine, sharding
     from chronomind_b200.engine import ChronoMindB200, default_config
 
     if not torch.cuda.is_available():
@@ -314,7 +314,7 @@ def main():
 
     n_rows, nq = args.rows, args.queries
     corpus, queries_all = make_data(n_rows, nq * QUERY_BATCHES)
-    shard = np.ascontiguousarray(corpus[rank::world]) if world > 1 else corpus
+    shard = sharding.shard_rows(corpus, rank, world)
     t0 = time.time()
     st = ChronoMindB200.from_matrix(shard, default_config(dimensions=DIM)).set_shard(rank, world).upload(local_rank)
     st.set_exact_engine(args.engine)
@@ -324,9 +324,6 @@ def main():
     q_dev = [q.to(dev) for q in q_host]
     ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
     dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    if world > 1:
-        ids_g = torch.empty((world, nq, K), dtype=torch.int32, device=dev)
-        dist_g = torch.empty((world, nq, K), dtype=torch.float32, device=dev)
     out_ids_host = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     out_dist_host = torch.empty((nq, K), dtype=torch.float32).pin_memory()
 
@@ -334,8 +331,7 @@ def main():
         """Inputs resident in HBM; result stays on the device."""
         st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_l, dist_l)
         if world > 1:
-            dist.all_gather_into_tensor(ids_g, ids_l)
-            dist.all_gather_into_tensor(dist_g, dist_l)
+            ids_g, dist_g = sharding.allgather_lists(ids_l, dist_l)
             return engine.merge_topk_cuda(ids_g, dist_g, K)
         return ids_l, dist_l
 
@@ -345,8 +341,7 @@ def main():
             return st.search_exact(q_host[i % QUERY_BATCHES].numpy(), K)
         qd = q_host[i % QUERY_BATCHES].to(dev, non_blocking=True)
         st.search_exact_cuda(qd, K, ids_l, dist_l)
-        dist.all_gather_into_tensor(ids_g, ids_l)
-        dist.all_gather_into_tensor(dist_g, dist_l)
+        ids_g, dist_g = sharding.allgather_lists(ids_l, dist_l)
         mi, md = engine.merge_topk_cuda(ids_g, dist_g, K)
         out_ids_host.copy_(mi, non_blocking=True)
         out_dist_host.copy_(md, non_blocking=True)
@@ -409,7 +404,7 @@ def main():
         except Exception:
             pass
         counters = engine.last_counters()                      # of the last host-buffer call (the e2e leg)
-        tc = bool(counters.get("rescored", 0)) or args.engine == 2
+        tc = counters.get("exact_engine") == 2
         unresolved = int((dev_ids[:, 0] == 0xFFFFFFFF).sum() + np.isnan(dev_dist[:, 0]).sum())
         log("[bench] counters of the last e2e call: %s; unresolved rows in the timed device result: %d" % (counters, unresolved))
         flops_per_launch = 2.0 * nq * (n_rows / world) * DIM * args.steps / max(kernel_n, 1)

@@ -47,7 +47,8 @@ class Config(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("dist_evals", C.c_uint64), ("expansions", C.c_uint64), ("list_entries", C.c_uint64),
-                ("rescored", C.c_uint64), ("fallback_queries", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("rescored", C.c_uint64), ("fallback_queries", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("exact_engine", C.c_uint64)]
 
 
 _lib = None

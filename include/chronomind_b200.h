@@ -72,9 +72,11 @@ typedef struct {
   uint64_t dist_evals;      /* distance_prepared evaluations (HNSW) or nq*N (exact) */
   uint64_t expansions;      /* neighbor lists walked */
   uint64_t list_entries;    /* neighbor ids read */
-  uint64_t rescored;        /* fp32 rescore candidates (tensor-core scan) */
-  uint64_t fallback_queries; /* queries re-run through the fp32 scan because the bf16 pool could not prove exactness */
+  uint64_t rescored;        /* fp32 rescore candidates (tensor-core scan); host-buffer calls only */
+  uint64_t fallback_queries; /* queries re-run through the fp32 scan because the bf16 pool could not prove exactness
+                                (host-buffer calls only: the _dev variants never synchronise to read it back) */
   uint64_t kernel_launches; /* kernels launched by this call */
+  uint64_t exact_engine;    /* exact search: 1 = fp32 CUDA-core scan, 2 = tcgen05 scan + fp32 rescore; 0 otherwise */
 } cm_counters;
 
 #define CM_MAX_K 1024u  /* largest k / ef the select kernels accept */
