@@ -5,6 +5,8 @@
 // in scan_tc.cu and the graph traversal in hnsw_search.cu.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -12,42 +14,57 @@ namespace cm {
 
 // ---------------------------------------------------------------------------------------------------------
 // K0 preprocess — CosineDistance::preprocess (src/metric.rs:208-214).
-// One warp owns 32 rows. Tiles of 32x32 floats are staged through shared memory so that global reads are
-// coalesced while each lane still walks ITS row sequentially: s += x*x with a separately rounded multiply and
-// add, exactly like the reference's scalar `map(|x| x * x).sum()`.
+// One CTA (8 warps) owns 32 rows. Tiles of 32 rows x 32 columns are staged through shared memory by all 8 warps
+// (coalesced 128-byte reads, 4 rows per warp in flight at once), then lane r of warp 0 walks ITS row of the
+// tile sequentially: s += x*x with a separately rounded multiply and add, exactly like the reference's scalar
+// `map(|x| x * x).sum()`. The division pass is again spread over the 8 warps.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_preprocess_rows(const float* __restrict__ x, uint64_t n, uint32_t dim,
-                                                        uint32_t ld_in, float* __restrict__ out, uint32_t ld_out,
-                                                        uint32_t* bad_row) {
-  __shared__ float tile[32][33];
+constexpr int PP_THREADS = 256;
+
+__global__ void __launch_bounds__(PP_THREADS) k_preprocess_rows(const float* __restrict__ x, uint64_t n, uint32_t dim,
+                                                                uint32_t ld_in, float* __restrict__ out,
+                                                                uint32_t ld_out, uint32_t* bad_row) {
+  __shared__ float tile[2][32][33];
   __shared__ float norms[32];
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t row0 = (uint64_t)blockIdx.x * 32;
   float s = 0.0f;
-  for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
-    for (uint32_t r = 0; r < 32; ++r) {
-      uint64_t row = row0 + r;
-      uint32_t c = c0 + lane;
+  auto load_tile = [&](uint32_t c0, int buf) {
+#pragma unroll
+    for (uint32_t rr = 0; rr < 4; ++rr) {
+      const uint32_t r = warp * 4 + rr;
+      const uint64_t row = row0 + r;
+      const uint32_t c = c0 + lane;
       float v = (row < n && c < dim) ? x[row * ld_in + c] : 0.0f;
       // validate_query (src/store.rs:386-390): remember the first row with a NaN/Inf component.
       if (bad_row && !isfinite(v)) atomicMin(bad_row, (uint32_t)row);
-      tile[r][lane] = v;
+      tile[buf][r][lane] = v;
     }
-    __syncwarp();
-    uint32_t lim = min(32u, dim - c0);
-    for (uint32_t c = 0; c < lim; ++c) {
-      float v = tile[lane][c];
-      s = __fadd_rn(s, __fmul_rn(v, v));
+  };
+  int buf = 0;
+  if (dim) load_tile(0, 0);
+  __syncthreads();
+  for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
+    if (c0 + 32 < dim) load_tile(c0 + 32, buf ^ 1);  // next tile in flight while warp 0 walks this one
+    if (warp == 0) {
+      const uint32_t lim = min(32u, dim - c0);
+      for (uint32_t c = 0; c < lim; ++c) {
+        const float v = tile[buf][lane][c];
+        s = __fadd_rn(s, __fmul_rn(v, v));
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    buf ^= 1;
   }
-  norms[lane] = __fsqrt_rn(s);
-  __syncwarp();
-  for (uint32_t r = 0; r < 32; ++r) {
-    uint64_t row = row0 + r;
-    if (row >= n) break;
-    float nr = norms[r];
-    bool degenerate = nr <= 1.1920929e-7f;  // f32::EPSILON: left unchanged
+  if (warp == 0) norms[lane] = __fsqrt_rn(s);
+  __syncthreads();
+#pragma unroll
+  for (uint32_t rr = 0; rr < 4; ++rr) {
+    const uint32_t r = warp * 4 + rr;
+    const uint64_t row = row0 + r;
+    if (row >= n) continue;
+    const float nr = norms[r];
+    const bool degenerate = nr <= 1.1920929e-7f;  // f32::EPSILON: left unchanged
     for (uint32_t c = lane; c < ld_out; c += 32) {
       float v = 0.0f;
       if (c < dim) {
@@ -62,9 +79,9 @@ __global__ void __launch_bounds__(32) k_preprocess_rows(const float* __restrict_
 cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, float* out,
                                    uint32_t ld_out, uint32_t* bad_row, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  // In-place use is only safe when the strides match (each row is fully read before it is written by the
-  // same warp: reads happen in the first loop, writes in the second).
-  k_preprocess_rows<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(x, n, dim, ld_in, out, ld_out, bad_row);
+  // In-place use is only safe when the strides match: a CTA reads all of its 32 rows (first loop) before any of
+  // them is written (second loop, after a barrier), and no other CTA touches those rows.
+  k_preprocess_rows<<<(unsigned)((n + 31) / 32), PP_THREADS, 0, s>>>(x, n, dim, ld_in, out, ld_out, bad_row);
   count_launch();
   return cudaGetLastError();
 }
@@ -164,7 +181,9 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
   }
   __syncthreads();
 
-  const uint64_t row_base = (uint64_t)blockIdx.x * EX_ROWS;
+  const uint64_t n_row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
+  for (uint64_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
+  const uint64_t row_base = rb * EX_ROWS;
   for (uint32_t pass = 0; pass < EX_ROWS / 32; ++pass) {
     uint64_t row = row_base + pass * 32 + warp * 4 + rsub;
     bool valid = row < n;
@@ -205,6 +224,7 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
       if ((qi & 7) == (int)j && valid && qq < nq) D[(uint64_t)qq * ldD + row] = clamp02(__fsub_rn(1.0f, sum));
     }
   }
+  }
 }
 
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
@@ -220,7 +240,11 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
     attr_set = true;
   }
   // D rows are indexed by the query's position inside this launch.
-  dim3 grid((unsigned)((n + EX_ROWS - 1) / EX_ROWS), (nq + EX_QT - 1) / EX_QT);
+  // The in-stream fallback of the tensor-core scan (active_count != nullptr) is almost always empty: keep its
+  // grid small (row blocks are walked with a grid stride) so that an empty launch costs microseconds.
+  uint64_t row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
+  if (active_count) row_blocks = std::min<uint64_t>(row_blocks, 296);
+  dim3 grid((unsigned)row_blocks, (nq + EX_QT - 1) / EX_QT);
   k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base);
   count_launch();
   return cudaGetLastError();
