@@ -1,4 +1,4 @@
-// hnsw_search.cu — K3: batched HNSW search, one CTA per query.
+// hnsw_search.cu — K3: batched HNSW search, one small CTA (2 warps) per query.
 //
 // Replaces `LockFreeHnsw::search` (src/index/lockfree_hnsw.rs:469-495) and `search_layer` (:140-194) for a
 // batch of prepared queries over the frozen, flattened graph (padded CSR, see cm::DeviceIndex):
@@ -16,17 +16,26 @@
 //   * `visited` (HashSet<u32>) is an open-addressing table in shared memory, tagged with an 8-bit epoch so it
 //     never has to be cleared between layers or queries. Membership is exact. When a query would crowd the
 //     table past 3/4 the CTA restarts that query on a larger per-CTA table in global memory.
-//   * distance_prepared is evaluated bit-exactly: thread (n, j) of the CTA owns SIMD lane j of neighbor n,
-//     i.e. the reference's 8-lane FMA chain over elements j, j+8, ... (src/metric.rs:129-147); an octet reads
-//     one 32-byte sector per step, then the reference's reduction order and scalar tail.
+//   * the fresh neighbors' rows are GATHERED BY THE COPY ENGINE: one `cp.async.bulk` (UBLKCP) per row, issued by
+//     one thread each, lands the whole dim*4-byte row in shared memory and signals an mbarrier — all rows of a
+//     round (up to HN_ROWS x 3 KB) are in flight at once and cost no registers. (A register-staged gather keeps
+//     only ~8 loads per thread in flight: 12 dependent DRAM round trips per expansion, measured 18 us/expansion.)
+//   * distance_prepared is then evaluated bit-exactly out of shared memory: a QUAD of threads owns one row;
+//     thread c of the quad carries the reference's SIMD lanes 2c, 2c+1 (src/metric.rs:129-147), i.e. two FMA
+//     chains over elements 8t+2c, 8t+2c+1 (one LDS.64 per step; rows are padded by 32 bytes so the 8 rows of a
+//     warp hit distinct banks), then the reference's reduction order and scalar tail.
 //
-// Gather-bound: per expansion one 128-byte neighbor list and up to 32 rows of dim*4 bytes.
+// Gather-bound: per expansion one 128-byte neighbor list and up to 32 rows of dim*4 bytes. The traversal is a
+// dependent chain (pop -> list -> visited -> rows -> merge), so HBM is kept busy by bytes in flight per query
+// (bulk copies) times queries in flight (64-thread CTAs, ~70 KB of shared memory each, 3 per SM).
 #include "device_common.cuh"
 #include "kernels.h"
 
 namespace cm {
 
-constexpr int HN_THREADS = 256;
+constexpr int HN_THREADS = 64;
+constexpr uint32_t HN_ROWS = 16;       // rows staged per round (HN_THREADS / 4)
+constexpr uint32_t HN_ROW_PAD = 32;    // bytes; makes the row stride = 32 (mod 128): conflict-free LDS.64
 
 struct HnswKernelArgs {
   const float* x;
@@ -50,6 +59,7 @@ struct HnswKernelArgs {
 };
 
 struct HnShared {
+  unsigned long long mbar;   // completion barrier of the row copies
   unsigned long long cand[32];
   uint32_t fresh[32];
   uint32_t list_count;
@@ -92,28 +102,85 @@ __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t t
   }
 }
 
-// distance_prepared(x[id], q) by one octet; every lane of the octet returns the same bits.
-__device__ __forceinline__ float octet_distance(const HnswKernelArgs& a, const float* qs, uint32_t id, uint32_t j,
-                                                bool active) {
-  const uint32_t body = a.dim & ~7u;
-  const float* xr = a.x + (uint64_t)id * a.ldx;
-  float acc = 0.0f;
-  if (active && !a.degenerate) {
-#pragma unroll 8
-    for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(__ldg(xr + e), qs[e], acc);
+__device__ __forceinline__ uint32_t hn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Bounded wait on the copy barrier: a lost completion traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void hn_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
   }
-  float sum = octet_hsum(acc);
+}
+
+// Stage rows ids[0 .. cnt) (cnt <= HN_ROWS) into rowbuf with one bulk copy per row and wait for them.
+// Called by all threads; `phase` is each thread's private copy of the barrier parity.
+__device__ __forceinline__ void stage_rows(const HnswKernelArgs& a, HnShared* sh, unsigned char* rowbuf,
+                                           uint32_t row_stride, const uint32_t* ids, uint32_t cnt, uint32_t& phase) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t row_bytes = a.ldx * 4;  // multiple of 32
+  const uint32_t bar = hn_smem_u32(&sh->mbar);
+  if (!a.degenerate) {
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * row_bytes) : "memory");
+    if (tid < cnt) {
+      // rowbuf was last read through the generic proxy (before the preceding barrier): order those reads
+      // before the async-proxy writes of this copy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const float* src = a.x + (uint64_t)ids[tid] * a.ldx;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(hn_smem_u32(rowbuf + (size_t)tid * row_stride)), "l"(src), "r"(row_bytes), "r"(bar)
+          : "memory");
+    }
+    hn_mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+}
+
+// distance_prepared(row, q) out of shared memory by one thread quad; all four threads return the same bits.
+__device__ __forceinline__ float quad_distance(const HnswKernelArgs& a, const float* qs, const unsigned char* row,
+                                               uint32_t c, bool active) {
+  const uint32_t body = a.dim & ~7u;
+  const float* xr = reinterpret_cast<const float*>(row);
+  float a0 = 0.0f, a1 = 0.0f;  // SIMD lanes 2c, 2c+1 of the reference's accumulator
+  if (active && !a.degenerate) {
+    const float2* xv = reinterpret_cast<const float2*>(xr) + c;
+    const float2* qv = reinterpret_cast<const float2*>(qs) + c;
+#pragma unroll 8
+    for (uint32_t t = 0; t < body / 8; ++t) {
+      const float2 x = xv[4 * t];
+      const float2 q = qv[4 * t];
+      a0 = __fmaf_rn(x.x, q.x, a0);
+      a1 = __fmaf_rn(x.y, q.y, a1);
+    }
+  }
+  // (a0+a4, a1+a5, a2+a6, a3+a7) -> (s0+s2, s1+s3) -> t0+t1 (src/metric.rs:137-141). Thread c holds lanes
+  // (2c, 2c+1): lane j pairs with j+4 across threads c and c^2, then (s0,s1)|(s2,s3) across threads c and c^1.
+  // IEEE addition commutes, so all four threads end with the same bits.
+  const float s_lo = __fadd_rn(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, 2));
+  const float s_hi = __fadd_rn(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, 2));
+  const float t0 = __fadd_rn(s_lo, __shfl_xor_sync(0xFFFFFFFFu, s_lo, 1));  // s0 + s2
+  const float t1 = __fadd_rn(s_hi, __shfl_xor_sync(0xFFFFFFFFu, s_hi, 1));  // s1 + s3
+  float sum = __fadd_rn(t0, t1);
   if (active && !a.degenerate)
-    for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(__ldg(xr + e), qs[e]));
+    for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(xr[e], qs[e]));
   return a.degenerate ? 2.0f : clamp02(__fsub_rn(1.0f, sum));
 }
 
 // One search_layer call over shared state. `lists` holds two ping-pong buffers of `ef_cap` keys; returns which
 // one holds the result (ascending). All threads of the CTA call this.
 __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const float* qs, unsigned long long* lists,
-                                uint32_t ef_cap, const VisitedTable& vt, uint32_t ef, uint32_t layer, uint32_t ep) {
+                                uint32_t ef_cap, const VisitedTable& vt, uint32_t ef, uint32_t layer, uint32_t ep,
+                                unsigned char* rowbuf, uint32_t row_stride, uint32_t& phase) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_slot = tid >> 3, j = tid & 7;
+  const uint32_t r_slot = tid >> 2, c4 = tid & 3;
   const uint32_t cap = layer == 0 ? a.cap0 : a.capU;
   const uint32_t table_size = 1u << vt.bits;
   const uint32_t limit = (table_size >> 1) + (table_size >> 2);
@@ -139,7 +206,10 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
     sh->visited_count = 1;
   }
   {
-    float d = octet_distance(a, qs, ep, j, n_slot == 0);
+    if (tid == 0) sh->fresh[0] = ep;
+    __syncthreads();
+    stage_rows(a, sh, rowbuf, row_stride, sh->fresh, 1, phase);
+    float d = quad_distance(a, qs, rowbuf, c4, r_slot == 0);
     if (tid == 0) {
       lists[0] = make_key(d, ep);
       sh->list_count = 1;
@@ -206,14 +276,15 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
         __syncthreads();
         continue;
       }
-      // distances (:181): thread (n_slot, j) = SIMD lane j of fresh neighbor n_slot
-      {
-        const bool active = n_slot < m;
-        const uint32_t nb = active ? sh->fresh[n_slot] : 0;
-        float d = octet_distance(a, qs, nb, j, active);
-        if (active && j == 0) sh->cand[n_slot] = make_key(d, nb);
+      // distances (:181): rounds of up to HN_ROWS rows — bulk-copied to shared memory, one thread quad per row
+      for (uint32_t r0 = 0; r0 < m; r0 += HN_ROWS) {
+        const uint32_t cntr = min(HN_ROWS, m - r0);
+        stage_rows(a, sh, rowbuf, row_stride, sh->fresh + r0, cntr, phase);
+        const bool active = r_slot < cntr;
+        float d = quad_distance(a, qs, rowbuf + (size_t)r_slot * row_stride, c4, active);
+        if (active && c4 == 0) sh->cand[r0 + r_slot] = make_key(d, sh->fresh[r0 + r_slot]);
+        __syncthreads();  // cand visible to the merge; rowbuf free for the next round
       }
-      __syncthreads();
       // admit + evict (:182-189) as a merge by rank into the other buffer
       {
         const uint32_t cnt = sh->list_count;
@@ -258,14 +329,21 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   off += (size_t)2 * ef_cap * 8;
   uint32_t* stable = reinterpret_cast<uint32_t*>(smem_raw + off);
   off += (size_t)4 << a.hash_bits;
-  HnShared* sh = reinterpret_cast<HnShared*>(smem_raw + ((off + 15) & ~(size_t)15));
+  off = (off + 15) & ~(size_t)15;
+  HnShared* sh = reinterpret_cast<HnShared*>(smem_raw + off);
+  off = (off + sizeof(HnShared) + 127) & ~(size_t)127;
+  unsigned char* rowbuf = smem_raw + off;                 // HN_ROWS rows, 128-byte aligned
+  const uint32_t row_stride = a.ldx * 4 + HN_ROW_PAD;
 
   const uint32_t tid = threadIdx.x;
   for (uint32_t i = tid; i < (1u << a.hash_bits); i += HN_THREADS) stable[i] = 0;
   if (tid == 0) {
     sh->epoch = 0;
     sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hn_smem_u32(&sh->mbar)), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  uint32_t phase = 0;  // parity of the copy barrier (every thread waits on every round, so all copies agree)
   __syncthreads();
 
   for (;;) {
@@ -292,11 +370,11 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
 
       uint32_t ep = a.entry_id;
       for (uint32_t layer = a.entry_top; layer >= 1 && !sh->overflow; --layer) {  // descend_layer (:196-201)
-        int bb = search_layer_dev(a, sh, qs, lists, ef_cap, vt, 1, layer, ep);
+        int bb = search_layer_dev(a, sh, qs, lists, ef_cap, vt, 1, layer, ep, rowbuf, row_stride, phase);
         ep = key_handle(lists[(size_t)bb * ef_cap]);
         __syncthreads();
       }
-      if (!sh->overflow) b = search_layer_dev(a, sh, qs, lists, ef_cap, vt, a.ef, 0, ep);
+      if (!sh->overflow) b = search_layer_dev(a, sh, qs, lists, ef_cap, vt, a.ef, 0, ep, rowbuf, row_stride, phase);
       __syncthreads();
       if (!sh->overflow) break;
       if (use_global) {  // cannot happen for sane ef; reported, never silent
@@ -346,7 +424,9 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
 }
 
 static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits) {
-  return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + ((size_t)4 << hash_bits) + 16 + sizeof(HnShared);
+  const size_t dim_pad = (dim + 7) & ~7u;
+  return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + ((size_t)4 << hash_bits) + 16 + sizeof(HnShared) +
+         128 + (size_t)HN_ROWS * (dim_pad * 4 + HN_ROW_PAD);
 }
 
 cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid) {
