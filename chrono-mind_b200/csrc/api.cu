@@ -324,7 +324,8 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   }
   uint32_t hb = hash_bits_for(ef);
   unsigned grid = 0;
-  cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid);
+  uint32_t rows = 0;
+  cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid, &rows);
   if (ge != cudaSuccess) return fail(CM_ERR_INVALID_ARGUMENT, "ef / dim too large for the HNSW kernel's shared memory");
   CM_CUDA(ws->small.ensure(kSmallBytes));
   CM_CUDA(ws->gtable.ensure(((size_t)grid << kGHashBits) * 4));
@@ -343,6 +344,7 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   l.gtable = ws->gtable.as<uint32_t>();
   l.ghash_bits = kGHashBits;
   l.grid = grid;
+  l.rows = rows;
   {
     ProfileScope prof(s);
     CM_CUDA(launch_hnsw_search(d, l, s));

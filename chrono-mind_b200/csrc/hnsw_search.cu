@@ -28,13 +28,16 @@
 // Gather-bound: per expansion one 128-byte neighbor list and up to 32 rows of dim*4 bytes. The traversal is a
 // dependent chain (pop -> list -> visited -> rows -> merge), so HBM is kept busy by bytes in flight per query
 // (bulk copies) times queries in flight (64-thread CTAs, ~70 KB of shared memory each, 3 per SM).
+#include <algorithm>
+#include <cstdlib>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
 namespace cm {
 
 constexpr int HN_THREADS = 64;
-constexpr uint32_t HN_ROWS = 16;       // rows staged per round (HN_THREADS / 4)
+constexpr uint32_t HN_ROWS = 16;       // most rows staged per round (HN_THREADS / 4); the launcher may pick fewer
 constexpr uint32_t HN_ROW_PAD = 32;    // bytes; makes the row stride = 32 (mod 128): conflict-free LDS.64
 
 struct HnswKernelArgs {
@@ -56,6 +59,7 @@ struct HnswKernelArgs {
   uint32_t hash_bits;      // shared-memory table
   uint32_t* gtable;        // [gridDim.x] slabs of 1 << ghash_bits entries
   uint32_t ghash_bits;
+  uint32_t rows;           // rows staged per round, <= HN_ROWS
 };
 
 struct HnShared {
@@ -66,6 +70,7 @@ struct HnShared {
   uint32_t fresh_count;
   int cur_pos;
   uint32_t cur_id;
+  unsigned long long next_key;  // nearest unexpanded entry after the popped one (kKeyMax: none)
   uint32_t query;
   uint32_t visited_count;
   uint32_t overflow;
@@ -101,6 +106,8 @@ __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t t
     h = (h + 1) & mask;
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t hn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -233,13 +240,29 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
           break;
         }
       }
+      // The next pop is either the following unexpanded entry or a neighbor admitted by this expansion: start
+      // pulling the former's neighbor list into L2 now (the latter's follows once its distance is known).
+      unsigned long long nxt = kKeyMax;
+      if (pos >= 0 && layer == 0) {
+        for (uint32_t base = (uint32_t)pos + 1; base < cnt; base += 32) {
+          uint32_t i = base + lane;
+          bool un = i < cnt && !(L[i] & 1ull);
+          uint32_t m2 = __ballot_sync(0xFFFFFFFFu, un);
+          if (m2) {
+            nxt = L[base + __ffs(m2) - 1];
+            break;
+          }
+        }
+      }
       if (lane == 0) {
         sh->cur_pos = pos;
+        sh->next_key = nxt;
         if (pos >= 0) {
           sh->cur_id = key_handle(L[pos]);
           L[pos] |= 1ull;
           sh->ctr_exp += 1;
         }
+        if (nxt != kKeyMax) prefetch_l2(a.nbr0 + (uint64_t)key_handle(nxt) * a.cap0);
       }
     }
     __syncthreads();
@@ -277,13 +300,22 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
         continue;
       }
       // distances (:181): rounds of up to HN_ROWS rows — bulk-copied to shared memory, one thread quad per row
-      for (uint32_t r0 = 0; r0 < m; r0 += HN_ROWS) {
-        const uint32_t cntr = min(HN_ROWS, m - r0);
+      for (uint32_t r0 = 0; r0 < m; r0 += a.rows) {
+        const uint32_t cntr = min(a.rows, m - r0);
         stage_rows(a, sh, rowbuf, row_stride, sh->fresh + r0, cntr, phase);
         const bool active = r_slot < cntr;
         float d = quad_distance(a, qs, rowbuf + (size_t)r_slot * row_stride, c4, active);
         if (active && c4 == 0) sh->cand[r0 + r_slot] = make_key(d, sh->fresh[r0 + r_slot]);
         __syncthreads();  // cand visible to the merge; rowbuf free for the next round
+      }
+      if (warp == 0 && layer == 0) {  // nearest fresh neighbor pops before next_key: prefetch its list instead
+        unsigned long long best = lane < m ? sh->cand[lane] : kKeyMax;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+          best = other < best ? other : best;
+        }
+        if (lane == 0 && best < sh->next_key) prefetch_l2(a.nbr0 + (uint64_t)key_handle(best) * a.cap0);
       }
       // admit + evict (:182-189) as a merge by rank into the other buffer
       {
@@ -423,22 +455,35 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   }
 }
 
-static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits) {
+static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits, uint32_t rows) {
   const size_t dim_pad = (dim + 7) & ~7u;
   return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + ((size_t)4 << hash_bits) + 16 + sizeof(HnShared) +
-         128 + (size_t)HN_ROWS * (dim_pad * 4 + HN_ROW_PAD);
+         128 + (size_t)rows * (dim_pad * 4 + HN_ROW_PAD);
 }
 
-cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid) {
-  size_t smem = hnsw_smem_bytes(ix.dim, ef, hash_bits);
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+// Rows per round vs CTAs per SM: fewer rows per round leave shared memory for more queries in flight but add a
+// dependent copy round per expansion (an expansion evaluates ~17 of its 32 neighbors on average). Measured on
+// 1M x 768 (tools/diag_hnsw_rows.py, ms per 10k-query batch at rows = 16/14/12/10/8/6):
+//   ef=64: 11.3/9.4/9.9/9.1/8.5/8.9   ef=128: 21.2/22.1/23.2/19.0/20.2/19.5   ef=200: 46.6/48.0/50.1/37.3/40.6/45.7
+// => a ~32 KB row buffer (10 rows of 768 floats) is the sweet spot; small rows take the full 16.
+cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid, uint32_t* rows_out) {
   cudaError_t e = cudaFuncSetAttribute(k_hnsw_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) return e;
+  const uint32_t row_stride = ix.dim_pad * 4 + HN_ROW_PAD;
+  uint32_t rows = std::min(HN_ROWS, std::max(4u, (32u * 1024u) / row_stride));
+  if (const char* env = getenv("CM_HNSW_ROWS")) {  // experiments only
+    uint32_t forced = (uint32_t)atoi(env);
+    if (forced) rows = std::min(std::max(forced, 1u), HN_ROWS);
+  }
+  while (rows > 1 && hnsw_smem_bytes(ix.dim, ef, hash_bits, rows) > 220 * 1024) --rows;
+  const size_t smem = hnsw_smem_bytes(ix.dim, ef, hash_bits, rows);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hnsw_search, HN_THREADS, smem);
   if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  if (per_sm < 1) return cudaErrorInvalidValue;
   *grid = (unsigned)ix.sm_count * per_sm;
+  *rows_out = rows;
   return cudaSuccess;
 }
 
@@ -468,10 +513,11 @@ cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& l, cudaS
   a.hash_bits = l.hash_bits;
   a.gtable = l.gtable;
   a.ghash_bits = l.ghash_bits;
+  a.rows = l.rows;
   cudaError_t e = cudaMemsetAsync(l.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned grid = l.grid < l.nq ? l.grid : l.nq;
-  k_hnsw_search<<<grid, HN_THREADS, hnsw_smem_bytes(ix.dim, l.ef, l.hash_bits), s>>>(a);
+  k_hnsw_search<<<grid, HN_THREADS, hnsw_smem_bytes(ix.dim, l.ef, l.hash_bits, l.rows), s>>>(a);
   count_launch();
   return cudaGetLastError();
 }
