@@ -37,15 +37,59 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_data(n_rows, n_queries_total):
-    from chronomind_b200 import datasets
+def measured_traffic(kernel, **match):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+    except Exception:
+        return None
+    return t["dram_bytes_per_launch"] if all(t.get(k) == v for k, v in match.items()) else None
+
+
+def make_corpus(kind, n_rows):
+    from chronomind_b200.datasets import ChunkedCorpus
+    return ChunkedCorpus(kind, n_rows, DIM, SEED)
+
+
+def make_data(n_rows, n_queries_total, kind="emb", rank=0, world=1):
+    """(this rank's shard of the corpus, all queries, the corpus generator). Chunked generation: a rank never holds
+    more than its shard, a checker can stream the whole corpus."""
     t0 = time.time()
-    rng = np.random.default_rng(SEED)
-    basis = datasets.unit_vectors(rng, 16, DIM)
-    corpus = datasets.embedding_rows(rng, basis, n_rows)
-    queries = datasets.embedding_rows(np.random.default_rng(SEED ^ 0xFACE), basis, n_queries_total)
-    log("[bench] synthetic embedding-like data: corpus %s queries %s in %.1fs" % (corpus.shape, queries.shape, time.time() - t0))
-    return corpus, queries
+    gen = make_corpus(kind, n_rows)
+    shard = gen.shard(rank, world)
+    queries = gen.queries(n_queries_total)
+    log("[bench] synthetic %s data: shard %d/%d %s of %d rows, queries %s in %.1fs"
+        % ("embedding-like (16-d subspace)" if kind == "emb" else "uniform", rank, world, shard.shape, n_rows, queries.shape, time.time() - t0))
+    return shard, queries, gen
+
+
+def total_keys(dist, ids):
+    """(TotalF32, u32) tuples as sortable u64 keys (src/index/mod.rs:37-52; lockfree_hnsw.rs:149-150)."""
+    b = np.ascontiguousarray(dist, np.float32).view(np.uint32).astype(np.uint64)
+    k = np.where(b & np.uint64(0x80000000), ~b & np.uint64(0xFFFFFFFF), b | np.uint64(0x80000000))
+    return (k << np.uint64(32)) | ids.astype(np.uint64)
+
+
+def cpu_scan_streaming(gen, q, k, threads):
+    """The reference algorithm's CPU brute force (oracle, tests/property_test.rs:201-206 arithmetic, queries split
+    statically over `threads` like benches/comparison.rs:125-139) over the WHOLE corpus, streamed chunk by chunk so
+    the corpus never has to fit in host memory. Returns (ids, dist, seconds spent scanning)."""
+    import oracle
+    q = np.ascontiguousarray(q, np.float32)
+    best = None
+    scan_s = 0.0
+    for ci in range(gen.n_chunks):
+        prepared = oracle.preprocess_rows(gen.chunk(ci), threads=threads)   # the index stores preprocess()ed rows
+        t0 = time.perf_counter()
+        ids, d = oracle.brute_force(prepared, q, k, mode="prepared", threads=threads)
+        scan_s += time.perf_counter() - t0
+        keys = total_keys(d, ids.astype(np.uint64) + np.uint64(ci * gen.CHUNK))
+        best = keys if best is None else np.sort(np.concatenate([best, keys], axis=1), axis=1)[:, :k]
+    best = np.sort(best, axis=1)[:, :k]
+    out_ids = (best & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    kb = (best >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(kb & np.uint32(0x80000000), kb & np.uint32(0x7FFFFFFF), ~kb)
+    return out_ids, bits.astype(np.uint32).view(np.float32), scan_s
 
 
 class ClockSampler(threading.Thread):
@@ -81,53 +125,32 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
 
 
-def cpu_reference(corpus_prepared, queries, threads, sample_queries, steps=1, warmup=0):
-    """The reference algorithm's CPU scan (oracle brute force, tests/property_test.rs:201-206 arithmetic) on a bounded
-    query sample with all host threads; queries split statically (benches/comparison.rs:125-139). Returns
-    (qps, seconds per sample)."""
-    import oracle
-    q = np.ascontiguousarray(queries[:sample_queries])
-    for _ in range(warmup):
-        oracle.brute_force(corpus_prepared, q, K, mode="prepared", threads=threads)
-    best = None
-    for _ in range(max(1, steps)):
-        t0 = time.perf_counter()
-        oracle.brute_force(corpus_prepared, q, K, mode="prepared", threads=threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)          # best_qps, benches/external.rs:118-124
-    return sample_queries / best, best
-
-
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU form of the path. The Rust crate cannot be built in this image, so
+    this times the oracle port of its brute-force scan on all host threads, a bounded query sample per step."""
     if rank != 0:
         return
-    import oracle
     threads = os.cpu_count() or 1
     n_rows, nq = args.rows, args.queries
-    corpus, queries = make_data(n_rows, nq)
-    t0 = time.time()
-    prepared = _preprocess_mt(corpus, threads)      # the index stores preprocess()ed rows
-    log("[bench] reference: preprocess %.1fs" % (time.time() - t0))
+    gen = make_corpus(args.data, n_rows)
+    queries = gen.queries(nq)
     sample = min(args.cpu_sample or 2 * threads, nq)
-    t_all = []
-    for _ in range(args.warmup):
-        cpu_reference(prepared, queries, threads, sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_scan_streaming(gen, queries[:sample], K, threads)
+    total = 0.0
     for s in range(args.steps):
         q = queries[(s * sample) % max(1, nq - sample):][:sample]
-        t0 = time.perf_counter()
-        oracle.brute_force(prepared, np.ascontiguousarray(q), K, mode="prepared", threads=threads)
-        t_all.append(time.perf_counter() - t0)
-    total = sum(t_all)
+        total += cpu_scan_streaming(gen, q, K, threads)[2]
     qps = sample * args.steps / total
     line = {
         "impl": "reference", "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": qps,
         "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "exact brute-force kNN %dx%d cosine, %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, nq, K),
+        "config": {"workload": "exact brute-force kNN %dx%d cosine (%s), %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, args.data, nq, K),
                    "recall_at_10": 1.0, "engine": "CPU scan of the reference algorithm (oracle port, AVX2+FMA)"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": "%d queries per step x %d steps against the full %d x %d corpus" % (sample, args.steps, n_rows, DIM)},
+                         "sample": "%d queries per step x %d steps against the full %d x %d corpus (scan time only)" % (sample, args.steps, n_rows, DIM)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -151,10 +174,7 @@ def run_hnsw(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     n_rows, nq = args.rows, args.queries
     efs = sorted({int(e) for e in args.efs.split(",")} | {args.ef})
-    if args.data == "emb":
-        corpus, queries_all = make_data(n_rows, nq * 2)
-    else:
-        corpus, queries_all = datasets.uniform_dataset(n_rows, nq * 2, DIM, SEED)
+    corpus, queries_all, _ = make_data(n_rows, nq * 2, args.data)
     now = (1_790_000_000, 0)
     ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, now[0])
     cfg = default_config(dimensions=DIM, ef_construction=args.efc)
@@ -261,7 +281,9 @@ def run_hnsw(args, rank, world, local_rank):
         "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
         "gpu_launches": head["gpu_launches"],
         "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
-                     "traffic": None, "kernel": "k_hnsw_search", "kernel_ms_avg": head["kernel_ms_avg"],
+                     "traffic": measured_traffic("k_hnsw_search", rows=n_rows, queries=nq, n_gpus=1, data=args.data, ef=args.ef),
+                     "traffic_unit": "DRAM bytes per launch (ncu) vs algorithmic %d" % int(head["algorithmic_bytes_per_query"] * nq),
+                     "kernel": "k_hnsw_search", "kernel_ms_avg": head["kernel_ms_avg"],
                      "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
         "cpu_baseline": cpu, "clocks": clocks,
@@ -313,8 +335,7 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     n_rows, nq = args.rows, args.queries
-    corpus, queries_all = make_data(n_rows, nq * QUERY_BATCHES)
-    shard = sharding.shard_rows(corpus, rank, world)
+    shard, queries_all, gen = make_data(n_rows, nq * QUERY_BATCHES, args.data, rank, world)
     t0 = time.time()
     st = ChronoMindB200.from_matrix(shard, default_config(dimensions=DIM)).set_shard(rank, world).upload(local_rank)
     st.set_exact_engine(args.engine)
@@ -412,27 +433,28 @@ def main():
         achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "frac": (achieved / peak) if achieved else None,
+                    "traffic": measured_traffic("scan_tc_kernel", rows=n_rows, queries=nq, n_gpus=world, data=args.data) if tc else None,
+                    "traffic_unit": "DRAM bytes per launch (ncu); algorithmic minimum = one pass over the bf16 corpus + queries = %d" % (n_rows // world * DIM * 2 + nq * DIM * 2),
                     "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
                     "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback of B200_PROFILING.md"}
         cpu = None
         if not args.no_cpu_baseline:
-            import oracle
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or 2 * threads
             t0 = time.time()
-            prepared = _preprocess_mt(corpus, threads)
-            qps, secs = cpu_reference(prepared, queries_all, threads, sample, steps=2)
-            # parity of the TIMED device result (last step's batch) against the oracle on the sample
+            # the oracle's scan of the sample: the CPU number AND the parity check of the TIMED device result
+            # (last step's batch)
             qs = queries_all[last_batch * nq:last_batch * nq + sample]
-            wi, wd = oracle.brute_force(prepared, qs, K, mode="prepared", threads=threads)
+            wi, wd, secs = cpu_scan_streaming(gen, qs, K, threads)
+            qps = sample / secs
             gi, gd = dev_ids[:sample], dev_dist[:sample]
             parity = bool(np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)))
             recall = float(np.mean([len(set(a) & set(b)) / K for a, b in zip(gi.tolist(), wi.tolist())]))
             cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                   "sample": "%d of the %d queries against the full %dx%d corpus, best of 2 passes (%.1fs each)"
+                   "sample": "%d of the %d queries against the full %dx%d corpus, one pass (%.1fs of scan time)"
                              % (sample, nq, n_rows, DIM, secs), "parity_on_sample": parity,
                    "recall_at_10_on_sample": recall}
             log("[bench] cpu baseline in %.1fs" % (time.time() - t0))
@@ -441,12 +463,13 @@ def main():
             "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if tc else "f32", "data": "synthetic",
-            "config": {"workload": "exact brute-force kNN %dx%d cosine, %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, nq, K),
+            "config": {"workload": "exact brute-force kNN %dx%d cosine (%s data), %d-query batch, k=%d (BASELINE configs[%s])"
+                                   % (n_rows, DIM, args.data, nq, K, "1" if n_rows <= 1_000_000 else "3"),
                        "recall_at_10": (cpu or {}).get("recall_at_10_on_sample", "exact by construction (unchecked: --no-cpu-baseline)"),
                        "unresolved_queries": unresolved, "fallback_queries_e2e": counters.get("fallback_queries"),
                        "engine": "tcgen05 bf16 scan + fp32 rescore" if tc else "fp32 CUDA-core scan",
                        "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
-                       "l2": "inputs larger than L2: %.2f GB corpus streamed per step; %d query batches rotated" % (n_rows * DIM * 4 / 1e9, QUERY_BATCHES)},
+                       "l2": "inputs larger than L2: %.2f GB bf16 corpus per GPU streamed per step; %d query batches rotated" % (n_rows / world * DIM * 2 / 1e9, QUERY_BATCHES)},
             "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4,
                     "d2h_bytes_per_step": nq * K * 8},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

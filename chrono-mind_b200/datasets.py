@@ -55,3 +55,50 @@ def temporal_attrs(n: int, seed: int, now_secs: int, span_days: float = 30.0):
     rates = np.array([0.0, 0.0, 0.0, 0.0, 0.05, 0.1, 0.15, 0.2, 0.25], dtype=np.float32)
     decay = rates[rng.integers(0, len(rates), size=n)]
     return ts_secs, ts_nanos, decay
+
+
+class ChunkedCorpus:
+    """A deterministic synthetic corpus generated in independent chunks (one RNG stream per 65,536-row chunk), so
+    that a rank can materialise only ITS shard of a corpus larger than host memory (10M x 768 = 30.7 GB) and a
+    checker can stream the whole corpus without ever holding it. kind: "emb" (`embedded_vector`,
+    tests/recall_test.rs:52-67, one shared basis) or "uniform" (`unit_vector`, :38-47)."""
+
+    CHUNK = 65536
+
+    def __init__(self, kind: str, n_rows: int, dim: int, seed: int, intrinsic: int = 16, chunk: int = 65536):
+        assert kind in ("emb", "uniform")
+        self.CHUNK = int(chunk)
+        self.kind, self.n_rows, self.dim, self.seed = kind, int(n_rows), int(dim), int(seed)
+        self.basis = unit_vectors(np.random.default_rng([self.seed, 0xBA515]), intrinsic, dim) if kind == "emb" else None
+
+    @property
+    def n_chunks(self) -> int:
+        return (self.n_rows + self.CHUNK - 1) // self.CHUNK
+
+    def _rows(self, rng, n):
+        if self.kind == "emb":
+            coeff = rng.uniform(-1.0, 1.0, size=(n, self.basis.shape[0])).astype(np.float32)
+            return _normalise(coeff @ self.basis)
+        return unit_vectors(rng, n, self.dim)
+
+    def chunk(self, ci: int) -> np.ndarray:
+        """Rows [ci * CHUNK, min(n_rows, (ci + 1) * CHUNK))."""
+        n = min(self.CHUNK, self.n_rows - ci * self.CHUNK)
+        return self._rows(np.random.default_rng([self.seed, 1, ci]), n)
+
+    def shard(self, rank: int = 0, world: int = 1) -> np.ndarray:
+        """Rows with global id = rank (mod world), in id order (src/index/sharded_rwlock.rs:70-74)."""
+        n_local = (self.n_rows - rank + world - 1) // world
+        out = np.empty((n_local, self.dim), dtype=np.float32)
+        o = 0
+        for ci in range(self.n_chunks):
+            start = ci * self.CHUNK
+            first = (rank - start) % world                     # first row of this chunk that belongs to `rank`
+            rows = self.chunk(ci)[first::world]
+            out[o:o + rows.shape[0]] = rows
+            o += rows.shape[0]
+        assert o == n_local
+        return out
+
+    def queries(self, nq: int, stream: int = 0) -> np.ndarray:
+        return self._rows(np.random.default_rng([self.seed, 2, stream]), nq)

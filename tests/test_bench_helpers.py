@@ -1,0 +1,33 @@
+"""bench.py's host-side helpers: chunked corpus generation (shards == strided views of the whole) and the streaming
+CPU scan used as cpu_baseline / parity checker (== one oracle scan over the concatenated corpus)."""
+import numpy as np
+
+import bench
+import oracle
+from chronomind_b200.datasets import ChunkedCorpus
+
+
+def test_chunked_corpus_shards_partition_the_corpus():
+    for kind in ("emb", "uniform"):
+        gen = ChunkedCorpus(kind, 1000, 24, 5, chunk=128)
+        full = gen.shard()
+        assert full.shape == (1000, 24) and np.allclose(np.linalg.norm(full, axis=1), 1.0, atol=1e-5)
+        assert np.array_equal(full, np.vstack([gen.chunk(c) for c in range(gen.n_chunks)]))
+        for world in (2, 3, 8):
+            for rank in range(world):
+                assert np.array_equal(gen.shard(rank, world), full[rank::world])
+        assert np.array_equal(ChunkedCorpus(kind, 1000, 24, 5, chunk=128).queries(7), gen.queries(7))
+
+
+def test_streaming_cpu_scan_equals_one_scan():
+    gen = ChunkedCorpus("uniform", 700, 16, 9, chunk=100)
+    q = gen.queries(13)
+    ids, d, secs = bench.cpu_scan_streaming(gen, q, 10, threads=2)
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(gen.shard()), q, 10, mode="prepared")
+    assert np.array_equal(ids, wi) and np.array_equal(d.view(np.uint32), wd.view(np.uint32)) and secs > 0
+
+
+def test_total_keys_order_is_total_cmp():
+    d = np.array([[-0.0, 0.0, 1.5, -2.0, np.inf]], np.float32)
+    k = bench.total_keys(d, np.zeros_like(d, dtype=np.uint32))
+    assert list(np.argsort(k[0])) == [3, 0, 1, 2, 4]
