@@ -141,7 +141,7 @@ struct WorkspaceLease {
 
 constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited table: 128 Ki entries
 constexpr size_t kDistWorkspaceBytes = 1ull << 30;  // fp32 scan: distance block [QB][n] floats
-constexpr uint32_t kFlagCap = 1024;            // queries per call the in-stream fp32 fallback can absorb
+constexpr uint32_t kFlagCap = 512;             // queries per call the in-stream fp32 fallback can absorb
 constexpr uint32_t kFlagChunk = 64;            // ... in fp32 scans of this many queries (empty chunks exit at once)
 // ws->small layout (bytes): 0 HNSW counters (8 x u64) | 64 rescored_total u64 | 72 flag_count u32 |
 // 128 work_counter u32 | 192 bad_row u32 | 256 flag_list (kFlagCap x u32)

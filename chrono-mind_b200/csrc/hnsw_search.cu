@@ -33,12 +33,13 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "row_gather.cuh"
 
 namespace cm {
 
 constexpr int HN_THREADS = 64;
 constexpr uint32_t HN_ROWS = 16;       // most rows staged per round (HN_THREADS / 4); the launcher may pick fewer
-constexpr uint32_t HN_ROW_PAD = 32;    // bytes; makes the row stride = 32 (mod 128): conflict-free LDS.64
+constexpr uint32_t HN_ROW_PAD = RG_ROW_PAD;
 
 struct HnswKernelArgs {
   const float* x;
@@ -109,78 +110,6 @@ __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t t
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ uint32_t hn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Bounded wait on the copy barrier: a lost completion traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void hn_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 24)) __trap();
-  }
-}
-
-// Stage rows ids[0 .. cnt) (cnt <= HN_ROWS) into rowbuf with one bulk copy per row and wait for them.
-// Called by all threads; `phase` is each thread's private copy of the barrier parity.
-__device__ __forceinline__ void stage_rows(const HnswKernelArgs& a, HnShared* sh, unsigned char* rowbuf,
-                                           uint32_t row_stride, const uint32_t* ids, uint32_t cnt, uint32_t& phase) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t row_bytes = a.ldx * 4;  // multiple of 32
-  const uint32_t bar = hn_smem_u32(&sh->mbar);
-  if (!a.degenerate) {
-    if (tid == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * row_bytes) : "memory");
-    if (tid < cnt) {
-      // rowbuf was last read through the generic proxy (before the preceding barrier): order those reads
-      // before the async-proxy writes of this copy
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const float* src = a.x + (uint64_t)ids[tid] * a.ldx;
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-          ::"r"(hn_smem_u32(rowbuf + (size_t)tid * row_stride)), "l"(src), "r"(row_bytes), "r"(bar)
-          : "memory");
-    }
-    hn_mbar_wait(bar, phase);
-    phase ^= 1;
-  }
-}
-
-// distance_prepared(row, q) out of shared memory by one thread quad; all four threads return the same bits.
-__device__ __forceinline__ float quad_distance(const HnswKernelArgs& a, const float* qs, const unsigned char* row,
-                                               uint32_t c, bool active) {
-  const uint32_t body = a.dim & ~7u;
-  const float* xr = reinterpret_cast<const float*>(row);
-  float a0 = 0.0f, a1 = 0.0f;  // SIMD lanes 2c, 2c+1 of the reference's accumulator
-  if (active && !a.degenerate) {
-    const float2* xv = reinterpret_cast<const float2*>(xr) + c;
-    const float2* qv = reinterpret_cast<const float2*>(qs) + c;
-#pragma unroll 8
-    for (uint32_t t = 0; t < body / 8; ++t) {
-      const float2 x = xv[4 * t];
-      const float2 q = qv[4 * t];
-      a0 = __fmaf_rn(x.x, q.x, a0);
-      a1 = __fmaf_rn(x.y, q.y, a1);
-    }
-  }
-  // (a0+a4, a1+a5, a2+a6, a3+a7) -> (s0+s2, s1+s3) -> t0+t1 (src/metric.rs:137-141). Thread c holds lanes
-  // (2c, 2c+1): lane j pairs with j+4 across threads c and c^2, then (s0,s1)|(s2,s3) across threads c and c^1.
-  // IEEE addition commutes, so all four threads end with the same bits.
-  const float s_lo = __fadd_rn(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, 2));
-  const float s_hi = __fadd_rn(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, 2));
-  const float t0 = __fadd_rn(s_lo, __shfl_xor_sync(0xFFFFFFFFu, s_lo, 1));  // s0 + s2
-  const float t1 = __fadd_rn(s_hi, __shfl_xor_sync(0xFFFFFFFFu, s_hi, 1));  // s1 + s3
-  float sum = __fadd_rn(t0, t1);
-  if (active && !a.degenerate)
-    for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(xr[e], qs[e]));
-  return a.degenerate ? 2.0f : clamp02(__fsub_rn(1.0f, sum));
-}
-
 // One search_layer call over shared state. `lists` holds two ping-pong buffers of `ef_cap` keys; returns which
 // one holds the result (ascending). All threads of the CTA call this.
 __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const float* qs, unsigned long long* lists,
@@ -215,8 +144,8 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
   {
     if (tid == 0) sh->fresh[0] = ep;
     __syncthreads();
-    stage_rows(a, sh, rowbuf, row_stride, sh->fresh, 1, phase);
-    float d = quad_distance(a, qs, rowbuf, c4, r_slot == 0);
+    if (!a.degenerate) rg_stage_rows(a.x, a.ldx, &sh->mbar, rowbuf, row_stride, sh->fresh, 1, phase);
+    float d = a.degenerate ? 2.0f : rg_quad_distance(qs, rowbuf, a.dim, c4, r_slot == 0);
     if (tid == 0) {
       lists[0] = make_key(d, ep);
       sh->list_count = 1;
@@ -302,9 +231,9 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
       // distances (:181): rounds of up to HN_ROWS rows — bulk-copied to shared memory, one thread quad per row
       for (uint32_t r0 = 0; r0 < m; r0 += a.rows) {
         const uint32_t cntr = min(a.rows, m - r0);
-        stage_rows(a, sh, rowbuf, row_stride, sh->fresh + r0, cntr, phase);
+        if (!a.degenerate) rg_stage_rows(a.x, a.ldx, &sh->mbar, rowbuf, row_stride, sh->fresh + r0, cntr, phase);
         const bool active = r_slot < cntr;
-        float d = quad_distance(a, qs, rowbuf + (size_t)r_slot * row_stride, c4, active);
+        float d = a.degenerate ? 2.0f : rg_quad_distance(qs, rowbuf + (size_t)r_slot * row_stride, a.dim, c4, active);
         if (active && c4 == 0) sh->cand[r0 + r_slot] = make_key(d, sh->fresh[r0 + r_slot]);
         __syncthreads();  // cand visible to the merge; rowbuf free for the next round
       }
@@ -372,8 +301,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   if (tid == 0) {
     sh->epoch = 0;
     sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = 0;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hn_smem_u32(&sh->mbar)), "r"(1u) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    rg_mbar_init(&sh->mbar);
   }
   uint32_t phase = 0;  // parity of the copy barrier (every thread waits on every round, so all copies agree)
   __syncthreads();

@@ -233,11 +233,9 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
   if (nq == 0 || n == 0) return cudaSuccess;
   size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device, so set on every launch (microseconds)
     cudaError_t e = cudaFuncSetAttribute(k_exact_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   // D rows are indexed by the query's position inside this launch.
   // The in-stream fallback of the tensor-core scan (active_count != nullptr) is almost always empty: keep its
@@ -396,11 +394,9 @@ cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n
   uint32_t P = next_pow2(n_shards * len < 32 ? 32 : n_shards * len);
   size_t smem = (size_t)P * sizeof(unsigned long long);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device, so set on every launch (microseconds)
     cudaError_t e = cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   k_merge_topk<<<nq, 256, smem, s>>>(ids, dist, n_shards, nq, len, out_len, P, out_ids, out_dist);
   count_launch();

@@ -47,6 +47,7 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "row_gather.cuh"
 #include "scan_tc.h"
 
 namespace cm {
@@ -488,9 +489,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 //   3. evaluate distance_prepared exactly for that prefix (octet per candidate, reference lane order) and
 //      sort by (distance, handle).
 // ---------------------------------------------------------------------------------------------------------
-constexpr uint32_t RS_THREADS = 256;
-constexpr uint32_t RS_MAX = 4096;    // candidates above the final scan threshold handled per query
-constexpr uint32_t RS2_MAX = 1024;   // candidates re-scored per query
+constexpr uint32_t RS_THREADS = 64;
+constexpr uint32_t RS_ROWS = 16;     // rows gathered per copy round (RS_THREADS / 4)
+constexpr uint32_t RS2_MAX = 512;    // candidates re-scored per query
 
 struct RescoreArgs {
   const float* qn;
@@ -501,6 +502,7 @@ struct RescoreArgs {
   const uint32_t* cand_cnt;
   const unsigned long long* cand;
   uint32_t cap;
+  uint32_t rs_max;        // candidates above the final scan threshold handled per query (power of two)
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -510,29 +512,36 @@ struct RescoreArgs {
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
-  extern __shared__ __align__(16) unsigned char rs_smem[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);          // [RS_MAX] ~(score key, row)
-  unsigned long long* dkeys = keys + RS_MAX;                                           // [RS2_MAX] (distance, row)
-  float* qs = reinterpret_cast<float*>(dkeys + RS2_MAX);                               // [dim]
+  extern __shared__ __align__(128) unsigned char rs_smem[];
+  const uint32_t row_stride = a.ldx * 4 + RG_ROW_PAD;
+  unsigned char* rowbuf = rs_smem;                                                       // [RS_ROWS][row_stride]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rowbuf + (size_t)RS_ROWS * row_stride);  // [rs_max] ~(score key, row)
+  unsigned long long* dkeys = keys + a.rs_max;                                           // [RS2_MAX] (distance, row)
+  uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);                         // [RS2_MAX] rows to re-score
+  float* qs = reinterpret_cast<float*>(rows + RS2_MAX);                                  // [ldq]
+  __shared__ unsigned long long mbar;
   __shared__ uint32_t n_surv, n_keep;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t cnt_raw = a.cand_cnt[q];
   const uint32_t cnt = min(cnt_raw, a.cap);
   const uint32_t tk = a.tau_key[q];
-  if (tid == 0) n_surv = 0, n_keep = 0;
+  if (tid == 0) {
+    n_surv = 0, n_keep = 0;
+    rg_mbar_init(&mbar);
+  }
   for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.qn[(uint64_t)q * a.ldq + e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
     const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
     if (c != 0ull && (uint32_t)(c >> 32) >= tk) {
       uint32_t slot = atomicAdd(&n_surv, 1u);
-      if (slot < RS_MAX) keys[slot] = ~c;  // ascending sort of ~c == descending score
+      if (slot < a.rs_max) keys[slot] = ~c;  // ascending sort of ~c == descending score
     }
   }
   __syncthreads();
   const uint32_t ns = n_surv;
   const uint32_t need = (uint32_t)(a.n_live < a.k ? a.n_live : a.k);
-  bool bad = cnt_raw > a.cap || ns > RS_MAX || ns < need;
+  bool bad = cnt_raw > a.cap || ns > a.rs_max || ns < need;
   uint32_t keep = 0;
   if (!bad) {
     const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
@@ -562,24 +571,18 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   }
   const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
   for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
+  for (uint32_t i = tid; i < keep; i += RS_THREADS) rows[i] = (uint32_t)(~keys[i]);
   __syncthreads();
-  const uint32_t body = a.dim & ~7u;
-  const uint32_t j = tid & 7, oct = tid >> 3;
-  for (uint32_t base = 0; base < keep; base += RS_THREADS / 8) {
-    uint32_t i = base + oct;
-    bool active = i < keep;
-    uint32_t row = active ? (uint32_t)(~keys[i]) : 0;
-    const float* xr = a.x + (uint64_t)row * a.ldx;
-    float acc = 0.0f;
-    if (active) {
-#pragma unroll 8
-      for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(__ldg(xr + e), qs[e], acc);
-    }
-    float sum = octet_hsum(acc);
-    if (active) {
-      for (uint32_t e = body; e < a.dim; ++e) sum = __fadd_rn(sum, __fmul_rn(__ldg(xr + e), qs[e]));
-      if (j == 0) dkeys[i] = pack_key(clamp02(__fsub_rn(1.0f, sum)), row);
-    }
+  // exact distances: rounds of RS_ROWS rows, bulk-copied into shared memory, one thread quad per row
+  const uint32_t r_slot = tid >> 2, c4 = tid & 3;
+  uint32_t phase = 0;
+  for (uint32_t r0 = 0; r0 < keep; r0 += RS_ROWS) {
+    const uint32_t cntr = min(RS_ROWS, keep - r0);
+    rg_stage_rows(a.x, a.ldx, &mbar, rowbuf, row_stride, rows + r0, cntr, phase);
+    const bool active = r_slot < cntr;
+    const float d = rg_quad_distance(qs, rowbuf + (size_t)r_slot * row_stride, a.dim, c4, active);
+    if (active && c4 == 0) dkeys[r0 + r_slot] = pack_key(d, rows[r0 + r_slot]);
+    __syncthreads();  // rowbuf free for the next round; dkeys visible to the sort
   }
   block_bitonic_sort(dkeys, P2);
   for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
@@ -697,12 +700,12 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.flag_list = l.flag_list;
   a.flag_cap = l.flag_cap;
   a.rescored_total = l.rescored_total;
-  const size_t smem = (size_t)(RS_MAX + RS2_MAX) * 8 + (size_t)ix.dim * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  a.rs_max = l.k <= 16 ? 2048u : 4096u;
+  const size_t smem = (size_t)RS_ROWS * ((size_t)ix.dim_pad * 4 + RG_ROW_PAD) + (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 +
+                      (size_t)ix.dim_pad * 4;
+  {  // per device, so set on every launch (microseconds)
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   rescore_kernel<<<l.nq, RS_THREADS, smem, s>>>(a);
