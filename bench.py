@@ -163,34 +163,61 @@ def _preprocess_mt(corpus, threads):
 
 
 def run_hnsw(args, rank, world, local_rank):
-    """BASELINE configs[2]: batched HNSW search (one CTA per query) + fused temporal rerank, w = 0.3, on the graph the
-    host builder constructs over the synthetic corpus (the snapshot carries no graph). value = queries/s
-    of `VectorIndex::search(q, ef)` + take(10) at --ef with recall@10 against the exact scan reported beside it."""
+    """BASELINE configs[2]: batched HNSW search (one small CTA per query, rows gathered by the copy engine) + temporal
+    rerank, w = 0.3, on the graph the host builder constructs over the synthetic corpus (the snapshot carries no graph,
+    SURVEY.md F2).
+      value = queries/s of `VectorIndex::search(q, ef)` + take(10) at --ef, device resident, with recall@10 against the
+              exact scan reported beside it. N > 1: every rank searches ITS shard's graph (independent HNSW sub-graph per
+              shard, rows by id mod N), lists all-gathered over NCCL and merged by (distance, global handle).
+      e2e   = `ChronoMind::search` semantics with HOST buffers: H2D of the queries, HNSW pool of ef candidates,
+              (N > 1: all-gather + merge to the GLOBAL top-ef,) temporal rerank, D2H of [nq][10] handles and scores."""
     import torch
-    from chronomind_b200 import datasets, engine
+    import torch.distributed as dist
+    from chronomind_b200 import datasets, engine, sharding
     from chronomind_b200.engine import ChronoMindB200, default_config
-    assert world == 1, "the hnsw workload is single-GPU in this round (the sharded exact path is --workload exact)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     n_rows, nq = args.rows, args.queries
     efs = sorted({int(e) for e in args.efs.split(",")} | {args.ef})
-    corpus, queries_all, _ = make_data(n_rows, nq * 2, args.data)
+    shard, queries_all, gen = make_data(n_rows, nq * 2, args.data, rank, world)
     now = (1_790_000_000, 0)
-    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, now[0])
+    W, BASE = 0.3, 0.1
+    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, now[0])          # indexed by GLOBAL handle
     cfg = default_config(dimensions=DIM, ef_construction=args.efc)
-    threads = os.cpu_count() or 1
-    st = ChronoMindB200.from_matrix(corpus, cfg, ts_s, ts_n, decay)
+    threads = max(1, (os.cpu_count() or 1) // world)
+    st = ChronoMindB200.from_matrix(shard, cfg, sharding.shard_attrs(ts_s, rank, world), sharding.shard_attrs(ts_n, rank, world),
+                                    sharding.shard_attrs(decay, rank, world)).set_shard(rank, world)
     t0 = time.time()
-    st.build_graph(SEED, threads)
+    st.build_graph(SEED + rank, threads)
     build_s = time.time() - t0
-    log("[bench] host graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
-        % (n_rows, args.efc, threads, build_s, n_rows / build_s, st.check_invariants()))
+    log("[bench] rank %d host graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
+        % (rank, shard.shape[0], args.efc, threads, build_s, shard.shape[0] / build_s, st.check_invariants()))
     st.upload(local_rank)
+    g_ts_s = torch.from_numpy(ts_s.view(np.int64)).to(dev)
+    g_ts_n = torch.from_numpy(ts_n.view(np.int32)).to(dev)
+    g_decay = torch.from_numpy(decay).to(dev)
     q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(2)]
     q_dev = [q.to(dev) for q in q_host]
     ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
     dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    truth = [st.search_exact_cuda(q, K)[0].cpu().numpy().view(np.uint32) for q in q_dev]   # exact ground truth
+    out_i = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    out_s = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+
+    def merged(ids, d, length):
+        if world == 1:
+            return ids, d
+        ig, dg = sharding.allgather_lists(ids, d)
+        return engine.merge_topk_cuda(ig, dg, length)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    truth = [merged(*st.search_exact_cuda(q, K), K)[0].cpu().numpy().view(np.uint32) for q in q_dev]   # exact ground truth
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -201,33 +228,63 @@ def run_hnsw(args, rank, world, local_rank):
     def recall(got, want):
         return float(np.mean([len(set(a) & set(b)) / K for a, b in zip(got.tolist(), want.tolist())]))
 
+    def step_device(i, ef):
+        st.search_index_cuda(q_dev[i % 2], ef, K, ids_l, dist_l)
+        return merged(ids_l, dist_l, K)
+
+    def step_e2e(i, ef):
+        """ChronoMind::search through host buffers."""
+        if world == 1:
+            return st.search(q_host[i % 2].numpy(), K, now=now, ef_search=ef, temporal_weight=W, base_decay_rate=BASE)
+        qd = q_host[i % 2].to(dev, non_blocking=True)
+        pool = max(ef, 3 * K)                                            # OVERSAMPLE, src/store.rs:40,323
+        pi, pd = st.search_index_cuda(qd, pool, pool)
+        mi, md = merged(pi, pd, pool)                                    # global top-ef first (SURVEY.md §8e) ...
+        ri, rs, _ = engine.rerank_cuda(mi, md, K, g_ts_s, g_ts_n, g_decay, W, BASE, now)   # ... then the temporal blend
+        out_i.copy_(ri, non_blocking=True)
+        out_s.copy_(rs, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_i, out_s
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     per_ef, head = {}, None
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for ef in efs:
         for i in range(args.warmup):
-            st.search_index_cuda(q_dev[i % 2], ef, K, ids_l, dist_l)
-        torch.cuda.synchronize()
+            step_device(i, ef)
+        barrier()
         engine.profile_enable(True)
         engine.profile_read()
         launches0 = engine.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
         ev0.record()
         for i in range(args.steps):
-            st.search_index_cuda(q_dev[(args.warmup + i) % 2], ef, K, ids_l, dist_l)
+            res = step_device(args.warmup + i, ef)
         ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
         launches = engine.launch_count() - launches0
         kernel_ms, kernel_n = engine.profile_read()
         engine.profile_enable(False)
         last = (args.warmup + args.steps - 1) % 2
-        got = ids_l.cpu().numpy().view(np.uint32)
-        # work counters (== the CPU oracle's at equal ef on the same graph: tests/test_gpu_parity.py) and the e2e leg
+        got = res[0].cpu().numpy().view(np.uint32)
+        for i in range(min(args.warmup, 2)):
+            step_e2e(i, ef)
+        barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            hid, hsc = st.search(q_host[i % 2].numpy(), K, now=now, ef_search=ef, temporal_weight=0.3)
-        e2e_s = time.perf_counter() - t0
+            step_e2e(args.warmup + i, ef)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        # work counters of this rank's shard (== the CPU oracle's at equal ef on the same graph: tests/test_gpu_parity.py)
         st.search_index(q_host[last].numpy(), ef, K)
         c = engine.last_counters()
         bytes_per_batch = c["dist_evals"] * DIM * 4 + c["list_entries"] * 4 + nq * DIM * 4
@@ -239,13 +296,14 @@ def run_hnsw(args, rank, world, local_rank):
              "hbm_frac": bytes_per_batch / (kern_avg * 1e-3) / 1e9 / hbm_peak if kern_avg > 0 else None,
              "temporal_e2e_qps": nq * args.steps / e2e_s, "gpu_launches": launches, "visited_table_restarts": c["fallback_queries"]}
         per_ef[str(ef)] = r
-        log("[bench] hnsw ef=%d: %s" % (ef, json.dumps(r)))
+        if rank == 0:
+            log("[bench] hnsw ef=%d: %s" % (ef, json.dumps(r)))
         if ef == args.ef:
             head = r
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         import oracle
         import tempfile
         t0 = time.time()
@@ -255,7 +313,7 @@ def run_hnsw(args, rank, world, local_rank):
             st.save_graph(path)
             g = oracle.read_graph_sidecar(path)
         orc = oracle.OracleHnsw(16, args.efc, 50, SEED)
-        orc.import_graph(_preprocess_mt(corpus, threads), g)
+        orc.import_graph(_preprocess_mt(shard, threads), g)
         qs = queries_all[:sample]
         orc.search_batch(qs, args.ef, K, threads=threads)
         best = None
@@ -270,25 +328,30 @@ def run_hnsw(args, rank, world, local_rank):
                "sample": "%d queries, ef=%d, same graph (sidecar import), best of 3 passes (%.2fs each)" % (sample, args.ef, best),
                "parity_on_sample": parity, "dist_evals_per_query": float(octr[0]) / sample}
         log("[bench] cpu baseline in %.1fs: %s" % (time.time() - t0, cpu))
-    line = {
-        "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": head["qps"], "unit": "queries/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, ef=%d, M=16 efC=%d host-built graph "
-                               "(BASELINE configs[2]); temporal rerank w=0.3 in the e2e leg" % (n_rows, DIM, args.data, nq, K, args.ef, args.efc),
-                   "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build_s": build_s, "build_threads": threads,
-                   "l2": "3.07 GB fp32 corpus gathered at random: larger than L2; 2 query batches rotated"},
-        "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
-        "gpu_launches": head["gpu_launches"],
-        "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
-                     "traffic": measured_traffic("k_hnsw_search", rows=n_rows, queries=nq, n_gpus=1, data=args.data, ef=args.ef),
-                     "traffic_unit": "DRAM bytes per launch (ncu) vs algorithmic %d" % int(head["algorithmic_bytes_per_query"] * nq),
-                     "kernel": "k_hnsw_search", "kernel_ms_avg": head["kernel_ms_avg"],
-                     "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
-        "cpu_baseline": cpu, "clocks": clocks,
-    }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        line = {
+            "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": head["qps"], "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, ef=%d, M=16 efC=%d host-built graph%s "
+                                   "(BASELINE configs[2]); temporal rerank w=0.3 in the e2e leg"
+                                   % (n_rows, DIM, args.data, nq, K, args.ef, args.efc, "" if world == 1 else " per shard, %d shards by id" % world),
+                       "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build_s": build_s, "build_threads": threads,
+                       "parallelism": "1 GPU" if world == 1 else "independent HNSW sub-graph per shard on %d GPUs, NCCL allgather + device merge (+ rerank of the global top-ef in e2e)" % world,
+                       "l2": "%.2f GB fp32 rows per GPU gathered at random: larger than L2; 2 query batches rotated" % (n_rows / world * DIM * 4 / 1e9)},
+            "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
+            "gpu_launches": head["gpu_launches"],
+            "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
+                         "traffic": measured_traffic("k_hnsw_search", rows=n_rows, queries=nq, n_gpus=world, data=args.data, ef=args.ef),
+                         "traffic_unit": "DRAM bytes per launch (ncu) vs algorithmic %d" % int(head["algorithmic_bytes_per_query"] * nq),
+                         "kernel": "k_hnsw_search (rank 0's shard)", "kernel_ms_avg": head["kernel_ms_avg"],
+                         "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

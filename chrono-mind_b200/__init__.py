@@ -15,7 +15,7 @@ def __getattr__(name):
     if name == "engine":
         import importlib
         return importlib.import_module(__name__ + ".engine")
-    if name in ("Index", "ChronoMindB200", "native", "CmError", "Config", "default_config", "merge_topk_cuda",
+    if name in ("Index", "ChronoMindB200", "native", "CmError", "Config", "default_config", "merge_topk_cuda", "rerank_cuda",
                 "last_counters", "launch_count", "NO_ID"):
         from . import engine
         return getattr(engine, name)

@@ -374,6 +374,25 @@ def merge_topk_cuda(ids, dist, out_len: int):
     return oi, od
 
 
+def rerank_cuda(pool_ids, pool_dist, k: int, ts_secs, ts_nanos, decay_rate, temporal_weight: float,
+                base_decay_rate: float, now):
+    """The rerank tail of `ChronoMind::search` (src/store.rs:327-344) on a merged pool of GLOBAL handles:
+    pool_ids/pool_dist `[nq, pool]` CUDA tensors (ascending (distance, handle), CM_NO_ID padded); ts_secs (int64 bits
+    of the u64 seconds), ts_nanos (int32), decay_rate (float32): CUDA tensors indexed by global handle.
+    Returns ([nq, k] handles, scores, distances)."""
+    import torch
+    nq, pool = pool_ids.shape
+    dev = pool_ids.device
+    oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    osc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _check(native().cm_rerank_dev(pool_ids.data_ptr(), pool_dist.data_ptr(), nq, pool, k, ts_secs.data_ptr(),
+                                  ts_nanos.data_ptr(), decay_rate.data_ptr(), temporal_weight, base_decay_rate,
+                                  now[0], now[1], oi.data_ptr(), osc.data_ptr(), od.data_ptr(), dev.index or 0, st))
+    return oi, osc, od
+
+
 class Index:
     """PyO3 `Index` (bindings/python/src/lib.rs:35-123) on the GPU engine.
 

@@ -343,3 +343,40 @@ def test_shard_merge_equals_global_scan():
     assert np.array_equal(bits(md.cpu().numpy()), bits(gd))
     oi, od = oracle.sharded_merge(ids.cpu().numpy().view(np.uint32), ds.cpu().numpy(), k)
     assert np.array_equal(oi, gi) and np.array_equal(bits(od), bits(gd))
+
+
+def test_sharded_store_search_is_merge_then_rerank():
+    """SURVEY.md §8e: with the corpus sharded by id, `ChronoMind::search` = per-shard `VectorIndex::search(q, ef)` ->
+    merge to the GLOBAL top-ef (src/index/sharded_rwlock.rs:81-94) -> rerank (src/store.rs:327-344) with attributes
+    indexed by global handle. Three shards emulated on one GPU; the oracle does the same three steps on the CPU."""
+    import torch
+    from chronomind_b200.engine import merge_topk_cuda, rerank_cuda
+    data, q = datasets.embedding_dataset(3000, 40, 0xD1CE)
+    ts_s, ts_n, dec = datasets.temporal_attrs(3000, 3, NOW[0])
+    G, ef, k, w, base = 3, 64, 10, 0.3, 0.1
+    cfg = default_config(dimensions=768, ef_construction=100)
+    tq = torch.from_numpy(q).cuda()
+    pool_i = torch.empty((G, len(q), ef), dtype=torch.int32, device="cuda")
+    pool_d = torch.empty((G, len(q), ef), dtype=torch.float32, device="cuda")
+    want_i, want_d = [], []
+    for s in range(G):
+        st = ChronoMindB200.from_matrix(data[s::G], cfg).build_graph(0xD1CE + s, 1).set_shard(s, G).upload(0)
+        st.search_index_cuda(tq, ef, ef, pool_i[s], pool_d[s])
+        torch.cuda.synchronize()
+        orc = oracle.OracleHnsw(16, 100, 50, 0xD1CE + s)
+        orc.insert_matrix(data[s::G])
+        oi, od, _, _ = orc.search_batch(q, ef, ef)
+        want_i.append(oi)
+        want_d.append(od)
+    mi, md = merge_topk_cuda(pool_i, pool_d, ef)
+    ri, rs, rd = rerank_cuda(mi, md, k, torch.from_numpy(ts_s.view(np.int64)).cuda(), torch.from_numpy(ts_n.view(np.int32)).cuda(),
+                             torch.from_numpy(dec).cuda(), w, base, NOW)
+    torch.cuda.synchronize()
+    gi, gd = oracle.sharded_merge(np.stack(want_i), np.stack(want_d), ef)
+    assert np.array_equal(mi.cpu().numpy().view(np.uint32), gi) and np.array_equal(bits(md.cpu().numpy()), bits(gd))
+    wi, ws = oracle.rerank_pool(gi, gd, k, w, base, ts_s, ts_n, dec, NOW[0], NOW[1])
+    got_i, got_s = ri.cpu().numpy().view(np.uint32), rs.cpu().numpy()
+    same = got_i == wi
+    assert same.mean() > 0.999
+    assert np.allclose(got_s[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert np.all(np.diff(got_s, axis=1) >= 0)
