@@ -92,12 +92,12 @@ struct DevBuf {
 
 // Scratch for one in-flight search call. Calls on different host threads take different workspaces.
 struct Workspace {
-  DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable;
+  DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable, qnorm, qctx;
   DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
   cudaStream_t stream = nullptr;  // host-buffer variants
   unsigned hnsw_grid = 0;
   void release() {
-    for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qbf16,
+    for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qnorm, &qctx, &qbf16,
                       &tc_state, &cand, &qflag})
       b->release();
     if (stream) cudaStreamDestroy(stream);
@@ -150,7 +150,8 @@ constexpr size_t kSmallBytes = 256 + kFlagCap * 4;
 static void free_device(DeviceIndex& d) {
   if (d.device < 0) return;
   cudaSetDevice(d.device);
-  for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.ts_secs, (void*)d.ts_nanos, (void*)d.decay,
+  for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.xraw, (void*)d.norm2_raw, (void*)d.ctx,
+                  (void*)d.ts_secs, (void*)d.ts_nanos, (void*)d.decay,
                   (void*)d.nbr0, (void*)d.deg0, (void*)d.upper_base, (void*)d.nbr_up, (void*)d.deg_up})
     if (p) cudaFree(p);
   d = DeviceIndex();
@@ -418,6 +419,55 @@ static cm_status search_temporal_dev_impl(const cm_index* idx, Workspace* ws, co
   return CM_OK;
 }
 
+// ChronoMind::search_in_context (src/store.rs:353-377): fp32 scan of the RAW rows with the context epilogue, then
+// the k smallest (score, handle). q: raw queries [nq][dim] (device), want: [nq] context ids (device).
+static cm_status search_in_context_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq,
+                                            const uint32_t* want, uint32_t k, float w, float base, uint64_t now_secs,
+                                            uint32_t now_nanos, uint32_t* bad_row, uint32_t* ids, float* score,
+                                            cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  if (!d.ctx && d.n) return fail(CM_ERR_STATE, "this index carries no contexts (cm_index_set_contexts / a snapshot, then upload)");
+  if (nq == 0) return CM_OK;
+  if (d.n == 0) {
+    CM_CUDA(cudaMemsetAsync(ids, 0xFF, (size_t)nq * k * 4, s));
+    CM_CUDA(launch_fill(score, (uint64_t)nq * k, INFINITY, s));
+    return CM_OK;
+  }
+  if (bad_row) {  // validate_query's finiteness check (the normalised copy is scratch)
+    CM_CUDA(ws->qn.ensure((size_t)nq * d.dim_pad * sizeof(float)));
+    CM_CUDA(launch_preprocess_rows(q, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
+  }
+  CM_CUDA(ws->qnorm.ensure((size_t)nq * 4));
+  CM_CUDA(launch_pair_dot(q, q, nq, d.dim, d.dim, ws->qnorm.as<float>(), s));
+  tl_counters.dist_evals += (uint64_t)nq * d.n;
+  uint64_t ldD = (d.n + 3) & ~3ull;
+  uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
+  qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
+  CM_CUDA(ws->D.ensure(qb * ldD * sizeof(float)));
+  float* D = ws->D.as<float>();
+  ContextEpilogue ce;
+  ce.enabled = 1;
+  ce.na = d.norm2_raw;
+  ce.ctx = d.ctx;
+  ce.deleted = d.deleted;
+  ce.ts_secs = reinterpret_cast<const unsigned long long*>(d.ts_secs);
+  ce.ts_nanos = d.ts_nanos;
+  ce.decay = d.decay;
+  ce.w = w;
+  ce.base = base;
+  ce.now_secs = now_secs;
+  ce.now_nanos = now_nanos;
+  for (uint32_t q0 = 0; q0 < nq; q0 += (uint32_t)qb) {
+    uint32_t nb = std::min<uint32_t>((uint32_t)qb, nq - q0);
+    ce.nb = ws->qnorm.as<float>() + q0;
+    ce.want = want + q0;
+    CM_CUDA(launch_exact_dist(q + (size_t)q0 * d.dim, nb, d.dim, d.xraw, d.n, d.dim, d.dim_pad, D, ldD, nullptr, 0, s, &ce));
+    CM_CUDA(launch_select_from_dist(D, ldD, nb, d.n, nullptr, k, ids + (size_t)q0 * k, score + (size_t)q0 * k, k, nullptr,
+                                    nullptr, 0, s, /*skip_inf=*/true));
+  }
+  return CM_OK;
+}
+
 static void fetch_scan_counters(Workspace* ws) {
   if (!ws->small.p) return;
   unsigned long long r = 0;
@@ -557,6 +607,21 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   });
   idx->all_finite = finite.load();
   idx->ext_ids.resize(n);
+  // contexts in order of first appearance; the raw rows stay for search_in_context (metric.distance on stored data)
+  idx->ctx.resize(n);
+  idx->importance.resize(n);
+  {
+    std::unordered_map<std::string, uint32_t> ctx_of;
+    for (uint64_t i = 0; i < n; ++i) {
+      idx->importance[i] = snap.memories[i].importance;
+      auto it = ctx_of.find(snap.memories[i].context);
+      if (it == ctx_of.end()) {
+        it = ctx_of.emplace(snap.memories[i].context, (uint32_t)idx->ctx_labels.size()).first;
+        idx->ctx_labels.push_back(snap.memories[i].context);
+      }
+      idx->ctx[i] = it->second;
+    }
+  }
   // Replay ChronoMind::insert's handle bookkeeping (src/store.rs:226-264): a repeated id publishes the new
   // handle and tombstones the one it replaces; capacity counts distinct ids.
   std::unordered_map<std::string, uint32_t> by_id;
@@ -580,8 +645,32 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
       by_id.emplace(m.id, (uint32_t)i);
     }
   }
+  idx->raw = std::move(snap.vectors);
   *out = idx;
   return CM_OK;
+}
+
+cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_t* context_ids) {
+  if (!idx || (idx->n && (!raw_x || !context_ids))) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  idx->raw.assign(raw_x, raw_x + idx->n * (uint64_t)idx->dim);
+  idx->ctx.assign(context_ids, context_ids + idx->n);
+  return CM_OK;
+}
+
+const char* cm_index_context_label(const cm_index* idx, uint32_t handle) {
+  if (!idx || handle >= idx->ctx.size() || idx->ctx[handle] >= idx->ctx_labels.size()) return "";
+  return idx->ctx_labels[idx->ctx[handle]].c_str();
+}
+
+float cm_index_importance(const cm_index* idx, uint32_t handle) {
+  return (idx && handle < idx->importance.size()) ? idx->importance[handle] : 0.0f;
+}
+
+uint32_t cm_index_context_id(const cm_index* idx, const char* label) {
+  if (!idx || !label) return CM_NO_ID;
+  for (size_t i = 0; i < idx->ctx_labels.size(); ++i)
+    if (idx->ctx_labels[i] == label) return (uint32_t)i;
+  return CM_NO_ID;
 }
 
 cm_status cm_index_set_attrs(cm_index* idx, const uint64_t* ts_secs, const uint32_t* ts_nanos, const float* decay_rate,
@@ -671,6 +760,16 @@ cm_status cm_index_upload(cm_index* idx, int device) {
     CM_CUDA(cudaMemcpy(d.ts_secs, idx->ts_secs.data(), n * 8, cudaMemcpyHostToDevice));
     CM_CUDA(cudaMemcpy(d.ts_nanos, idx->ts_nanos.data(), n * 4, cudaMemcpyHostToDevice));
     CM_CUDA(cudaMemcpy(d.decay, idx->decay.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  if (!idx->ctx.empty() && n) {  // store-level context scan: raw rows, their squared norms, context ids
+    CM_CUDA(cudaMalloc(&d.xraw, rows * d.dim_pad * sizeof(float)));
+    if (d.dim_pad != d.dim) CM_CUDA(cudaMemset(d.xraw, 0, rows * d.dim_pad * sizeof(float)));
+    CM_CUDA(cudaMemcpy2D(d.xraw, (size_t)d.dim_pad * 4, idx->raw.data(), (size_t)d.dim * 4, (size_t)d.dim * 4, n,
+                         cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMalloc(&d.norm2_raw, rows * 4));
+    CM_CUDA(launch_pair_dot(d.xraw, d.xraw, n, d.dim, d.dim_pad, d.norm2_raw, nullptr));
+    CM_CUDA(cudaMalloc(&d.ctx, rows * 4));
+    CM_CUDA(cudaMemcpy(d.ctx, idx->ctx.data(), n * 4, cudaMemcpyHostToDevice));
   }
   // bf16 copy for the tensor-core scan, padded to whole tiles; tombstoned and padding rows are NaN-masked.
   d.n_pad = scan_tc_pad_rows(std::max<uint64_t>(n, 1));
@@ -852,6 +951,19 @@ cm_status cm_search_temporal_dev(const cm_index* idx, const void* q, uint32_t nq
                                   (cudaStream_t)stream);
 }
 
+cm_status cm_search_in_context_dev(const cm_index* idx, const void* q, uint32_t nq, const void* context_ids, uint32_t k,
+                                   float w, float base, uint64_t now_secs, uint32_t now_nanos, void* ids, void* score,
+                                   void* stream) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, score);
+  if (st != CM_OK) return st;
+  if (nq && !context_ids) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  return search_in_context_dev_impl(idx, lease.ws, (const float*)q, nq, (const uint32_t*)context_ids, k, w, base, now_secs,
+                                    now_nanos, nullptr, (uint32_t*)ids, (float*)score, (cudaStream_t)stream);
+}
+
 cm_status cm_merge_topk_dev(const void* ids, const void* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
                             uint32_t out_len, void* out_ids, void* out_dist, int device, void* stream) {
   if (!ids || !dist || !out_ids || !out_dist || n_shards == 0 || len == 0 || out_len == 0)
@@ -1024,6 +1136,44 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
   }
   CM_CUDA(cudaStreamSynchronize(hc.s));
   if (!exact) fetch_hnsw_counters(lease.ws);
+  if (bad != 0xFFFFFFFFu)
+    return fail(CM_ERR_INVALID_VECTOR,
+                "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");
+  return CM_OK;
+}
+
+cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim,
+                               const uint32_t* context_ids, uint32_t k, float w, float base, uint64_t now_secs,
+                               uint32_t now_nanos, uint32_t* ids, float* score) {
+  cm_status st = check_search_args(idx, q, nq, k, ids, score);
+  if (st != CM_OK) return st;
+  if (nq && !context_ids) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  if (qdim != idx->dim) {  // validate_query (src/store.rs:379-392): dimensions first
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "invalid dimensions: got %u, expected %u", qdim, idx->dim);
+    return fail(CM_ERR_INVALID_DIMENSIONS, buf);
+  }
+  if ((st = set_device(idx)) != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  HostCall hc;
+  if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
+  CM_CUDA(lease.ws->small.ensure(kSmallBytes));
+  CM_CUDA(lease.ws->qctx.ensure(std::max<size_t>((size_t)nq * 4, 16)));
+  if (nq) CM_CUDA(cudaMemcpyAsync(lease.ws->qctx.p, context_ids, (size_t)nq * 4, cudaMemcpyHostToDevice, hc.s));
+  uint32_t* bad_row = lease.ws->small.as<uint32_t>() + 48;  // offset 192
+  CM_CUDA(cudaMemsetAsync(bad_row, 0xFF, 4, hc.s));
+  st = search_in_context_dev_impl(idx, lease.ws, hc.q_dev, nq, lease.ws->qctx.as<uint32_t>(), k, w, base, now_secs,
+                                  now_nanos, bad_row, hc.ids_dev, hc.a_dev, hc.s);
+  if (st != CM_OK) return st;
+  uint32_t bad = 0xFFFFFFFFu;
+  CM_CUDA(cudaMemcpyAsync(&bad, bad_row, 4, cudaMemcpyDeviceToHost, hc.s));
+  size_t ob = (size_t)nq * k * 4;
+  if (ob) {
+    CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+    CM_CUDA(cudaMemcpyAsync(score, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+  }
+  CM_CUDA(cudaStreamSynchronize(hc.s));
   if (bad != 0xFFFFFFFFu)
     return fail(CM_ERR_INVALID_VECTOR,
                 "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");

@@ -110,6 +110,10 @@ struct DeviceIndex {
   uint64_t n_pad = 0;         // rows padded to the scan's tile height
   uint32_t k_pad = 0;         // columns padded to a multiple of 64
   uint8_t* deleted = nullptr; // [n]
+  // store-level context scan (`search_in_context`): raw (un-preprocessed) rows, their squared norms, context ids
+  float* xraw = nullptr;      // [n][dim_pad], only when the index carries contexts
+  float* norm2_raw = nullptr; // [n]
+  uint32_t* ctx = nullptr;    // [n]
   uint64_t* ts_secs = nullptr;
   uint32_t* ts_nanos = nullptr;
   float* decay = nullptr;
@@ -140,6 +144,10 @@ struct cm_index {
   std::vector<uint32_t> ts_nanos;   // [n]
   std::vector<float> decay;         // [n]
   std::vector<std::string> ext_ids; // snapshot-loaded only
+  std::vector<float> raw;           // [n][dim] rows as stored (`StoredMemory.data`), only with contexts
+  std::vector<uint32_t> ctx;        // [n] context id per handle (empty: no contexts)
+  std::vector<std::string> ctx_labels;  // snapshot-loaded: id -> `MemoryAttributes.context`
+  std::vector<float> importance;    // snapshot-loaded: `MemoryAttributes.importance`
   uint64_t live = 0;
   bool all_finite = true;           // no NaN/Inf component in any stored row (gate of the tensor-core scan)
   cm::Graph graph;

@@ -24,11 +24,32 @@ cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld
 cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
                                  cudaStream_t s);
 
+// dot_avx2(a[i], b[i]) for n row pairs (a == b: the squared norm as dot_and_norms_avx2 accumulates it).
+cudaError_t launch_pair_dot(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
+                            cudaStream_t s);
+
+// Epilogue of the fp32 scan for `ChronoMind::search_in_context` (src/store.rs:353-377): x and q are RAW rows; the
+// kernel writes combined_score(distance(x[row], q[qi])) for the live members of context want[qi], +inf elsewhere.
+struct ContextEpilogue {
+  int enabled = 0;
+  const float* na = nullptr;       // [n]  squared norms of the raw rows
+  const float* nb = nullptr;       // [nq] squared norms of the raw queries
+  const uint32_t* ctx = nullptr;   // [n]  context id per handle
+  const uint32_t* want = nullptr;  // [nq] context id per query
+  const uint8_t* deleted = nullptr;
+  const unsigned long long* ts_secs = nullptr;
+  const uint32_t* ts_nanos = nullptr;
+  const float* decay = nullptr;
+  float w = 0.0f, base = 0.0f;
+  unsigned long long now_secs = 0;
+  uint32_t now_nanos = 0;
+};
+
 // fp32 exact scan, CUDA cores, bit-exact to dot_avx2: D[qi][row] = distance_prepared(x[row], q[qi]).
 // active_count (optional, device): query i of this launch is computed only when active_base + i < *active_count.
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
                               uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
-                              cudaStream_t s);
+                              cudaStream_t s, const ContextEpilogue* ce = nullptr);
 cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
 
 // k smallest (distance, handle) per row of D, tombstones dropped.
@@ -36,7 +57,8 @@ cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
 // active_base + b >= *active_count are skipped.
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
                                     uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, const uint32_t* qmap,
-                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s);
+                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s,
+                                    bool skip_inf = false);
 
 // K5 — shard merge (src/index/sharded_rwlock.rs:81-94).
 cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,

@@ -145,6 +145,62 @@ cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uin
   return cudaGetLastError();
 }
 
+// dot_avx2(a[i], b[i]) (src/metric.rs:129-147) for n row pairs — with a == b this is the squared norm exactly as
+// dot_and_norms_avx2 accumulates it (src/metric.rs:78-116: same FMA chain, same horizontal sum, same scalar tail).
+__global__ void __launch_bounds__(256) k_pair_dot(const float* __restrict__ a, const float* __restrict__ b, uint64_t n,
+                                                  uint32_t dim, uint32_t ld, float* __restrict__ out) {
+  uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  uint32_t j = threadIdx.x & 7;
+  bool valid = pair < n;
+  uint64_t p = valid ? pair : 0;
+  const float* pa = a + p * ld;
+  const float* pb = b + p * ld;
+  uint32_t body = dim & ~7u;
+  float acc = 0.0f;
+  for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(pa[e], pb[e], acc);
+  float sum = octet_hsum(acc);
+  for (uint32_t e = body; e < dim; ++e) sum = __fadd_rn(sum, __fmul_rn(pa[e], pb[e]));
+  if (valid && j == 0) out[pair] = sum;
+}
+
+cudaError_t launch_pair_dot(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
+                            cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint64_t threads = n * 8;
+  k_pair_dot<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, b, n, dim, ld, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// combined_score (src/store.rs:395-415), shared by the rerank (K4) and the context scan.
+__device__ __forceinline__ float combined_score_dev(float distance, unsigned long long ts_secs, uint32_t ts_nanos,
+                                                    float decay_rate, unsigned long long now_secs,
+                                                    uint32_t now_nanos, float w, float base_decay_rate) {
+  // now.duration_since(ts).unwrap_or_default()
+  unsigned long long dsecs = 0;
+  uint32_t dnanos = 0;
+  bool later = (now_secs > ts_secs) || (now_secs == ts_secs && now_nanos >= ts_nanos);
+  if (later) {
+    dsecs = now_secs - ts_secs;
+    if (now_nanos >= ts_nanos) {
+      dnanos = now_nanos - ts_nanos;
+    } else {
+      dsecs -= 1;
+      dnanos = now_nanos + 1000000000u - ts_nanos;
+    }
+  }
+  // Duration::as_secs_f32 = secs as f32 + nanos as f32 / 1e9
+  float age_secs = __fadd_rn(__ull2float_rn(dsecs), __fdiv_rn(__uint2float_rn(dnanos), 1.0e9f));
+  float age_hours = __fdiv_rn(age_secs, 3600.0f);
+  float rate = decay_rate > 0.0f ? decay_rate : base_decay_rate;
+  // f32::exp: evaluated in double and rounded once (correctly rounded fp32 result).
+  float temporal_relevance = (float)exp((double)__fmul_rn(-rate, age_hours));
+  float geo = __fmul_rn(__fsub_rn(1.0f, w), __fdiv_rn(distance, 2.0f));
+  float tmp = __fmul_rn(w, __fsub_rn(1.0f, temporal_relevance));
+  return __fadd_rn(geo, tmp);
+}
+
+
 // ---------------------------------------------------------------------------------------------------------
 // fp32 exact scan (CUDA cores), bit-exact to the reference's dot_avx2.
 //
@@ -161,7 +217,7 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
                                                     const float* __restrict__ x, uint64_t n, uint32_t dim,
                                                     uint32_t ldx, float* __restrict__ D, uint64_t ldD,
                                                     const uint32_t* __restrict__ active_count,
-                                                    uint32_t active_base) {
+                                                    uint32_t active_base, ContextEpilogue ce) {
   extern __shared__ __align__(16) float qs[];  // [body][16]
   if (active_count) {
     uint32_t ac = *active_count;
@@ -221,7 +277,28 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
         const float* qrow = q + (uint64_t)qq * ldq;
         for (uint32_t e = body; e < dim; ++e) sum = __fadd_rn(sum, __fmul_rn(xr[e], qrow[e]));
       }
-      if ((qi & 7) == (int)j && valid && qq < nq) D[(uint64_t)qq * ldD + row] = clamp02(__fsub_rn(1.0f, sum));
+      if ((qi & 7) == (int)j && valid && qq < nq) {
+        float out;
+        if (!ce.enabled) {
+          out = clamp02(__fsub_rn(1.0f, sum));  // distance_prepared
+        } else {
+          // search_in_context (src/store.rs:362-376): members of the query's context only; x/q are RAW rows, so
+          // `sum` is dot_and_norms' dot and the squared norms come precomputed in the same arithmetic.
+          out = __int_as_float(0x7F800000);
+          if (ce.ctx[row] == ce.want[qq] && !(ce.deleted && ce.deleted[row])) {
+            const float denom = __fsqrt_rn(__fmul_rn(ce.na[row], ce.nb[qq]));
+            float dist = 2.0f;                                   // zero vector: similarity undefined (metric.rs:181-184)
+            if (!(denom <= 1.1920929e-7f)) {
+              float c = __fdiv_rn(sum, denom);
+              c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);      // f32::clamp: NaN passes through
+              dist = __fsub_rn(1.0f, c);
+            }
+            out = combined_score_dev(dist, ce.ts_secs[row], ce.ts_nanos[row], ce.decay[row], ce.now_secs, ce.now_nanos,
+                                     ce.w, ce.base);
+          }
+        }
+        D[(uint64_t)qq * ldD + row] = out;
+      }
     }
   }
   }
@@ -229,7 +306,7 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
 
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
                               uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
-                              cudaStream_t s) {
+                              cudaStream_t s, const ContextEpilogue* ce) {
   if (nq == 0 || n == 0) return cudaSuccess;
   size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -243,7 +320,8 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
   uint64_t row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
   if (active_count) row_blocks = std::min<uint64_t>(row_blocks, 296);
   dim3 grid((unsigned)row_blocks, (nq + EX_QT - 1) / EX_QT);
-  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base);
+  ContextEpilogue none{};
+  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base, ce ? *ce : none);
   count_launch();
   return cudaGetLastError();
 }
@@ -307,7 +385,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
                                                                   float* __restrict__ dist, uint32_t out_ld,
                                                                   const uint32_t* __restrict__ qmap,
                                                                   const uint32_t* __restrict__ active_count,
-                                                                  uint32_t active_base) {
+                                                                  uint32_t active_base, int skip_inf) {
   extern __shared__ __align__(16) unsigned long long keys[];  // next_pow2(kp + SEL_BUF)
   __shared__ SelState st;
   if (active_count && active_base + blockIdx.x >= *active_count) return;
@@ -325,8 +403,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
     for (int c = 0; c < 4; ++c) {
       uint64_t i = base + c * SEL_THREADS + threadIdx.x;
       if (i < n) {
-        unsigned long long key = pack_key(row[i], (uint32_t)i);
-        if (key < tau && !(deleted && deleted[i])) {
+        const float v = row[i];
+        unsigned long long key = pack_key(v, (uint32_t)i);
+        if (key < tau && !(deleted && deleted[i]) && !(skip_inf && __float_as_uint(v) == 0x7F800000u)) {
           uint32_t slot = atomicAdd(&st.cnt, 1u);
           keys[kp + slot] = key;
         }
@@ -348,12 +427,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
 
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
                                     uint32_t k, uint32_t* ids, float* dist, uint32_t out_ld, const uint32_t* qmap,
-                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s) {
+                                    const uint32_t* active_count, uint32_t active_base, cudaStream_t s, bool skip_inf) {
   if (nq == 0) return cudaSuccess;
   uint32_t kp = next_pow2(k < 32 ? 32 : k);
   size_t smem = (size_t)next_pow2(kp + SEL_BUF) * sizeof(unsigned long long);
   k_select_from_dist<<<nq, SEL_THREADS, smem, s>>>(D, ldD, n, deleted, k, kp, ids, dist, out_ld, qmap, active_count,
-                                                   active_base);
+                                                   active_base, skip_inf ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }
@@ -406,33 +485,6 @@ cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n
 // ---------------------------------------------------------------------------------------------------------
 // K4 temporal rerank — ChronoMind::search's tail (src/store.rs:327-344) with combined_score (:395-415).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float combined_score_dev(float distance, unsigned long long ts_secs, uint32_t ts_nanos,
-                                                    float decay_rate, unsigned long long now_secs,
-                                                    uint32_t now_nanos, float w, float base_decay_rate) {
-  // now.duration_since(ts).unwrap_or_default()
-  unsigned long long dsecs = 0;
-  uint32_t dnanos = 0;
-  bool later = (now_secs > ts_secs) || (now_secs == ts_secs && now_nanos >= ts_nanos);
-  if (later) {
-    dsecs = now_secs - ts_secs;
-    if (now_nanos >= ts_nanos) {
-      dnanos = now_nanos - ts_nanos;
-    } else {
-      dsecs -= 1;
-      dnanos = now_nanos + 1000000000u - ts_nanos;
-    }
-  }
-  // Duration::as_secs_f32 = secs as f32 + nanos as f32 / 1e9
-  float age_secs = __fadd_rn(__ull2float_rn(dsecs), __fdiv_rn(__uint2float_rn(dnanos), 1.0e9f));
-  float age_hours = __fdiv_rn(age_secs, 3600.0f);
-  float rate = decay_rate > 0.0f ? decay_rate : base_decay_rate;
-  // f32::exp: evaluated in double and rounded once (correctly rounded fp32 result).
-  float temporal_relevance = (float)exp((double)__fmul_rn(-rate, age_hours));
-  float geo = __fmul_rn(__fsub_rn(1.0f, w), __fdiv_rn(distance, 2.0f));
-  float tmp = __fmul_rn(w, __fsub_rn(1.0f, temporal_relevance));
-  return __fadd_rn(geo, tmp);
-}
-
 __global__ void __launch_bounds__(128) k_rerank(const uint32_t* __restrict__ pool_ids, const float* __restrict__ pool_dist,
                                                 uint32_t pool, uint32_t P, uint32_t k,
                                                 const unsigned long long* __restrict__ ts_secs,

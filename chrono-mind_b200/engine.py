@@ -60,6 +60,8 @@ ABI = {
     "cm_index_from_matrix": (_i, [_vp, _u64, _u32, C.POINTER(Config), C.POINTER(_vp)]),
     "cm_index_from_snapshot": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "cm_index_set_attrs": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cm_index_set_contexts": (_i, [_vp, _vp, _vp]),
+    "cm_index_context_id": (_u32, [_vp, C.c_char_p]),
     "cm_index_remove": (_i, [_vp, _u32, C.POINTER(_i)]),
     "cm_index_build_graph": (_i, [_vp, _u64, _i]),
     "cm_index_set_shard": (_i, [_vp, _u32, _u32]),
@@ -70,6 +72,8 @@ ABI = {
     "cm_index_dim": (_u32, [_vp]),
     "cm_index_get_config": (_i, [_vp, C.POINTER(Config)]),
     "cm_index_external_id": (C.c_char_p, [_vp, _u32]),
+    "cm_index_context_label": (C.c_char_p, [_vp, _u32]),
+    "cm_index_importance": (_f, [_vp, _u32]),
     "cm_index_check_invariants": (_i, [_vp]),
     "cm_index_entry": (_u64, [_vp]),
     "cm_index_top_layer": (_u32, [_vp, _u32]),
@@ -80,6 +84,8 @@ ABI = {
     "cm_search_exact": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "cm_search_hnsw": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "cm_search_temporal": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp]),
+    "cm_search_in_context": (_i, [_vp, _vp, _u32, _u32, _vp, _u32, _f, _f, _u64, _u32, _vp, _vp]),
+    "cm_search_in_context_dev": (_i, [_vp, _vp, _u32, _vp, _u32, _f, _f, _u64, _u32, _vp, _vp, _vp]),
     "cm_search_exact_dev": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_hnsw_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_temporal_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp, _vp]),
@@ -200,6 +206,20 @@ class ChronoMindB200:
             arrs.append(a)
         _check(native().cm_index_set_attrs(self._h, *[_ptr(a) for a in arrs]))
 
+    def set_contexts(self, raw_x, context_ids):
+        """Store-level contexts: the rows as stored (not preprocessed) and one context id per handle."""
+        raw_x = np.ascontiguousarray(raw_x, dtype=np.float32)
+        context_ids = np.ascontiguousarray(context_ids, dtype=np.uint32)
+        if raw_x.shape != (self.slots, self.dim) or context_ids.shape != (self.slots,):
+            raise ValueError("raw_x must be [slots, dim] and context_ids [slots]")
+        _check(native().cm_index_set_contexts(self._h, _ptr(raw_x), _ptr(context_ids)))
+        return self
+
+    def context_id(self, label: str):
+        """Id of a context label of a snapshot-loaded store (None when no memory carries it)."""
+        r = int(native().cm_index_context_id(self._h, label.encode("utf-8")))
+        return None if r == NO_ID else r
+
     def remove(self, handle: int) -> bool:
         r = C.c_int(0)
         _check(native().cm_index_remove(self._h, handle, C.byref(r)))
@@ -260,6 +280,12 @@ class ChronoMindB200:
 
     def external_id(self, handle: int) -> str:
         return native().cm_index_external_id(self._h, handle).decode("utf-8")
+
+    def context_label(self, handle: int) -> str:
+        return native().cm_index_context_label(self._h, handle).decode("utf-8")
+
+    def importance(self, handle: int) -> float:
+        return float(native().cm_index_importance(self._h, handle))
 
     def check_invariants(self) -> int:
         return int(native().cm_index_check_invariants(self._h))
@@ -322,6 +348,24 @@ class ChronoMindB200:
         _check(native().cm_search_temporal(self._h, _ptr(q), q.shape[0], q.shape[1], k, efs, w, base, secs, nanos,
                                            1 if exact else 0, _ptr(ids), _ptr(score), _ptr(dist)))
         return (ids, score, dist) if want_dist else (ids, score)
+
+    def search_in_context(self, context, q, k: int, now=None, temporal_weight=None, base_decay_rate=None):
+        """`ChronoMind::search_in_context(context, query, k)` per row (src/store.rs:353-377) -> (handles, scores).
+        `context`: a label (snapshot-loaded stores), an id, or one id per query."""
+        q = self._queries(q)
+        cfg = self.config
+        w = cfg.temporal_weight if temporal_weight is None else temporal_weight
+        base = cfg.base_decay_rate if base_decay_rate is None else base_decay_rate
+        secs, nanos = _now() if now is None else now
+        if isinstance(context, str):
+            cid = self.context_id(context)
+            context = NO_ID if cid is None else cid
+        want = np.ascontiguousarray(np.broadcast_to(np.asarray(context, dtype=np.uint32), (q.shape[0],)))
+        ids = np.empty((q.shape[0], k), dtype=np.uint32)
+        score = np.empty((q.shape[0], k), dtype=np.float32)
+        _check(native().cm_search_in_context(self._h, _ptr(q), q.shape[0], q.shape[1], _ptr(want), k, w, base, secs, nanos,
+                                             _ptr(ids), _ptr(score)))
+        return ids, score
 
     # ---- search (torch CUDA tensors, asynchronous on the current stream) ------------------------------------------
     def search_exact_cuda(self, q, k: int, out_ids=None, out_dist=None):

@@ -104,6 +104,14 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out);
 cm_status cm_index_set_attrs(cm_index* idx, const uint64_t* ts_secs, const uint32_t* ts_nanos,
                              const float* decay_rate, const uint8_t* deleted);
 
+/* Store-level contexts (`MemoryAttributes.context`, src/types.rs:32-49) for cm_search_in_context: `raw_x` [n][dim]
+ * are the rows AS STORED (`StoredMemory.data`, not preprocessed — `search_in_context` calls `metric.distance` on
+ * them), `context_ids` [n] one id per handle. Snapshot-loaded indexes carry both already (ids in order of first
+ * appearance, see cm_index_context_id). Must precede cm_index_upload. */
+cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_t* context_ids);
+/* Context id of a label of a snapshot-loaded index; CM_NO_ID when no memory carries it. */
+uint32_t cm_index_context_id(const cm_index* idx, const char* label);
+
 /* `VectorIndex::remove` (src/index/lockfree_hnsw.rs:451-467): tombstone one handle. *removed = 1 when this
  * call flipped it. Takes effect on the device at the next cm_index_upload. */
 cm_status cm_index_remove(cm_index* idx, uint32_t handle, int* removed);
@@ -132,6 +140,10 @@ uint32_t cm_index_dim(const cm_index* idx);
 cm_status cm_index_get_config(const cm_index* idx, cm_config* out);
 /* External id of a handle (snapshot-loaded indexes; "" otherwise). Pointer valid until cm_index_free. */
 const char* cm_index_external_id(const cm_index* idx, uint32_t handle);
+/* `MemoryAttributes.context` / `.importance` of a handle (snapshot-loaded indexes; "" / 0 otherwise) — what the
+ * reference CLI prints per result (src/main.rs:213-222). Pointer valid until cm_index_free. */
+const char* cm_index_context_label(const cm_index* idx, uint32_t handle);
+float cm_index_importance(const cm_index* idx, uint32_t handle);
 /* `check_invariants` (src/index/lockfree_hnsw.rs:295-347): 0 when the built graph is sound. */
 int cm_index_check_invariants(const cm_index* idx);
 /* Graph readout for tests / sidecar files: entry word ((top_layer << 32) | id, ~0 when empty),
@@ -171,6 +183,15 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
                              uint64_t now_secs, uint32_t now_nanos, int exact, uint32_t* ids, float* score,
                              float* dist);
 
+/* `ChronoMind::search_in_context(context, query, k)` for each row (src/store.rs:353-377): validate, then an EXACT
+ * scan of the live members of the row's context with `metric.distance` on the raw stored rows (full cosine with
+ * both norms, src/metric.rs:163-195), `combined_score`, sort by score, truncate k. `context_ids` [nq] (one per
+ * query; CM_NO_ID matches nothing). The reference iterates a hash map, so its order among EQUAL scores is
+ * unspecified; here ties resolve toward the lower handle. */
+cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim,
+                               const uint32_t* context_ids, uint32_t k, float temporal_weight, float base_decay_rate,
+                               uint64_t now_secs, uint32_t now_nanos, uint32_t* ids, float* score);
+
 /* ---- search: device buffers on the index's device, asynchronous on `stream` ------------------------ */
 /* Same contracts; q/ids/dist/score are device pointers; qdim must equal dim; no validation of query
  * values (the caller owns them). Work is enqueued on `stream` (a cudaStream_t, NULL = default stream). */
@@ -181,6 +202,9 @@ cm_status cm_search_hnsw_dev(const cm_index* idx, const void* q, uint32_t nq, ui
 cm_status cm_search_temporal_dev(const cm_index* idx, const void* q, uint32_t nq, uint32_t k, uint32_t ef_search,
                                  float temporal_weight, float base_decay_rate, uint64_t now_secs,
                                  uint32_t now_nanos, int exact, void* ids, void* score, void* dist, void* stream);
+cm_status cm_search_in_context_dev(const cm_index* idx, const void* q, uint32_t nq, const void* context_ids, uint32_t k,
+                                   float temporal_weight, float base_decay_rate, uint64_t now_secs, uint32_t now_nanos,
+                                   void* ids, void* score, void* stream);
 
 /* Merge step of `ShardedRwLockHnsw::search` (src/index/sharded_rwlock.rs:81-94): concatenate per-shard lists,
  * sort by (distance, global handle), truncate. ids/dist: device [n_shards][nq][len] LOCAL handles as produced

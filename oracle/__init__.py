@@ -88,6 +88,9 @@ def lib():
     sig("orc_rerank_pool", None,
         [_u32p, _f32p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, _u64p, _u32p, _f32p, C.c_uint64, C.c_uint32,
          C.c_uint64, _u32p, _f32p])
+    sig("orc_search_in_context", C.c_int,
+        [_f32p, C.c_uint64, C.c_uint64, _u32p, C.c_void_p, C.c_float, C.c_float, _u64p, _u32p, _f32p, C.c_uint64,
+         C.c_uint32, _f32p, C.c_uint64, C.c_uint64, _u32p, C.c_uint64, _u32p, _f32p, C.c_int])
     sig("orc_sharded_merge", None,
         [_u32p, _f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _f32p])
     if not L.orc_cpu_has_avx2_fma():
@@ -290,6 +293,25 @@ def rerank_pool(cand_ids, cand_dists, k, w, base_decay, ts_secs, ts_nanos, decay
     lib().orc_rerank_pool(cand_ids, cand_dists, nq, pool, w, base_decay, np.ascontiguousarray(ts_secs, np.uint64),
                           np.ascontiguousarray(ts_nanos, np.uint32), _f32(decay), now_secs, now_nanos, k, ids, sc)
     return ids, sc
+
+
+def search_in_context(raw, context_of, q, want_ctx, k, w, base_decay, ts_secs, ts_nanos, decay, now_secs, now_nanos,
+                      deleted=None, threads=1):
+    """`ChronoMind::search_in_context` (src/store.rs:353-377) per query row: exact scan of the context's live members
+    with `metric.distance` on RAW rows + `combined_score`. Returns (rc, ids[nq,k], scores[nq,k])."""
+    raw, q = _f32(raw), _f32(q)
+    nq = q.shape[0]
+    ids = np.empty((nq, k), dtype=np.uint32)
+    sc = np.empty((nq, k), dtype=np.float32)
+    dptr = None
+    if deleted is not None:
+        deleted = np.ascontiguousarray(deleted, dtype=np.uint8)
+        dptr = deleted.ctypes.data_as(C.c_void_p)
+    rc = lib().orc_search_in_context(raw, raw.shape[0], raw.shape[1], np.ascontiguousarray(context_of, np.uint32), dptr,
+                                     w, base_decay, np.ascontiguousarray(ts_secs, np.uint64),
+                                     np.ascontiguousarray(ts_nanos, np.uint32), _f32(decay), now_secs, now_nanos, q, nq,
+                                     q.shape[1], np.ascontiguousarray(want_ctx, np.uint32), k, ids, sc, threads)
+    return rc, ids, sc
 
 
 def sharded_merge(ids, dists, out_len):

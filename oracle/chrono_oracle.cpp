@@ -766,6 +766,40 @@ void orc_rerank_pool(const uint32_t* cand_ids, const float* cand_dists, uint64_t
   }
 }
 
+// src/store.rs:353-377 — ChronoMind::search_in_context: validate; for every LIVE memory whose context matches:
+// distance = metric.distance(raw stored data, raw query) (the full cosine with norms, NOT distance_prepared),
+// score = combined_score; sort by score (total_cmp); truncate k. The reference iterates a concurrent hash map, so
+// the order among EQUAL scores is unspecified there; here (and on the device) ties resolve toward the lower handle.
+// raw: [n][dim] un-preprocessed rows; context_of: [n] context id per handle; deleted: optional tombstones (handles
+// replaced or removed are not in `by_id`). want_ctx: [nq] context id per query.
+// Returns 0, or 1 = InvalidDimensions, 2 = InvalidVector.
+int orc_search_in_context(const float* raw, uint64_t n, uint64_t dim, const uint32_t* context_of, const uint8_t* deleted,
+                          float temporal_weight, float base_decay_rate, const uint64_t* ts_secs, const uint32_t* ts_nanos,
+                          const float* decay_rate, uint64_t now_secs, uint32_t now_nanos, const float* q, uint64_t nq,
+                          uint64_t qdim, const uint32_t* want_ctx, uint64_t k, uint32_t* ids, float* scores, int threads) {
+  if (qdim != dim) return 1;
+  for (uint64_t i = 0; i < nq * qdim; ++i)
+    if (!std::isfinite(q[i])) return 2;
+  parallel_for(nq, threads, [&](size_t qi) {
+    std::vector<ScoredHandle> scored;
+    for (uint64_t r = 0; r < n; ++r) {
+      if (context_of[r] != want_ctx[qi] || (deleted && deleted[r])) continue;
+      float d = metric_distance(raw + r * dim, dim, q + qi * qdim, qdim);
+      scored.push_back({(uint32_t)r, combined_score(d, ts_secs[r], ts_nanos[r], decay_rate[r], now_secs, now_nanos,
+                                                    temporal_weight, base_decay_rate)});
+    }
+    std::stable_sort(scored.begin(), scored.end(), [](const ScoredHandle& a, const ScoredHandle& b) {
+      return total_key(a.score) < total_key(b.score);
+    });
+    for (uint64_t j = 0; j < k; ++j) {
+      bool ok = j < scored.size();
+      ids[qi * k + j] = ok ? scored[j].handle : 0xFFFFFFFFu;
+      scores[qi * k + j] = ok ? scored[j].score : std::numeric_limits<float>::infinity();
+    }
+  });
+  return 0;
+}
+
 // src/index/sharded_rwlock.rs:81-94 — merge per-shard lists: concat, sort by
 // (dist, global id), truncate. lists: [n_shards][nq][len] local ids/dists
 // (UINT32_MAX = padding); global id = local * n_shards + shard (the
