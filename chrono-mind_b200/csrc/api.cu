@@ -304,7 +304,7 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   bool tc_ok = !pq.degenerate && idx->all_finite && scan_tc_supported(d, k);
   bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && nq >= 64 && d.n >= 8192);
   if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
-    return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 64 and a corpus without NaN/Inf components");
+    return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;
   if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s);
   return exact_topk_fp32(idx, ws, pq.qn, pq.ld, pq.degenerate, nq, k, ids, dist, nullptr, nullptr, s);

@@ -630,10 +630,10 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 uint64_t scan_tc_pad_rows(uint64_t n) { return (n + BN - 1) / BN * BN; }
 uint32_t scan_tc_pad_queries(uint32_t nq) { return (nq + PAIR_M - 1) / PAIR_M * PAIR_M; }
 uint32_t scan_tc_pad_k(uint32_t dim) { return (dim + BK - 1) / BK * BK; }
-uint32_t scan_tc_cand_cap(uint32_t k) { return k <= 16 ? 4096u : 8192u; }
+uint32_t scan_tc_cand_cap(uint32_t k) { return k <= 16 ? 4096u : (k <= 64 ? 8192u : 16384u); }
 
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
-  return ix.xbf16 != nullptr && k >= 1 && k <= 64 && encode_fn() != nullptr;
+  return ix.xbf16 != nullptr && k >= 1 && k <= 128 && encode_fn() != nullptr;
 }
 
 // Corpus splits per query-tile pair: minimise waves x (tiles per unit + a few tiles of pipeline fill / cold start).
@@ -700,7 +700,7 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.flag_list = l.flag_list;
   a.flag_cap = l.flag_cap;
   a.rescored_total = l.rescored_total;
-  a.rs_max = l.k <= 16 ? 2048u : 4096u;
+  a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
   const size_t smem = (size_t)RS_ROWS * ((size_t)ix.dim_pad * 4 + RG_ROW_PAD) + (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 +
                       (size_t)ix.dim_pad * 4;
   {  // per device, so set on every launch (microseconds)
