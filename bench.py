@@ -191,10 +191,13 @@ def run_hnsw(args, rank, world, local_rank):
     st = ChronoMindB200.from_matrix(shard, cfg, sharding.shard_attrs(ts_s, rank, world), sharding.shard_attrs(ts_n, rank, world),
                                     sharding.shard_attrs(decay, rank, world)).set_shard(rank, world)
     t0 = time.time()
-    st.build_graph(SEED + rank, threads)
+    if args.build == "gpu":
+        st.build_graph_gpu(SEED + rank, local_rank, threads)
+    else:
+        st.build_graph(SEED + rank, threads)
     build_s = time.time() - t0
-    log("[bench] rank %d host graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
-        % (rank, shard.shape[0], args.efc, threads, build_s, shard.shape[0] / build_s, st.check_invariants()))
+    log("[bench] rank %d %s graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
+        % (rank, args.build, shard.shape[0], args.efc, threads, build_s, shard.shape[0] / build_s, st.check_invariants()))
     st.upload(local_rank)
     g_ts_s = torch.from_numpy(ts_s.view(np.int64)).to(dev)
     g_ts_n = torch.from_numpy(ts_n.view(np.int32)).to(dev)
@@ -336,7 +339,8 @@ def run_hnsw(args, rank, world, local_rank):
             "config": {"workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, ef=%d, M=16 efC=%d host-built graph%s "
                                    "(BASELINE configs[2]); temporal rerank w=0.3 in the e2e leg"
                                    % (n_rows, DIM, args.data, nq, K, args.ef, args.efc, "" if world == 1 else " per shard, %d shards by id" % world),
-                       "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build_s": build_s, "build_threads": threads,
+                       "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build": args.build, "graph_build_s": build_s,
+                       "graph_build_inserts_per_s": shard.shape[0] / build_s, "build_threads": threads,
                        "parallelism": "1 GPU" if world == 1 else "independent HNSW sub-graph per shard on %d GPUs, NCCL allgather + device merge (+ rerank of the global top-ef in e2e)" % world,
                        "l2": "%.2f GB fp32 rows per GPU gathered at random: larger than L2; 2 query batches rotated" % (n_rows / world * DIM * 4 / 1e9)},
             "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
@@ -371,6 +375,9 @@ def main():
     ap.add_argument("--efs", default="64,128,200", help="hnsw: every ef measured (reported under config.per_ef)")
     ap.add_argument("--efc", type=int, default=100, help="hnsw: ef_construction of the host-built graph")
     ap.add_argument("--data", default="emb", choices=["emb", "uniform"])
+    ap.add_argument("--build", default="host", choices=["host", "gpu"],
+                    help="hnsw: graph construction — host (LockFreeHnsw::insert restatement, all cores) or gpu-assisted "
+                         "(all-pairs kNN candidates on the device, select/link on the host)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

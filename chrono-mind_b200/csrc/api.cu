@@ -238,7 +238,7 @@ static cm_status exact_topk_fp32(const cm_index* idx, Workspace* ws, const float
 
 // tcgen05 bf16 scan + exact fp32 rescore (+ in-stream fp32 fallback for flagged queries). See scan_tc.cu.
 static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
-                               uint32_t* ids, float* dist, cudaStream_t s) {
+                               uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
   const DeviceIndex& d = idx->dev;
   const uint32_t nq_pad = scan_tc_pad_queries(nq);
   tl_used_tc = true;
@@ -281,6 +281,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
   rl.flag_list = reinterpret_cast<uint32_t*>(small + 256);
   rl.flag_cap = kFlagCap;
+  rl.approx = approx;
   CM_CUDA(launch_rescore(d, rl, s));
   // Flagged queries (candidate overflow / too few survivors): exact fp32 scan, in stream, no host round trip.
   CM_CUDA(launch_gather_rows(pq.qn, pq.ld, rl.flag_list, rl.flag_count, kFlagCap, ws->qflag.as<float>(), s));
@@ -290,7 +291,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
 
 // Exact top-`k` by (distance, handle) into ids/dist [nq][k] (device).
 static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
-                            uint32_t* ids, float* dist, cudaStream_t s) {
+                            uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
   const DeviceIndex& d = idx->dev;
   if (nq == 0) return CM_OK;
   if (d.n == 0) {
@@ -306,7 +307,7 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
     return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;
-  if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s);
+  if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s, approx);
   return exact_topk_fp32(idx, ws, pq.qn, pq.ld, pq.degenerate, nq, k, ids, dist, nullptr, nullptr, s);
 }
 
@@ -375,11 +376,11 @@ static cm_status strided_copy(void* dst, size_t dpitch, const void* src, size_t 
 }
 
 static cm_status search_exact_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim,
-                                       uint32_t k, uint32_t* ids, float* dist, cudaStream_t s) {
+                                       uint32_t k, uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
   PreparedQueries pq;
   cm_status st = prepare_queries(idx, ws, q, nq, qdim, nullptr, s, &pq);
   if (st != CM_OK) return st;
-  return exact_topk(idx, ws, pq, nq, k, ids, dist, s);
+  return exact_topk(idx, ws, pq, nq, k, ids, dist, s, approx);
 }
 
 static cm_status search_hnsw_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim,
@@ -1040,8 +1041,8 @@ static cm_status host_begin(const cm_index* idx, Workspace* ws, const float* q, 
   return CM_OK;
 }
 
-cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k, uint32_t* ids,
-                          float* dist) {
+static cm_status search_exact_host(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
+                                   uint32_t* ids, float* dist, bool approx) {
   cm_status st = check_search_args(idx, q, nq, k, ids, dist);
   if (st != CM_OK) return st;
   if ((st = set_device(idx)) != CM_OK) return st;
@@ -1050,7 +1051,7 @@ cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
   tl_used_tc = false;
-  st = search_exact_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, hc.ids_dev, hc.a_dev, hc.s);
+  st = search_exact_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, hc.ids_dev, hc.a_dev, hc.s, approx);
   if (st != CM_OK) return st;
   size_t ob = (size_t)nq * k * 4;
   if (ob) {
@@ -1072,6 +1073,60 @@ cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint
       CM_CUDA(cudaStreamSynchronize(hc.s));
     }
   }
+  return CM_OK;
+}
+
+cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k, uint32_t* ids,
+                          float* dist) {
+  return search_exact_host(idx, q, nq, qdim, k, ids, dist, false);
+}
+
+// GPU-assisted graph construction (host half in hnsw_build.cpp): per layer, the candidate
+// neighbors of every member come from one all-pairs kNN of the layer's members on the device (tensor-core scan,
+// bf16-ranked, in batches of queries), then the host selects and links like `LockFreeHnsw::insert`.
+cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const uint64_t n = idx->n;
+  const uint32_t dim = idx->dim;
+  const uint32_t M = (uint32_t)idx->config.index.max_connections;
+  uint32_t C = n_candidates ? n_candidates : (uint32_t)std::min<uint64_t>(idx->config.index.ef_construction, 64);
+  C = std::min(std::max(C, M + 1), 127u);
+  std::vector<std::vector<uint32_t>> members;
+  layer_members(n, idx->config.index, layer_seed, &members);
+  std::vector<LayerCandidates> layers(members.size());
+  for (size_t layer = 0; layer < members.size(); ++layer) {
+    LayerCandidates& lc = layers[layer];
+    lc.members.swap(members[layer]);
+    const uint64_t nm = lc.members.size();
+    if (nm <= 1) continue;
+    const uint32_t k = (uint32_t)std::min<uint64_t>(C + 1, nm);  // + the member itself (its own nearest neighbor)
+    lc.width = k;
+    lc.ids.assign(nm * k, CM_NO_ID);
+    cm_index* tmp = new_index(idx->config, nm, dim);
+    tmp->all_finite = idx->all_finite;
+    if (layer == 0) {
+      tmp->x.swap(idx->x);  // layer 0 == every row: borrow the matrix instead of copying it
+    } else {
+      tmp->x.resize(nm * (uint64_t)dim);
+      for (uint64_t i = 0; i < nm; ++i)
+        std::memcpy(&tmp->x[i * dim], &idx->x[(uint64_t)lc.members[i] * dim], (size_t)dim * 4);
+    }
+    cm_status st = cm_index_upload(tmp, device);
+    const uint32_t batch = 16384;
+    std::vector<float> dist_scratch((size_t)std::min<uint64_t>(batch, nm) * k);
+    for (uint64_t q0 = 0; st == CM_OK && q0 < nm; q0 += batch) {
+      const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nm - q0);
+      st = search_exact_host(tmp, tmp->x.data() + q0 * dim, nb, dim, k, &lc.ids[q0 * k], dist_scratch.data(), /*approx=*/true);
+    }
+    if (layer == 0) tmp->x.swap(idx->x);
+    cm_index_free(tmp);
+    if (st != CM_OK) return st;
+    if (layer > 0)  // subset-local -> global handles
+      for (uint32_t& v : lc.ids)
+        if (v != CM_NO_ID) v = lc.members[v];
+  }
+  build_graph_from_candidates(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
   return CM_OK;
 }
 

@@ -69,6 +69,17 @@ void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params
                  Graph* g);
 int check_graph_invariants(const Graph& g);
 
+// GPU-assisted construction (hnsw_build.cpp): per layer, the members (ascending handles) and `width` candidate
+// neighbors per member (global handles, CM_NO_ID padded; may contain the member itself).
+struct LayerCandidates {
+  std::vector<uint32_t> members;
+  std::vector<uint32_t> ids;  // [members.size()][width]
+  uint32_t width = 0;
+};
+void layer_members(uint64_t n, const cm_index_params& p, uint64_t seed, std::vector<std::vector<uint32_t>>* out);
+void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
+                                 int threads, const std::vector<LayerCandidates>& layers, Graph* g);
+
 // Host metric kernels (same arithmetic as src/metric.rs; see metric_host.h).
 void preprocess_row(const float* v, uint32_t n, float* out);
 

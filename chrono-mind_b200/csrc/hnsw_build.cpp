@@ -305,8 +305,8 @@ struct Builder {
 
 }  // namespace
 
-void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed, int threads,
-                 Graph* g) {
+// Layer draw (ticket == handle) and the empty flat layout.
+static void init_layout(uint64_t n, const cm_index_params& p, uint64_t seed, Graph* g) {
   g->n = n;
   g->cap0 = (uint32_t)(p.max_connections * 2);
   g->capU = (uint32_t)p.max_connections;
@@ -327,6 +327,11 @@ void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params
   g->nbr_up.assign(slots * g->capU, CM_NO_ID);
   g->deg_up.assign(slots, 0);
   g->entry = kEmptyEntry;
+}
+
+void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed, int threads,
+                 Graph* g) {
+  init_layout(n, p, seed, g);
 
   Builder b;
   b.x = x;
@@ -367,6 +372,103 @@ void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params
   }
   g->entry = b.entry.load();
   g->built = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GPU-assisted construction. The expensive part of `LockFreeHnsw::insert` is the
+// `search_layer(ef_construction)` that finds each new node's candidate neighbors (:419-432); here the candidates of
+// EVERY node of a layer come from one exact all-pairs kNN over the layer's members on the tensor cores (the K1 scan
+// with the corpus as its own query set, bf16-ranked — see cm_index_build_graph_gpu in api.cu). The host then does
+// what the reference does with candidates: exact distances, `select_diverse(cands, M)` (:205-240) for the node's
+// own list, and `add_backlink` with overflow re-selection (:246-280) for the reverse edges. Layers and the entry
+// point are the reference's (:126-132, :351-371). The graph is not the one sequential insertion would build (no
+// GPU/CPU build can be, the reference's own concurrent build is order dependent, :21-26) but satisfies
+// `check_invariants` and is searched by the CPU oracle and the device alike.
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+static void parallel_range(uint64_t n, int threads, F f) {
+  if (threads <= 1 || n < 1024) {
+    Scratch s;
+    for (uint64_t i = 0; i < n; ++i) f(i, s);
+    return;
+  }
+  std::atomic<uint64_t> next{0};
+  std::vector<std::thread> ts;
+  for (int t = 0; t < threads; ++t)
+    ts.emplace_back([&] {
+      Scratch s;
+      for (;;) {
+        uint64_t b0 = next.fetch_add(256, std::memory_order_relaxed);
+        if (b0 >= n) break;
+        for (uint64_t i = b0; i < std::min(n, b0 + 256); ++i) f(i, s);
+      }
+    });
+  for (auto& t : ts) t.join();
+}
+
+void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
+                                 int threads, const std::vector<LayerCandidates>& layers, Graph* g) {
+  init_layout(n, p, seed, g);
+  Builder b;
+  b.x = x;
+  b.n = n;
+  b.dim = dim;
+  b.M = (uint32_t)p.max_connections;
+  b.efC = (uint32_t)p.ef_construction;
+  b.cap0 = g->cap0;
+  b.capU = g->capU;
+  b.g = g;
+  if (threads < 1) threads = 1;
+  b.mt = threads > 1;
+  if (b.mt) {
+    b.locks.reset(new std::atomic<uint8_t>[n]);
+    for (uint64_t i = 0; i < n; ++i) b.locks[i].store(0, std::memory_order_relaxed);
+  }
+  for (uint32_t layer = 0; layer < layers.size(); ++layer) {
+    const LayerCandidates& lc = layers[layer];
+    const uint64_t nm = lc.members.size();
+    std::vector<uint32_t> own(nm * b.M, CM_NO_ID);
+    std::vector<uint8_t> own_deg(nm, 0);
+    // phase A: every member's own list from its candidates (no shared writes)
+    parallel_range(nm, threads, [&](uint64_t i, Scratch& s) {
+      const uint32_t u = lc.members[i];
+      s.with_d.clear();
+      for (uint32_t j = 0; j < lc.width; ++j) {
+        uint32_t v = lc.ids[i * lc.width + j];
+        if (v == CM_NO_ID || v == u) continue;
+        s.with_d.push_back(pack(dist_prepared(b.row(v), b.row(u), dim), v));
+      }
+      std::sort(s.with_d.begin(), s.with_d.end());
+      s.with_d.erase(std::unique(s.with_d.begin(), s.with_d.end()), s.with_d.end());
+      b.select_diverse(s.with_d.data(), s.with_d.size(), b.M, s);
+      own_deg[i] = (uint8_t)s.result.size();
+      std::memcpy(&own[i * b.M], s.result.data(), s.result.size() * sizeof(uint32_t));
+      uint32_t* deg;
+      uint32_t* l = b.list_ptr(u, layer, &deg);
+      std::memcpy(l, s.result.data(), s.result.size() * sizeof(uint32_t));
+      *deg = (uint32_t)s.result.size();
+    });
+    // phase B: reverse edges (per-node locks; overflowing lists are re-selected like the reference's)
+    parallel_range(nm, threads, [&](uint64_t i, Scratch& s) {
+      const uint32_t u = lc.members[i];
+      for (uint32_t j = 0; j < own_deg[i]; ++j) b.add_backlink(own[i * b.M + j], u, layer, s);
+    });
+  }
+  // raise_entry under in-order insertion (:351-371): the first handle that reaches the highest layer
+  for (uint64_t i = 0; i < n; ++i)
+    if (g->entry == kEmptyEntry || g->top_layer[i] > (uint32_t)(g->entry >> 32)) g->entry = ((uint64_t)g->top_layer[i] << 32) | i;
+  g->built = true;
+}
+
+// Members of layer `layer` (ascending handles) for the layer draw of (n, params, seed).
+void layer_members(uint64_t n, const cm_index_params& p, uint64_t seed, std::vector<std::vector<uint32_t>>* out) {
+  double ml = 1.0 / std::log((double)p.max_connections);
+  out->clear();
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t t = draw_layer(seed, i, ml);
+    if (out->size() < (size_t)t + 1) out->resize(t + 1);
+    for (uint32_t l = 0; l <= t; ++l) (*out)[l].push_back((uint32_t)i);
+  }
 }
 
 // src/index/lockfree_hnsw.rs:295-347 on the flat layout. 0 == sound.

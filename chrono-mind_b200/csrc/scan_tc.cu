@@ -503,6 +503,7 @@ struct RescoreArgs {
   const unsigned long long* cand;
   uint32_t cap;
   uint32_t rs_max;        // candidates above the final scan threshold handled per query (power of two)
+  uint32_t approx;        // 1: emit the top-k by bf16 score (distance = 1 - score) without the exact rescore
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
       if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);  // sorted: the kept set is a prefix
     __syncthreads();
     keep = n_keep;
-    bad = keep > RS2_MAX;
+    bad = !a.approx && keep > RS2_MAX;
   }
   if (bad) {
     if (tid == 0) {
@@ -566,6 +567,15 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
       a.ids[(uint64_t)q * a.k + i] = CM_NO_ID_DEV;
       a.dist[(uint64_t)q * a.k + i] = __int_as_float(0x7FC00000);
+    }
+    return;
+  }
+  if (a.approx) {  // candidate generation for graph construction: bf16 ranking is enough, the host re-measures
+    for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
+      const bool ok = i < ns;
+      const unsigned long long c = ok ? ~keys[i] : 0ull;
+      a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)c : CM_NO_ID_DEV;
+      a.dist[(uint64_t)q * a.k + i] = ok ? clamp02(1.0f - key_to_float((uint32_t)(c >> 32))) : __int_as_float(0x7F800000);
     }
     return;
   }
@@ -637,10 +647,13 @@ bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
 }
 
 // Corpus splits per query-tile pair: minimise waves x (tiles per unit + a few tiles of pipeline fill / cold start).
-static uint32_t pick_splits(uint32_t m_pairs, uint32_t n_tiles, uint32_t clusters) {
+// Every split of a query starts cold (its own running top-k) and emits ~k·(1 + ln(rows/k)) candidates before its
+// threshold converges, so the number of splits is also bounded by the candidate buffer: splits·k·16 <= cap.
+static uint32_t pick_splits(uint32_t m_pairs, uint32_t n_tiles, uint32_t clusters, uint32_t k, uint32_t cap) {
   uint32_t best = 1;
   uint64_t best_cost = ~0ull;
-  for (uint32_t s = 1; s <= std::min<uint32_t>(n_tiles, 128); ++s) {
+  const uint32_t max_splits = std::max(1u, cap / (16u * k));
+  for (uint32_t s = 1; s <= std::min<uint32_t>(std::min<uint32_t>(n_tiles, 128), max_splits); ++s) {
     uint64_t tiles_per = (n_tiles + s - 1) / s;
     uint64_t waves = ((uint64_t)m_pairs * s + clusters - 1) / clusters;
     uint64_t cost = waves * (tiles_per + 3);
@@ -661,7 +674,7 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.n_tiles = (uint32_t)(ix.n_pad / BN);
   a.k_blocks = ix.k_pad / BK;
   a.k = l.k;
-  a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters);
+  a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters, l.k, l.cap);
   a.tau_key = l.tau_key;
   a.cand_cnt = l.cand_cnt;
   a.cand = l.cand;
@@ -701,6 +714,7 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.flag_cap = l.flag_cap;
   a.rescored_total = l.rescored_total;
   a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
+  a.approx = l.approx ? 1u : 0u;
   const size_t smem = (size_t)RS_ROWS * ((size_t)ix.dim_pad * 4 + RG_ROW_PAD) + (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 +
                       (size_t)ix.dim_pad * 4;
   {  // per device, so set on every launch (microseconds)

@@ -36,6 +36,7 @@ struct RescoreLaunch {
   uint32_t* flag_list;       // [flag_cap]
   uint32_t flag_cap;
   unsigned long long* rescored_total;
+  bool approx = false;       // top-k by bf16 score, no exact rescore (graph-construction candidates)
 };
 cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaStream_t s);
 

@@ -64,6 +64,7 @@ ABI = {
     "cm_index_context_id": (_u32, [_vp, C.c_char_p]),
     "cm_index_remove": (_i, [_vp, _u32, C.POINTER(_i)]),
     "cm_index_build_graph": (_i, [_vp, _u64, _i]),
+    "cm_index_build_graph_gpu": (_i, [_vp, _u64, _i, _i, _u32]),
     "cm_index_set_shard": (_i, [_vp, _u32, _u32]),
     "cm_index_upload": (_i, [_vp, _i]),
     "cm_index_free": (None, [_vp]),
@@ -227,6 +228,11 @@ class ChronoMindB200:
 
     def build_graph(self, layer_seed: int = 0x5EED, threads: int = 1):
         _check(native().cm_index_build_graph(self._h, layer_seed & (2 ** 64 - 1), threads))
+        return self
+
+    def build_graph_gpu(self, layer_seed: int = 0x5EED, device: int = 0, threads: int = 0, n_candidates: int = 0):
+        """GPU-assisted construction: per-layer all-pairs kNN candidates on the device, select/link on the host."""
+        _check(native().cm_index_build_graph_gpu(self._h, layer_seed & (2 ** 64 - 1), device, threads, n_candidates))
         return self
 
     def save_graph(self, path):

@@ -122,6 +122,14 @@ cm_status cm_index_remove(cm_index* idx, uint32_t handle, int* removed);
  * to run. Needed before cm_search_hnsw / cm_search_temporal(exact = 0). */
 cm_status cm_index_build_graph(cm_index* idx, uint64_t layer_seed, int threads);
 
+/* GPU-assisted construction: the candidate neighbors of every node (`search_layer(ef_construction)`
+ * in `LockFreeHnsw::insert`, src/index/lockfree_hnsw.rs:419-432) come from an all-pairs kNN of each layer's members
+ * on CUDA device `device` (tensor-core scan, `n_candidates` nearest per node, 0 = min(ef_construction, 64), at most
+ * 127); the host then applies the reference's `select_diverse` (:205-240) and `add_backlink` (:246-280) with `threads`
+ * threads. Same layer draw and entry point as cm_index_build_graph; the linkage differs (as it does between any two
+ * concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. */
+cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates);
+
 /* Sharding by vector id (generalises `join_handle`/`split`, src/index/sharded_rwlock.rs:54-66):
  * this index holds the rows whose global handle = local * shard_count + shard_rank. Only affects the ids the
  * merge kernel emits. Default (0, 1). */

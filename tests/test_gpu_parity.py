@@ -380,3 +380,33 @@ def test_sharded_store_search_is_merge_then_rerank():
     assert same.mean() > 0.999
     assert np.allclose(got_s[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
     assert np.all(np.diff(got_s, axis=1) >= 0)
+
+
+def test_gpu_assisted_build_is_sound_searchable_and_oracle_identical(tmp_path):
+    """candidates from the device's all-pairs kNN, select/link on the host. Same layer draw and entry
+    as the host builder; passes check_invariants; recall@10 at ef=64 no worse than the host-built graph's minus 0.01;
+    and the traversal of THAT graph is still the oracle's traversal (ids, distance bits, work counters)."""
+    data, q = datasets.embedding_dataset(30000, 256, 0xB111D)
+    cfg = default_config(dimensions=768, ef_construction=100)
+    host = ChronoMindB200.from_matrix(data, cfg).build_graph(0xB111D, 8).upload(0)
+    gpu = ChronoMindB200.from_matrix(data, cfg).build_graph_gpu(0xB111D, 0, 8).upload(0)
+    assert gpu.check_invariants() == 0
+    assert gpu.entry() == host.entry()
+    assert [gpu.top_layer(i) for i in range(0, 30000, 97)] == [host.top_layer(i) for i in range(0, 30000, 97)]
+    truth, _ = host.search_exact(q, 10)
+
+    def recall(st):
+        ids, _ = st.search_index(q, 64, 10)
+        return float(np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ids.tolist(), truth.tolist())]))
+    r_host, r_gpu = recall(host), recall(gpu)
+    assert r_gpu >= 0.95 and r_gpu >= r_host - 0.01, (r_host, r_gpu)
+    p = str(tmp_path / "g.cmg")
+    gpu.save_graph(p)
+    orc = oracle.OracleHnsw(16, 100, 50, 0xB111D)
+    orc.import_graph(oracle.preprocess_rows(data, threads=8), oracle.read_graph_sidecar(p))
+    assert orc.check_invariants() == 0
+    oi, od, _, octr = orc.search_batch(q, 64, 10, threads=8)
+    gi, gd = gpu.search_index(q, 64, 10)
+    c = last_counters()
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1])
