@@ -652,9 +652,12 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
 }
 
 cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_t* context_ids) {
-  if (!idx || (idx->n && (!raw_x || !context_ids))) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!idx || (idx->n && !raw_x)) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
   idx->raw.assign(raw_x, raw_x + idx->n * (uint64_t)idx->dim);
-  idx->ctx.assign(context_ids, context_ids + idx->n);
+  if (context_ids)
+    idx->ctx.assign(context_ids, context_ids + idx->n);
+  else
+    idx->ctx.assign(idx->n, 0);  // one context
   return CM_OK;
 }
 
@@ -1127,6 +1130,92 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
         if (v != CM_NO_ID) v = lc.members[v];
   }
   build_graph_from_candidates(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
+  return CM_OK;
+}
+
+// consolidate's all-pairs pass (src/store.rs:516-568, the `similarity > similarity_threshold` test of every pair)
+// as a threshold self-join: the tensor-core scan with the corpus as its own query set emits the pairs whose bf16
+// score can exceed the threshold, the exact `metric.similarity` on the raw rows decides. Pairs (i < j, both live),
+// ascending (i, j). *count receives the number found; at most `cap` are written.
+cm_status cm_similar_pairs(const cm_index* idx, float threshold, uint32_t* out_i, uint32_t* out_j, float* out_sim,
+                           uint64_t cap, uint64_t* count) {
+  if (!idx || !count) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  *count = 0;
+  if (!idx->uploaded) return fail(CM_ERR_CUDA, "index is not resident on a CUDA device (call cm_index_upload); there is no CPU path");
+  const DeviceIndex& d = idx->dev;
+  if (d.n == 0) return CM_OK;
+  if (!d.xraw) return fail(CM_ERR_STATE, "the pair test runs on the rows as stored: cm_index_set_contexts / a snapshot, then upload");
+  if (!idx->all_finite || !scan_tc_supported(d, 1)) return fail(CM_ERR_STATE, "the self-join needs the tensor-core scan (finite rows)");
+  cm_status st = set_device(idx);
+  if (st != CM_OK) return st;
+  tl_counters = cm_counters();
+  WorkspaceLease lease(idx);
+  Workspace* ws = lease.ws;
+  if (!ws->stream) CM_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+  cudaStream_t s = ws->stream;
+  CM_CUDA(ws->small.ensure(kSmallBytes));
+  uint32_t* pair_count = ws->small.as<uint32_t>() + 32;  // offset 128
+  uint64_t pcap = std::max<uint64_t>(1u << 20, 4 * cap);
+  uint32_t found = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CM_CUDA(ws->cand.ensure(pcap * 8));
+    CM_CUDA(cudaMemsetAsync(pair_count, 0, 4, s));
+    ScanTcLaunch sl;
+    sl.q_bf16 = d.xbf16;
+    sl.nq = (uint32_t)d.n;
+    sl.k = 1;
+    sl.tau_key = nullptr;
+    sl.cand_cnt = nullptr;
+    sl.cand = nullptr;
+    sl.cap = 16;
+    sl.join = true;
+    sl.join_tau = threshold - scan_tc_eps() - 1e-5f;   // bf16 score >= cos - eps; cos of the unit rows ~ similarity
+    sl.pairs = ws->cand.as<unsigned long long>();
+    sl.pair_count = pair_count;
+    sl.pair_cap = (uint32_t)std::min<uint64_t>(pcap, 0xFFFFFFFFu);
+    {
+      ProfileScope prof(s);
+      CM_CUDA(launch_scan_tc(d, sl, s));
+    }
+    CM_CUDA(cudaMemcpyAsync(&found, pair_count, 4, cudaMemcpyDeviceToHost, s));
+    CM_CUDA(cudaStreamSynchronize(s));
+    if (found <= pcap) break;
+    if (attempt == 1) return fail(CM_ERR_CAPACITY_EXCEEDED, "more candidate pairs than the join buffer holds");
+    pcap = found;  // the count is exact: retry once with room for all of them
+  }
+  tl_counters.dist_evals += d.n * (d.n - 1) / 2;
+  tl_counters.rescored += found;
+  if (found == 0) return CM_OK;
+  CM_CUDA(ws->D.ensure((size_t)found * 4));
+  CM_CUDA(launch_pair_similarity(d.xraw, d.dim_pad, d.dim, d.norm2_raw, ws->cand.as<unsigned long long>(), found,
+                                 ws->D.as<float>(), s));
+  std::vector<unsigned long long> pairs(found);
+  std::vector<float> sims(found);
+  CM_CUDA(cudaMemcpyAsync(pairs.data(), ws->cand.p, (size_t)found * 8, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaMemcpyAsync(sims.data(), ws->D.p, (size_t)found * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaStreamSynchronize(s));
+  std::vector<std::pair<unsigned long long, float>> keep;
+  for (uint32_t i = 0; i < found; ++i)
+    if (sims[i] > threshold) keep.emplace_back(pairs[i], sims[i]);   // `similarity <= threshold => continue`
+  std::sort(keep.begin(), keep.end());
+  *count = keep.size();
+  for (uint64_t i = 0; i < keep.size() && i < cap; ++i) {
+    if (out_i) out_i[i] = (uint32_t)(keep[i].first >> 32);
+    if (out_j) out_j[i] = (uint32_t)keep[i].first;
+    if (out_sim) out_sim[i] = keep[i].second;
+  }
+  return CM_OK;
+}
+
+cm_status cm_decay_sweep_dev(void* importance, void* decayed_through_nanos, const void* last_access_nanos,
+                             const void* decay_rate, uint64_t n, float base_decay_rate, uint64_t now_nanos, int device,
+                             void* stream) {
+  if (n && (!importance || !decayed_through_nanos || !last_access_nanos || !decay_rate))
+    return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_decay_sweep((float*)importance, (unsigned long long*)decayed_through_nanos,
+                             (const unsigned long long*)last_access_nanos, (const float*)decay_rate, n, base_decay_rate,
+                             now_nanos, (cudaStream_t)stream));
   return CM_OK;
 }
 

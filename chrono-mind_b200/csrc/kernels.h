@@ -60,6 +60,14 @@ cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, u
                                     const uint32_t* active_count, uint32_t active_base, cudaStream_t s,
                                     bool skip_inf = false);
 
+// consolidate's pair test (src/store.rs:531-534) on candidate pairs (a << 32 | b) of raw rows: sim[p] = similarity.
+cudaError_t launch_pair_similarity(const float* x, uint32_t ld, uint32_t dim, const float* norm2,
+                                   const unsigned long long* pairs, uint32_t n_pairs, float* sim, cudaStream_t s);
+// apply_decay sweep (src/store.rs:428-458) over caller-owned state arrays.
+cudaError_t launch_decay_sweep(float* importance, unsigned long long* decayed_through, const unsigned long long* last_access,
+                               const float* decay_rate, uint64_t n, float base_rate, unsigned long long now_nanos,
+                               cudaStream_t s);
+
 // K5 — shard merge (src/index/sharded_rwlock.rs:81-94).
 cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
                               uint32_t out_len, uint32_t* out_ids, float* out_dist, cudaStream_t s);

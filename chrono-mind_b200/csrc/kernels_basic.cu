@@ -352,6 +352,83 @@ cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// consolidate's pair test (src/store.rs:531-534): similarity = metric.similarity(a.data, b.data) on the RAW rows —
+// cosine (src/metric.rs:163-186) or 0 when undefined. One lane octet per candidate pair of the self-join; the dot
+// chain is dot_and_norms_avx2's, the squared norms come precomputed in the same arithmetic.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_similarity(const float* __restrict__ x, uint32_t ld, uint32_t dim,
+                                                         const float* __restrict__ norm2,
+                                                         const unsigned long long* __restrict__ pairs, uint32_t n_pairs,
+                                                         float* __restrict__ sim) {
+  uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  uint32_t j = threadIdx.x & 7;
+  bool valid = p < n_pairs;
+  unsigned long long pr = valid ? pairs[p] : 0ull;
+  uint32_t ia = (uint32_t)(pr >> 32), ib = (uint32_t)pr;
+  const float* pa = x + (uint64_t)ia * ld;
+  const float* pb = x + (uint64_t)ib * ld;
+  uint32_t body = dim & ~7u;
+  float acc = 0.0f;
+  if (valid)
+    for (uint32_t e = j; e < body; e += 8) acc = __fmaf_rn(__ldg(pa + e), __ldg(pb + e), acc);
+  float dot = octet_hsum(acc);
+  if (valid) {
+    for (uint32_t e = body; e < dim; ++e) dot = __fadd_rn(dot, __fmul_rn(pa[e], pb[e]));
+    if (j == 0) {
+      const float denom = __fsqrt_rn(__fmul_rn(norm2[ia], norm2[ib]));
+      float c = 0.0f;  // unwrap_or(0.0)
+      if (!(denom <= 1.1920929e-7f)) {
+        c = __fdiv_rn(dot, denom);
+        c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);
+      }
+      sim[p] = c;
+    }
+  }
+}
+
+cudaError_t launch_pair_similarity(const float* x, uint32_t ld, uint32_t dim, const float* norm2,
+                                   const unsigned long long* pairs, uint32_t n_pairs, float* sim, cudaStream_t s) {
+  if (n_pairs == 0) return cudaSuccess;
+  uint64_t threads = (uint64_t)n_pairs * 8;
+  k_pair_similarity<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, ld, dim, norm2, pairs, n_pairs, sim);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// apply_decay sweep (src/store.rs:428-458), one thread per memory: claim the interval (from, now], scale importance
+// by exp(-rate * hours), clamp to [0, 1] (scale_importance, :114-128). The CAS gate of the reference protects
+// against concurrent sweeps; one launch is one sweep.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_decay_sweep(float* __restrict__ importance, unsigned long long* __restrict__ decayed_through,
+                              const unsigned long long* __restrict__ last_access, const float* __restrict__ decay_rate,
+                              uint64_t n, float base_rate, unsigned long long now_nanos) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long prev = decayed_through[i];
+    const unsigned long long la = last_access[i];
+    const unsigned long long from = prev > la ? prev : la;
+    if (now_nanos <= from) continue;
+    decayed_through[i] = now_nanos;
+    const float hours = __fdiv_rn(__fdiv_rn(__ull2float_rn(now_nanos - from), 1.0e9f), 3600.0f);
+    const float r = decay_rate[i];
+    const float rate = r > 0.0f ? r : base_rate;
+    const float factor = (float)exp((double)__fmul_rn(-rate, hours));  // correctly rounded f32::exp
+    float v = __fmul_rn(importance[i], factor);
+    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);                    // f32::clamp(0, 1): NaN passes through
+    importance[i] = v;
+  }
+}
+
+cudaError_t launch_decay_sweep(float* importance, unsigned long long* decayed_through, const unsigned long long* last_access,
+                               const float* decay_rate, uint64_t n, float base_rate, unsigned long long now_nanos,
+                               cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_decay_sweep<<<148 * 4, 256, 0, s>>>(importance, decayed_through, last_access, decay_rate, n, base_rate, now_nanos);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Top-k select: the k smallest (TotalF32 distance, handle) tuples of one row of D per CTA — the stable
 // `sort_by(total_cmp)` + `take(k)` of tests/recall_test.rs:77-78 / tests/property_test.rs:206 without sorting
 // the row. Threshold filter + shared-memory candidate buffer + bitonic flushes.

@@ -195,6 +195,12 @@ struct ScanArgs {
   uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
   unsigned long long* cand;      // [m_pairs*256][cap]  (ordered score key << 32 | row); 0 = unused slot
   uint32_t cap;
+  // threshold self-join (consolidate's all-pairs pass): fixed threshold, only row > query, pairs to one list
+  uint32_t join;                 // 1: join mode (Q == X)
+  float join_tau;                // bf16-score threshold (the caller already subtracted the error bound)
+  unsigned long long* pairs;     // [pair_cap] (query << 32 | row)
+  uint32_t* pair_count;          // pairs found (may exceed pair_cap: the caller retries with a larger buffer)
+  uint32_t pair_cap;
 };
 
 // Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists [k][128] | barriers | tmem ptr.
@@ -284,8 +290,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
-        const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+        uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
         const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         const int32_t q_row = (int32_t)(m * PAIR_M + rank * BM);
         for (uint32_t t = t0; t < t1; ++t) {
           const int32_t x_row = (int32_t)(t * BN + rank * BN_HALF);
@@ -312,8 +319,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t sp = u / a.m_pairs;
-        const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+        uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
         const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         for (uint32_t t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&tail->tmem_empty[acc]), acc_phase ^ 1);  // both epilogues drained this accumulator
           tc_fence_after();
@@ -354,8 +362,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t u = cluster_id; u < units; u += n_clusters) {
       const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
-      const uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
+      uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
       const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+      if (a.join) t0 = max(t0, m);  // self-join keeps row > query: tiles below the diagonal are skipped
       const uint32_t q = m * PAIR_M + rank * BM + row_in_cta;
       const bool q_valid = q < a.nq;
       unsigned long long* my_cand = a.cand + (uint64_t)q * a.cap;
@@ -366,7 +375,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t slot_next = 0, slots_left = 0;
       for (uint32_t t = t0; t < t1; ++t) {
         float tau = INFINITY;  // padding queries: nothing passes
-        if (q_valid) {
+        if (q_valid && a.join) {
+          tau = a.join_tau;
+        } else if (q_valid) {
           const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
           const float g = tk ? key_to_float(tk) : -INFINITY;
           tau = fmaxf(g, top.filled == top.k ? top.kth - 2.0f * kEps : -INFINITY);
@@ -380,7 +391,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // main pass below emits ~k rows instead of all 256. Tombstoned and padding rows score NaN (see
         // launch_to_bf16) and never enter a list or pass a threshold.
         const bool cold = q_valid && tau == -INFINITY;
-        bool listed = false;  // this tile's rows are already in the running top-k
+        bool listed = a.join != 0;  // this tile's rows are already in the running top-k (join: there is none)
         if (__any_sync(0xFFFFFFFFu, cold)) {
 #pragma unroll 1
           for (uint32_t c = 0; c < BN; c += 32) {
@@ -417,7 +428,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               const uint32_t i = __ffs(mask) - 1;
               mask &= mask - 1;
               const float s = pick32(r, i);
-              if (s >= tau) {  // tau may have risen inside this loop
+              if (s >= tau && a.join) {
+                const uint32_t row = (uint32_t)(row0 + c + i);
+                if (row > q) {
+                  const uint32_t at = atomicAdd(a.pair_count, 1u);
+                  if (at < a.pair_cap) a.pairs[at] = ((unsigned long long)q << 32) | row;
+                }
+              } else if (s >= tau) {  // tau may have risen inside this loop
                 if (slots_left == 0) {
                   slot_next = atomicAdd(&a.cand_cnt[q], kSlotChunk);
                   slots_left = kSlotChunk;
@@ -640,6 +657,7 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 uint64_t scan_tc_pad_rows(uint64_t n) { return (n + BN - 1) / BN * BN; }
 uint32_t scan_tc_pad_queries(uint32_t nq) { return (nq + PAIR_M - 1) / PAIR_M * PAIR_M; }
 uint32_t scan_tc_pad_k(uint32_t dim) { return (dim + BK - 1) / BK * BK; }
+float scan_tc_eps() { return kEps; }
 uint32_t scan_tc_cand_cap(uint32_t k) { return k <= 16 ? 4096u : (k <= 64 ? 8192u : 16384u); }
 
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
@@ -679,6 +697,12 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.cand_cnt = l.cand_cnt;
   a.cand = l.cand;
   a.cap = l.cap;
+  a.join = l.join ? 1u : 0u;
+  a.join_tau = l.join_tau;
+  a.pairs = l.pairs;
+  a.pair_count = l.pair_count;
+  a.pair_cap = l.pair_cap;
+  if (l.join) a.splits = 1;  // units = query-tile pairs, each from its diagonal tile to the end
   const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 16;
   a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
   if (a.stages < 2) return cudaErrorInvalidValue;

@@ -10,6 +10,7 @@ namespace cm {
 uint64_t scan_tc_pad_rows(uint64_t n);        // corpus rows padded to the X tile height (256)
 uint32_t scan_tc_pad_queries(uint32_t nq);    // queries padded to the Q tile-pair height (256)
 uint32_t scan_tc_cand_cap(uint32_t k);        // candidate slots per query
+float scan_tc_eps();                          // bound on |bf16 tensor-core score - fp32 dot| for unit vectors
 uint32_t scan_tc_pad_k(uint32_t dim);         // columns padded to the K block (64)
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k);
 
@@ -20,6 +21,12 @@ struct ScanTcLaunch {
   uint32_t* cand_cnt;        // [pad_queries(nq)] zeroed
   unsigned long long* cand;  // [pad_queries(nq)][cap]
   uint32_t cap;
+  // threshold self-join (q_bf16 == the corpus copy, nq == n): pairs (query < row) whose bf16 score >= join_tau
+  bool join = false;
+  float join_tau = 0.0f;
+  unsigned long long* pairs = nullptr;
+  uint32_t* pair_count = nullptr;  // zeroed by the caller
+  uint32_t pair_cap = 0;
 };
 cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s);
 

@@ -90,6 +90,8 @@ ABI = {
     "cm_search_exact_dev": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_hnsw_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_temporal_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp, _vp]),
+    "cm_similar_pairs": (_i, [_vp, _f, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "cm_decay_sweep_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _f, _u64, _i, _vp]),
     "cm_merge_topk_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _i, _vp]),
     "cm_rerank_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _f, _f, _u64, _u32, _vp, _vp, _vp, _i, _vp]),
     "cm_metric_preprocess_dev": (_i, [_vp, _u64, _u32, _vp, _i, _vp]),
@@ -207,11 +209,26 @@ class ChronoMindB200:
             arrs.append(a)
         _check(native().cm_index_set_attrs(self._h, *[_ptr(a) for a in arrs]))
 
-    def set_contexts(self, raw_x, context_ids):
+    def similar_pairs(self, threshold=None, cap: int = 1 << 20):
+        """The pair test of `ChronoMind::consolidate` (src/store.rs:531-534) for every pair of live memories:
+        (i[], j[], similarity[]) with i < j and similarity > threshold (default: the config's similarity_threshold)."""
+        thr = self.config.similarity_threshold if threshold is None else threshold
+        while True:
+            i = np.empty(cap, dtype=np.uint32)
+            j = np.empty(cap, dtype=np.uint32)
+            sim = np.empty(cap, dtype=np.float32)
+            cnt = C.c_uint64(0)
+            _check(native().cm_similar_pairs(self._h, thr, _ptr(i), _ptr(j), _ptr(sim), cap, C.byref(cnt)))
+            if cnt.value <= cap:
+                return i[:cnt.value], j[:cnt.value], sim[:cnt.value]
+            cap = int(cnt.value)
+
+    def set_contexts(self, raw_x, context_ids=None):
         """Store-level contexts: the rows as stored (not preprocessed) and one context id per handle."""
         raw_x = np.ascontiguousarray(raw_x, dtype=np.float32)
-        context_ids = np.ascontiguousarray(context_ids, dtype=np.uint32)
-        if raw_x.shape != (self.slots, self.dim) or context_ids.shape != (self.slots,):
+        if context_ids is not None:
+            context_ids = np.ascontiguousarray(context_ids, dtype=np.uint32)
+        if raw_x.shape != (self.slots, self.dim) or (context_ids is not None and context_ids.shape != (self.slots,)):
             raise ValueError("raw_x must be [slots, dim] and context_ids [slots]")
         _check(native().cm_index_set_contexts(self._h, _ptr(raw_x), _ptr(context_ids)))
         return self
@@ -441,6 +458,18 @@ def rerank_cuda(pool_ids, pool_dist, k: int, ts_secs, ts_nanos, decay_rate, temp
                                   ts_nanos.data_ptr(), decay_rate.data_ptr(), temporal_weight, base_decay_rate,
                                   now[0], now[1], oi.data_ptr(), osc.data_ptr(), od.data_ptr(), dev.index or 0, st))
     return oi, osc, od
+
+
+def decay_sweep_cuda(importance, decayed_through_nanos, last_access_nanos, decay_rate, base_decay_rate: float,
+                     now_nanos: int):
+    """One `apply_decay` sweep (src/store.rs:428-458) in place over CUDA tensors: importance f32[n],
+    decayed_through_nanos int64[n] (u64 bits), last_access_nanos int64[n], decay_rate f32[n]."""
+    import torch
+    dev = importance.device
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _check(native().cm_decay_sweep_dev(importance.data_ptr(), decayed_through_nanos.data_ptr(), last_access_nanos.data_ptr(),
+                                       decay_rate.data_ptr(), importance.numel(), base_decay_rate, now_nanos,
+                                       dev.index or 0, st))
 
 
 class Index:

@@ -107,7 +107,7 @@ cm_status cm_index_set_attrs(cm_index* idx, const uint64_t* ts_secs, const uint3
 /* Store-level contexts (`MemoryAttributes.context`, src/types.rs:32-49) for cm_search_in_context: `raw_x` [n][dim]
  * are the rows AS STORED (`StoredMemory.data`, not preprocessed — `search_in_context` calls `metric.distance` on
  * them), `context_ids` [n] one id per handle. Snapshot-loaded indexes carry both already (ids in order of first
- * appearance, see cm_index_context_id). Must precede cm_index_upload. */
+ * appearance, see cm_index_context_id). `context_ids` may be NULL (one context). Must precede cm_index_upload. */
 cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_t* context_ids);
 /* Context id of a label of a snapshot-loaded index; CM_NO_ID when no memory carries it. */
 uint32_t cm_index_context_id(const cm_index* idx, const char* label);
@@ -228,6 +228,20 @@ cm_status cm_rerank_dev(const void* pool_ids, const void* pool_dist, uint32_t nq
                         const void* ts_secs, const void* ts_nanos, const void* decay_rate, float temporal_weight,
                         float base_decay_rate, uint64_t now_secs, uint32_t now_nanos, void* out_ids,
                         void* out_score, void* out_dist, int device, void* stream);
+
+/* ---- maintenance passes over the same device-resident arrays ------------------------------- */
+/* The all-pairs test of `ChronoMind::consolidate` (src/store.rs:516-568: `metric.similarity(a.data, b.data) >
+ * similarity_threshold` for every pair of live memories) as a threshold self-join on the tensor cores: candidate pairs
+ * from the bf16 scan of the corpus against itself, decided by the exact similarity on the rows as stored (needs
+ * cm_index_set_contexts / a snapshot). Pairs i < j ascending (i, j); *count = pairs found, at most `cap` written (any
+ * out pointer may be NULL). The greedy keeper/absorbed bookkeeping stays with the store (write path). */
+cm_status cm_similar_pairs(const cm_index* idx, float threshold, uint32_t* out_i, uint32_t* out_j, float* out_sim,
+                           uint64_t cap, uint64_t* count);
+/* One `apply_decay` sweep (src/store.rs:428-458) over caller-owned device arrays: importance f32[n] (in/out),
+ * decayed_through_nanos u64[n] (in/out), last_access_nanos u64[n], decay_rate f32[n]. */
+cm_status cm_decay_sweep_dev(void* importance, void* decayed_through_nanos, const void* last_access_nanos,
+                             const void* decay_rate, uint64_t n, float base_decay_rate, uint64_t now_nanos, int device,
+                             void* stream);
 
 /* ---- metric surface (`DistanceMetric`, src/metric.rs:13-48) on device rows ---------------------------- */
 /* `preprocess` for each row of a device matrix [n][dim] -> out [n][dim] (may alias). */

@@ -91,6 +91,9 @@ def lib():
     sig("orc_search_in_context", C.c_int,
         [_f32p, C.c_uint64, C.c_uint64, _u32p, C.c_void_p, C.c_float, C.c_float, _u64p, _u32p, _f32p, C.c_uint64,
          C.c_uint32, _f32p, C.c_uint64, C.c_uint64, _u32p, C.c_uint64, _u32p, _f32p, C.c_int])
+    sig("orc_similar_pairs", C.c_uint64,
+        [_f32p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_float, _u32p, _u32p, _f32p, C.c_uint64])
+    sig("orc_decay_sweep", None, [_f32p, _u64p, _u64p, _f32p, C.c_uint64, C.c_float, C.c_uint64])
     sig("orc_sharded_merge", None,
         [_u32p, _f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _f32p])
     if not L.orc_cpu_has_avx2_fma():
@@ -312,6 +315,30 @@ def search_in_context(raw, context_of, q, want_ctx, k, w, base_decay, ts_secs, t
                                      np.ascontiguousarray(ts_nanos, np.uint32), _f32(decay), now_secs, now_nanos, q, nq,
                                      q.shape[1], np.ascontiguousarray(want_ctx, np.uint32), k, ids, sc, threads)
     return rc, ids, sc
+
+
+def similar_pairs(raw, threshold, deleted=None, cap=1 << 20):
+    """The pair test of `ChronoMind::consolidate` (src/store.rs:531-534): (i, j, similarity), i < j, ascending (i, j)."""
+    raw = _f32(raw)
+    oi = np.empty(cap, dtype=np.uint32)
+    oj = np.empty(cap, dtype=np.uint32)
+    osim = np.empty(cap, dtype=np.float32)
+    dptr = None
+    if deleted is not None:
+        deleted = np.ascontiguousarray(deleted, dtype=np.uint8)
+        dptr = deleted.ctypes.data_as(C.c_void_p)
+    n = int(lib().orc_similar_pairs(raw, raw.shape[0], raw.shape[1], dptr, threshold, oi, oj, osim, cap))
+    assert n <= cap
+    return oi[:n], oj[:n], osim[:n]
+
+
+def decay_sweep(importance, decayed_through_nanos, last_access_nanos, decay_rate, base_rate, now_nanos):
+    """One `apply_decay` sweep (src/store.rs:428-458); returns the new (importance, decayed_through_nanos)."""
+    imp = _f32(importance).copy()
+    dt = np.ascontiguousarray(decayed_through_nanos, np.uint64).copy()
+    lib().orc_decay_sweep(imp, dt, np.ascontiguousarray(last_access_nanos, np.uint64), _f32(decay_rate), imp.size,
+                          base_rate, now_nanos)
+    return imp, dt
 
 
 def sharded_merge(ids, dists, out_len):

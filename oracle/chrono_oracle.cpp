@@ -800,6 +800,47 @@ int orc_search_in_context(const float* raw, uint64_t n, uint64_t dim, const uint
   return 0;
 }
 
+// src/store.rs:516-568 — the pair test of ChronoMind::consolidate: for every pair i < j of live memories,
+// similarity = metric.similarity(a.data, b.data) (cosine on the raw rows, 0 when undefined); the pair qualifies
+// when `similarity > similarity_threshold` (:531-534). Only the test is restated: the greedy keeper/absorbed
+// bookkeeping that follows is write-path state. Returns the number of qualifying pairs; writes at most `cap`.
+uint64_t orc_similar_pairs(const float* raw, uint64_t n, uint64_t dim, const uint8_t* deleted, float threshold,
+                           uint32_t* out_i, uint32_t* out_j, float* out_sim, uint64_t cap) {
+  uint64_t found = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (deleted && deleted[i]) continue;
+    for (uint64_t j = i + 1; j < n; ++j) {
+      if (deleted && deleted[j]) continue;
+      float c;
+      float sim = cosine(raw + i * dim, dim, raw + j * dim, dim, true, &c) ? c : 0.0f;
+      if (sim <= threshold) continue;
+      if (found < cap) {
+        out_i[found] = (uint32_t)i;
+        out_j[found] = (uint32_t)j;
+        out_sim[found] = sim;
+      }
+      ++found;
+    }
+  }
+  return found;
+}
+
+// src/store.rs:428-458 — one apply_decay sweep over plain arrays (the per-memory CAS gate only matters for
+// concurrent sweeps): from = max(previous sweep, last access); skip when now <= from; claim; hours = (now - from)
+// as f32 / 1e9 / 3600; importance = clamp(importance * exp(-rate * hours), 0, 1) (:114-128).
+void orc_decay_sweep(float* importance, uint64_t* decayed_through, const uint64_t* last_access, const float* decay_rate,
+                     uint64_t n, float base_rate, uint64_t now_nanos) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t from = std::max(decayed_through[i], last_access[i]);
+    if (now_nanos <= from) continue;
+    decayed_through[i] = now_nanos;
+    float hours = (float)(now_nanos - from) / 1e9f / 3600.0f;
+    float rate = decay_rate[i] > 0.0f ? decay_rate[i] : base_rate;
+    float v = importance[i] * std::exp(-rate * hours);
+    importance[i] = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  }
+}
+
 // src/index/sharded_rwlock.rs:81-94 — merge per-shard lists: concat, sort by
 // (dist, global id), truncate. lists: [n_shards][nq][len] local ids/dists
 // (UINT32_MAX = padding); global id = local * n_shards + shard (the

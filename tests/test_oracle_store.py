@@ -148,3 +148,25 @@ def test_loaded_store_is_searchable():                     # :48-56
     s = _store([m.data for m in mems2], 4)
     rc, ids, _, _ = s([0.0, 1.0, 2.0, 3.0], 1)
     assert mems2[ids[0]].id == "m0"
+
+
+def test_decay_sweep_matches_the_documented_curve():       # tests/store_test.rs:241-273 (exp(-2.4) within 0.01)
+    h = 3600 * 10**9
+    imp, dt = oracle.decay_sweep([1.0, 1.0, 0.5], [0, 0, 0], [0, 0, 30 * h], [0.0, 0.2, 0.1], 0.1, 24 * h)
+    assert abs(imp[0] - np.exp(-2.4)) < 0.01 and abs(imp[1] - np.exp(-4.8)) < 0.01
+    assert imp[2] == 0.5 and dt[2] == 0 and dt[0] == 24 * h          # accessed after `now`: interval not claimed
+    imp2, dt2 = oracle.decay_sweep(imp, dt, [0, 0, 30 * h], [0.0, 0.2, 0.1], 0.1, 24 * h)
+    assert np.array_equal(imp2, imp)                                  # the same interval is never applied twice
+
+
+def test_similar_pairs_is_the_consolidate_pair_test():     # src/store.rs:531-534
+    rng = np.random.default_rng(4)
+    base = rng.normal(size=(40, 16)).astype(np.float32)
+    raw = np.vstack([base, base[:5] * 3.0 + 1e-3 * rng.normal(size=(5, 16)).astype(np.float32)])   # 5 near-duplicates
+    i, j, sim = oracle.similar_pairs(raw, 0.95)
+    assert list(zip(i.tolist(), j.tolist())) == [(a, 40 + a) for a in range(5)]
+    assert np.all(sim > 0.95) and all(abs(s - oracle.similarity(raw[a], raw[b])) == 0 for a, b, s in zip(i, j, sim))
+    dele = np.zeros(45, np.uint8)
+    dele[2] = 1
+    i, j, _ = oracle.similar_pairs(raw, 0.95, deleted=dele)
+    assert (2, 42) not in list(zip(i.tolist(), j.tolist())) and len(i) == 4
