@@ -25,7 +25,10 @@ __host__ __device__
 #endif
 inline uint32_t total_key(float f) {
 #ifdef __CUDA_ARCH__
-  uint32_t b = __float_as_uint(f);
+  // An opaque bit cast: with __float_as_uint nvcc 12.9 may keep the value in the float domain and set the sign
+  // bit with `FADD -|x|, -0`, which canonicalises a NaN (payload and sign lost => wrong key for NaN distances).
+  uint32_t b;
+  asm("mov.b32 %0, %1;" : "=r"(b) : "f"(f));
 #else
   uint32_t b;
   std::memcpy(&b, &f, 4);

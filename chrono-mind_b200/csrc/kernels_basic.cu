@@ -480,9 +480,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
     for (int c = 0; c < 4; ++c) {
       uint64_t i = base + c * SEL_THREADS + threadIdx.x;
       if (i < n) {
-        const float v = row[i];
-        unsigned long long key = pack_key(v, (uint32_t)i);
-        if (key < tau && !(deleted && deleted[i]) && !(skip_inf && __float_as_uint(v) == 0x7F800000u)) {
+        unsigned long long key = pack_key(row[i], (uint32_t)i);
+        if (key < tau && !(deleted && deleted[i]) && !(skip_inf && (uint32_t)(key >> 32) == 0xFF800000u)) {  // +inf
           uint32_t slot = atomicAdd(&st.cnt, 1u);
           keys[kp + slot] = key;
         }

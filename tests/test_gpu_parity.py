@@ -101,6 +101,25 @@ def test_exact_scan_edge_cases():
     assert ids.shape == (0, 3)
 
 
+def test_nan_query_orders_like_total_cmp_on_both_engines():
+    """Index-level search never fails on a degenerate query: a NaN component makes every distance NaN
+    (src/metric.rs:223 — clamp passes NaN through), and (TotalF32, handle) ordering then returns the lowest handles.
+    (Regression: a float-domain rewrite of total_key by the compiler once turned those NaN keys into -0.0.)"""
+    rng = np.random.default_rng(5)
+    data = datasets.unit_vectors(rng, 9000, 64)
+    q = datasets.unit_vectors(rng, 70, 64)
+    q[13, 5] = np.nan
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 10, mode="prepared")
+    assert np.isnan(wd[13]).all()
+    for engine in (1, 2):
+        st, _ = make_store(data, attrs=False)
+        ids, d = st.set_exact_engine(engine).search_exact(q, 10)
+        assert np.array_equal(ids, wi)
+        assert np.isnan(d[13]).all()
+        keep = np.arange(70) != 13
+        assert np.array_equal(bits(d[keep]), bits(wd[keep]))
+
+
 def test_empty_index():
     st = ChronoMindB200.from_matrix(np.zeros((0, 8), np.float32), default_config(dimensions=8))
     st.build_graph(1).upload(0)
