@@ -429,3 +429,34 @@ def test_gpu_assisted_build_is_sound_searchable_and_oracle_identical(tmp_path):
     c = last_counters()
     assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
     assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1])
+
+
+def test_concurrent_callers_share_one_index():
+    """`&self` + `Send + Sync` (src/index/mod.rs:59-81): every cm_search_* is re-entrant on a shared uploaded index —
+    each in-flight call leases its own workspace and stream. Eight host threads mix exact (both engines), HNSW and
+    temporal searches; every result must equal the single-threaded one."""
+    import threading
+    data, q = datasets.embedding_dataset(12000, 96, 0xC0C0)
+    ts_s, ts_n, dec = datasets.temporal_attrs(12000, 2, NOW[0])
+    cfg = default_config(dimensions=768, ef_construction=100)
+    st = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec).build_graph(7, 8).upload(0)
+    want = {"exact": st.search_exact(q, 10), "hnsw": st.search_index(q, 64, 10), "temporal": st.search(q, 5, now=NOW)}
+    errors = []
+
+    def worker(kind, reps):
+        try:
+            for _ in range(reps):
+                got = {"exact": lambda: st.search_exact(q, 10), "hnsw": lambda: st.search_index(q, 64, 10),
+                       "temporal": lambda: st.search(q, 5, now=NOW)}[kind]()
+                for a, b in zip(got, want[kind]):
+                    if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
+                        errors.append(kind)
+        except Exception as e:                           # noqa: BLE001
+            errors.append("%s: %r" % (kind, e))
+
+    threads = [threading.Thread(target=worker, args=(k, 6)) for k in ("exact", "hnsw", "temporal", "exact", "hnsw", "temporal", "exact", "hnsw")]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
