@@ -210,15 +210,17 @@ __device__ __forceinline__ float combined_score_dev(float distance, unsigned lon
 // accumulators — the reference's lane-j partial sum for each of the 16 queries — so every x value is reused
 // 16 times from a register.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int EX_QT = 16;
+constexpr int EX_QT = 16;   // queries per CTA; 8 or 4 for very long rows (the 16 x dim query tile must fit shared memory)
 constexpr int EX_ROWS = 256;
 
+template <int QT>
 __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
                                                     const float* __restrict__ x, uint64_t n, uint32_t dim,
                                                     uint32_t ldx, float* __restrict__ D, uint64_t ldD,
                                                     const uint32_t* __restrict__ active_count,
                                                     uint32_t active_base, ContextEpilogue ce) {
-  extern __shared__ __align__(16) float qs[];  // [body][16]
+  constexpr int EX_QT = QT;  // shadows the default inside the kernel
+  extern __shared__ __align__(16) float qs[];  // [body][QT]
   if (active_count) {
     uint32_t ac = *active_count;
     ac = ac > active_base ? ac - active_base : 0;
@@ -251,23 +253,14 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
     for (uint32_t e = j; e < body; e += 8) {
       float xv = __ldg(xr + e);
       const float4* qp = reinterpret_cast<const float4*>(qs + (size_t)e * EX_QT);
-      float4 a = qp[0], b = qp[1], c = qp[2], d = qp[3];
-      acc[0] = __fmaf_rn(xv, a.x, acc[0]);
-      acc[1] = __fmaf_rn(xv, a.y, acc[1]);
-      acc[2] = __fmaf_rn(xv, a.z, acc[2]);
-      acc[3] = __fmaf_rn(xv, a.w, acc[3]);
-      acc[4] = __fmaf_rn(xv, b.x, acc[4]);
-      acc[5] = __fmaf_rn(xv, b.y, acc[5]);
-      acc[6] = __fmaf_rn(xv, b.z, acc[6]);
-      acc[7] = __fmaf_rn(xv, b.w, acc[7]);
-      acc[8] = __fmaf_rn(xv, c.x, acc[8]);
-      acc[9] = __fmaf_rn(xv, c.y, acc[9]);
-      acc[10] = __fmaf_rn(xv, c.z, acc[10]);
-      acc[11] = __fmaf_rn(xv, c.w, acc[11]);
-      acc[12] = __fmaf_rn(xv, d.x, acc[12]);
-      acc[13] = __fmaf_rn(xv, d.y, acc[13]);
-      acc[14] = __fmaf_rn(xv, d.z, acc[14]);
-      acc[15] = __fmaf_rn(xv, d.w, acc[15]);
+#pragma unroll
+      for (int g = 0; g < EX_QT / 4; ++g) {
+        const float4 a = qp[g];
+        acc[4 * g + 0] = __fmaf_rn(xv, a.x, acc[4 * g + 0]);
+        acc[4 * g + 1] = __fmaf_rn(xv, a.y, acc[4 * g + 1]);
+        acc[4 * g + 2] = __fmaf_rn(xv, a.z, acc[4 * g + 2]);
+        acc[4 * g + 3] = __fmaf_rn(xv, a.w, acc[4 * g + 3]);
+      }
     }
 #pragma unroll
     for (int qi = 0; qi < EX_QT; ++qi) {
@@ -308,20 +301,25 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
                               uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
                               cudaStream_t s, const ContextEpilogue* ce) {
   if (nq == 0 || n == 0) return cudaSuccess;
-  size_t smem = (size_t)(dim & ~7u) * EX_QT * sizeof(float);
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  {  // per device, so set on every launch (microseconds)
-    cudaError_t e = cudaFuncSetAttribute(k_exact_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-  }
+  const int qt = (size_t)(dim & ~7u) * 16 * 4 <= 200 * 1024 ? 16 : ((size_t)(dim & ~7u) * 8 * 4 <= 200 * 1024 ? 8 : 4);
+  size_t smem = (size_t)(dim & ~7u) * qt * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;  // dim > 12,800
   // D rows are indexed by the query's position inside this launch.
   // The in-stream fallback of the tensor-core scan (active_count != nullptr) is almost always empty: keep its
   // grid small (row blocks are walked with a grid stride) so that an empty launch costs microseconds.
   uint64_t row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
   if (active_count) row_blocks = std::min<uint64_t>(row_blocks, 296);
-  dim3 grid((unsigned)row_blocks, (nq + EX_QT - 1) / EX_QT);
+  dim3 grid((unsigned)row_blocks, (nq + qt - 1) / qt);
   ContextEpilogue none{};
-  k_exact_dist<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base, ce ? *ce : none);
+  auto launch = [&](auto kernel) -> cudaError_t {
+    // per device, so set on every launch (microseconds)
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 256, smem, s>>>(q, nq, ldq, x, n, dim, ldx, D, ldD, active_count, active_base, ce ? *ce : none);
+    return cudaSuccess;
+  };
+  cudaError_t e = qt == 16 ? launch(k_exact_dist<16>) : (qt == 8 ? launch(k_exact_dist<8>) : launch(k_exact_dist<4>));
+  if (e != cudaSuccess) return e;
   count_launch();
   return cudaGetLastError();
 }

@@ -507,7 +507,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 //      sort by (distance, handle).
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t RS_THREADS = 64;
-constexpr uint32_t RS_ROWS = 16;     // rows gathered per copy round (RS_THREADS / 4)
+constexpr uint32_t RS_ROWS = 16;     // most rows gathered per copy round (RS_THREADS / 4); fewer when rows are long
 constexpr uint32_t RS2_MAX = 512;    // candidates re-scored per query
 
 struct RescoreArgs {
@@ -521,6 +521,7 @@ struct RescoreArgs {
   uint32_t cap;
   uint32_t rs_max;        // candidates above the final scan threshold handled per query (power of two)
   uint32_t approx;        // 1: emit the top-k by bf16 score (distance = 1 - score) without the exact rescore
+  uint32_t rows;          // rows gathered per copy round, <= RS_ROWS
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   extern __shared__ __align__(128) unsigned char rs_smem[];
   const uint32_t row_stride = a.ldx * 4 + RG_ROW_PAD;
   unsigned char* rowbuf = rs_smem;                                                       // [RS_ROWS][row_stride]
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rowbuf + (size_t)RS_ROWS * row_stride);  // [rs_max] ~(score key, row)
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rowbuf + (size_t)a.rows * row_stride);  // [rs_max] ~(score key, row)
   unsigned long long* dkeys = keys + a.rs_max;                                           // [RS2_MAX] (distance, row)
   uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);                         // [RS2_MAX] rows to re-score
   float* qs = reinterpret_cast<float*>(rows + RS2_MAX);                                  // [ldq]
@@ -603,8 +604,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   // exact distances: rounds of RS_ROWS rows, bulk-copied into shared memory, one thread quad per row
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
   uint32_t phase = 0;
-  for (uint32_t r0 = 0; r0 < keep; r0 += RS_ROWS) {
-    const uint32_t cntr = min(RS_ROWS, keep - r0);
+  for (uint32_t r0 = 0; r0 < keep; r0 += a.rows) {
+    const uint32_t cntr = min(a.rows, keep - r0);
     rg_stage_rows(a.x, a.ldx, &mbar, rowbuf, row_stride, rows + r0, cntr, phase);
     const bool active = r_slot < cntr;
     const float d = rg_quad_distance(qs, rowbuf + (size_t)r_slot * row_stride, a.dim, c4, active);
@@ -739,8 +740,11 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.rescored_total = l.rescored_total;
   a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
   a.approx = l.approx ? 1u : 0u;
-  const size_t smem = (size_t)RS_ROWS * ((size_t)ix.dim_pad * 4 + RG_ROW_PAD) + (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 +
-                      (size_t)ix.dim_pad * 4;
+  const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
+  const size_t other = (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
+  a.rows = RS_ROWS;
+  while (a.rows > 1 && a.rows * row_stride + other > 200 * 1024) --a.rows;   // very long rows: fewer per round
+  const size_t smem = a.rows * row_stride + other;
   {  // per device, so set on every launch (microseconds)
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;

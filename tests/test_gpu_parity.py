@@ -142,7 +142,8 @@ def _oracle_for(data, M, efc, seed, deleted=None):
 @pytest.mark.parametrize("n,nq,dim,ef,kind,seed", [(2000, 20, 768, 50, "emb", 0xBEEF), (2000, 20, 32, 50, "uni", 0xC0FFEE),
                                                    (2000, 20, 768, 200, "uni", 0xBEEF), (10000, 200, 768, 64, "emb", 5),
                                                    (10000, 100, 768, 128, "emb", 5), (3000, 50, 100, 200, "uni", 9),
-                                                   (500, 10, 13, 10, "uni", 2)])
+                                                   (500, 10, 13, 10, "uni", 2), (1500, 12, 4096, 40, "uni", 3),
+                                                   (1200, 8, 300, 1000, "uni", 4)])
 def test_hnsw_search_identical_to_oracle_on_same_graph(n, nq, dim, ef, kind, seed):
     """Same graph (single-threaded build == the oracle's), equal ef: ids identical, distances bit-identical,
     and the work counters (dist evals, expansions) equal the CPU's — the traversal is the same traversal."""
