@@ -181,11 +181,11 @@ static bool row_is_finite(const float* v, uint32_t dim) {
   return acc == 0.0f;
 }
 
-static uint32_t hash_bits_for(uint32_t ef) {
-  uint32_t want = std::max(2048u, 32u * ef);
-  uint32_t bits = 11;
-  while ((1u << bits) < want) ++bits;
-  return std::min(bits, 15u);
+// Entries of the shared-memory visited table: a search visits ~17-19 nodes per unit of ef on the bench corpus
+// (dist_evals / ef), the table restarts on the global one past 3/4 full. Not rounded to a power of two: this table
+// is the largest shared-memory consumer at large ef and decides how many queries an SM holds.
+static uint32_t visited_entries_for(uint32_t ef) {
+  return std::min<uint32_t>(std::max<uint32_t>(2048u, 30u * ef), 32768u);
 }
 
 // ---- search plumbing (device pointers, async on `s`) --------------------------------------------------------
@@ -324,7 +324,7 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
     CM_CUDA(launch_fill(ws->pool_dist.as<float>(), (uint64_t)nq * ef, INFINITY, s));
     return CM_OK;
   }
-  uint32_t hb = hash_bits_for(ef);
+  uint32_t hb = visited_entries_for(ef);
   unsigned grid = 0;
   uint32_t rows = 0;
   cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid, &rows);
@@ -342,7 +342,7 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   l.pool_dist = ws->pool_dist.as<float>();
   l.counters = ws->small.as<unsigned long long>();          // 8 x u64 at offset 0
   l.work_counter = ws->small.as<uint32_t>() + 32;           // offset 128
-  l.hash_bits = hb;
+  l.table_entries = hb;
   l.gtable = ws->gtable.as<uint32_t>();
   l.ghash_bits = kGHashBits;
   l.grid = grid;

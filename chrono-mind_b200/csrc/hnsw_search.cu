@@ -57,7 +57,7 @@ struct HnswKernelArgs {
   float* pool_dist;
   unsigned long long* counters;  // [0] dist_evals [1] expansions [2] list_entries [3] global-table restarts [4] failures
   uint32_t* work_counter;
-  uint32_t hash_bits;      // shared-memory table
+  uint32_t table_entries;  // shared-memory visited table (any size >= 64)
   uint32_t* gtable;        // [gridDim.x] slabs of 1 << ghash_bits entries
   uint32_t ghash_bits;
   uint32_t rows;           // rows staged per round, <= HN_ROWS
@@ -81,7 +81,7 @@ struct HnShared {
 
 struct VisitedTable {
   uint32_t* slots;
-  uint32_t bits;
+  uint32_t size;  // entries (not necessarily a power of two: shared memory is what limits the CTAs per SM)
 };
 
 __device__ __forceinline__ uint32_t key_handle(unsigned long long key) { return ((uint32_t)key) >> 1; }
@@ -92,9 +92,8 @@ __device__ __forceinline__ unsigned long long make_key(float d, uint32_t id) {
 // HashSet::insert — true when `id` was not present. Called by the lanes of warp 0 concurrently. The caller
 // keeps the load below 3/4, so the probe always ends.
 __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t tag, uint32_t id) {
-  const uint32_t mask = (1u << t.bits) - 1;
   uint32_t want = tag | id;
-  uint32_t h = (id * 2654435761u) >> (32 - t.bits);
+  uint32_t h = __umulhi(id * 2654435761u, t.size);  // multiply-shift range reduction: [0, size)
   for (;;) {
     uint32_t old = t.slots[h];
     if (old == want) return false;
@@ -104,7 +103,7 @@ __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t t
       if (prev == want) return false;
       continue;  // another lane took the slot for a different id of this epoch: look at it again
     }
-    h = (h + 1) & mask;
+    h = h + 1 == t.size ? 0 : h + 1;
   }
 }
 
@@ -118,7 +117,7 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
   const uint32_t cap = layer == 0 ? a.cap0 : a.capU;
-  const uint32_t table_size = 1u << vt.bits;
+  const uint32_t table_size = vt.size;
   const uint32_t limit = (table_size >> 1) + (table_size >> 2);
   int buf = 0;
 
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   unsigned long long* lists = reinterpret_cast<unsigned long long*>(smem_raw + off);
   off += (size_t)2 * ef_cap * 8;
   uint32_t* stable = reinterpret_cast<uint32_t*>(smem_raw + off);
-  off += (size_t)4 << a.hash_bits;
+  off += (size_t)4 * a.table_entries;
   off = (off + 15) & ~(size_t)15;
   HnShared* sh = reinterpret_cast<HnShared*>(smem_raw + off);
   off = (off + sizeof(HnShared) + 127) & ~(size_t)127;
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   const uint32_t row_stride = a.ldx * 4 + HN_ROW_PAD;
 
   const uint32_t tid = threadIdx.x;
-  for (uint32_t i = tid; i < (1u << a.hash_bits); i += HN_THREADS) stable[i] = 0;
+  for (uint32_t i = tid; i < a.table_entries; i += HN_THREADS) stable[i] = 0;
   if (tid == 0) {
     sh->epoch = 0;
     sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = 0;
@@ -319,11 +318,11 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
       VisitedTable vt;
       if (use_global) {
         vt.slots = a.gtable + ((size_t)blockIdx.x << a.ghash_bits);
-        vt.bits = a.ghash_bits;
-        for (uint32_t i = tid; i < (1u << vt.bits); i += HN_THREADS) vt.slots[i] = 0;
+        vt.size = 1u << a.ghash_bits;
+        for (uint32_t i = tid; i < vt.size; i += HN_THREADS) vt.slots[i] = 0;
       } else {
         vt.slots = stable;
-        vt.bits = a.hash_bits;
+        vt.size = a.table_entries;
       }
       if (tid == 0) sh->overflow = 0;
       __syncthreads();
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
       if (tid == 0) atomicAdd(&a.counters[3], 1ull);
     }
     if (use_global) {  // the shared table missed epochs while the global one was in use: start it over
-      for (uint32_t i = tid; i < (1u << a.hash_bits); i += HN_THREADS) stable[i] = 0;
+      for (uint32_t i = tid; i < a.table_entries; i += HN_THREADS) stable[i] = 0;
       if (tid == 0) sh->epoch = 0;
       __syncthreads();
     }
@@ -383,9 +382,9 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   }
 }
 
-static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits, uint32_t rows) {
+static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t table_entries, uint32_t rows) {
   const size_t dim_pad = (dim + 7) & ~7u;
-  return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + ((size_t)4 << hash_bits) + 16 + sizeof(HnShared) +
+  return (((size_t)dim * 4 + 15) & ~(size_t)15) + (size_t)2 * ef * 8 + (size_t)4 * table_entries + 16 + sizeof(HnShared) +
          128 + (size_t)rows * (dim_pad * 4 + HN_ROW_PAD);
 }
 
@@ -394,21 +393,30 @@ static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t hash_bits, uin
 // 1M x 768 (tools/diag_hnsw_rows.py, ms per 10k-query batch at rows = 16/14/12/10/8/6):
 //   ef=64: 11.3/9.4/9.9/9.1/8.5/8.9   ef=128: 21.2/22.1/23.2/19.0/20.2/19.5   ef=200: 46.6/48.0/50.1/37.3/40.6/45.7
 // => a ~32 KB row buffer (10 rows of 768 floats) is the sweet spot; small rows take the full 16.
-cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid, uint32_t* rows_out) {
+cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows_out) {
   cudaError_t e = cudaFuncSetAttribute(k_hnsw_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) return e;
   const uint32_t row_stride = ix.dim_pad * 4 + HN_ROW_PAD;
   uint32_t rows = std::min(HN_ROWS, std::max(4u, (32u * 1024u) / row_stride));
+  bool forced = false;
   if (const char* env = getenv("CM_HNSW_ROWS")) {  // experiments only
-    uint32_t forced = (uint32_t)atoi(env);
-    if (forced) rows = std::min(std::max(forced, 1u), HN_ROWS);
+    uint32_t f = (uint32_t)atoi(env);
+    if (f) rows = std::min(std::max(f, 1u), HN_ROWS), forced = true;
   }
-  while (rows > 1 && hnsw_smem_bytes(ix.dim, ef, hash_bits, rows) > 220 * 1024) --rows;
-  const size_t smem = hnsw_smem_bytes(ix.dim, ef, hash_bits, rows);
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  while (rows > 1 && hnsw_smem_bytes(ix.dim, ef, table_entries, rows) > 220 * 1024) --rows;
+  auto ctas = [&](uint32_t r, int* out) -> cudaError_t {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_hnsw_search, HN_THREADS, hnsw_smem_bytes(ix.dim, ef, table_entries, r));
+  };
+  if (hnsw_smem_bytes(ix.dim, ef, table_entries, rows) > 220 * 1024) return cudaErrorInvalidValue;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hnsw_search, HN_THREADS, smem);
+  e = ctas(rows, &per_sm);
   if (e != cudaSuccess) return e;
+  if (!forced && rows > 8) {  // large ef (big visited table): two rows fewer per round if that admits one more CTA per SM
+    int per_sm8 = 0;
+    e = ctas(rows - 2, &per_sm8);
+    if (e != cudaSuccess) return e;
+    if (per_sm8 > per_sm && per_sm < 4) rows -= 2, per_sm = per_sm8;
+  }
   if (per_sm < 1) return cudaErrorInvalidValue;
   *grid = (unsigned)ix.sm_count * per_sm;
   *rows_out = rows;
@@ -438,14 +446,14 @@ cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& l, cudaS
   a.pool_dist = l.pool_dist;
   a.counters = l.counters;
   a.work_counter = l.work_counter;
-  a.hash_bits = l.hash_bits;
+  a.table_entries = l.table_entries;
   a.gtable = l.gtable;
   a.ghash_bits = l.ghash_bits;
   a.rows = l.rows;
   cudaError_t e = cudaMemsetAsync(l.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned grid = l.grid < l.nq ? l.grid : l.nq;
-  k_hnsw_search<<<grid, HN_THREADS, hnsw_smem_bytes(ix.dim, l.ef, l.hash_bits, l.rows), s>>>(a);
+  k_hnsw_search<<<grid, HN_THREADS, hnsw_smem_bytes(ix.dim, l.ef, l.table_entries, l.rows), s>>>(a);
   count_launch();
   return cudaGetLastError();
 }

@@ -89,13 +89,13 @@ struct HnswLaunch {
   float* pool_dist;
   unsigned long long* counters;  // device, 8 x u64: dist_evals, expansions, list_entries, gtable restarts, failures
   uint32_t* work_counter;    // device u32, zeroed by the launcher
-  uint32_t hash_bits;        // shared-memory visited table = 1 << hash_bits entries
+  uint32_t table_entries;    // shared-memory visited table entries (u32 each)
   uint32_t* gtable;          // per-CTA overflow tables in global memory, grid << ghash_bits entries
   uint32_t ghash_bits;
   unsigned grid;             // from hnsw_grid_size()
   uint32_t rows;             // rows staged per copy round, from hnsw_grid_size()
 };
-cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t hash_bits, unsigned* grid, uint32_t* rows);
+cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows);
 cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& a, cudaStream_t s);
 
 // Fallback plumbing of the tensor-core scan: copy the flagged queries' prepared rows into a compact matrix.
