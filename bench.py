@@ -366,6 +366,7 @@ def run_hnsw(args, rank, world, local_rank):
 
 
 def main():
+    global DIM, K
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -382,10 +383,14 @@ def main():
     ap.add_argument("--efs", default="64,128,200", help="hnsw: every ef measured (reported under config.per_ef)")
     ap.add_argument("--efc", type=int, default=100, help="hnsw: ef_construction of the host-built graph")
     ap.add_argument("--data", default="emb", choices=["emb", "uniform"])
+    ap.add_argument("--dim", type=int, default=DIM, help="vector dimension (default 768; 32 with --k 100 is BASELINE configs[4])")
+    ap.add_argument("--k", type=int, default=K, help="neighbors per query (default 10)")
     ap.add_argument("--build", default="host", choices=["host", "gpu"],
                     help="hnsw: graph construction — host (LockFreeHnsw::insert restatement, all cores) or gpu-assisted "
                          "(all-pairs kNN candidates on the device, select/link on the host)")
     args = ap.parse_args()
+
+    DIM, K = args.dim, args.k            # the workload shape is module state for the helpers above
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -527,6 +532,7 @@ def main():
                     "traffic_unit": "DRAM bytes per launch (ncu); algorithmic minimum = one pass over the bf16 corpus + queries = %d" % (n_rows // world * DIM * 2 + nq * DIM * 2),
                     "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
                     "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
+                    "scores_per_s_per_gpu": (nq * (n_rows / world) / (kern_avg_ms * 1e-3)) if kern_avg_ms > 0 else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback of B200_PROFILING.md"}
         cpu = None
@@ -542,18 +548,22 @@ def main():
             gi, gd = dev_ids[:sample], dev_dist[:sample]
             parity = bool(np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)))
             recall = float(np.mean([len(set(a) & set(b)) / K for a, b in zip(gi.tolist(), wi.tolist())]))
+            if DIM != 768:
+                log("[bench] note: unit vectors, so the L2 ranking of BASELINE configs[4] is this cosine ranking "
+                    "(|a-b|^2 = 2(1 - a.b)); the reference has no L2 metric (SURVEY.md F3)")
             cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                    "sample": "%d of the %d queries against the full %dx%d corpus, one pass (%.1fs of scan time)"
                              % (sample, nq, n_rows, DIM, secs), "parity_on_sample": parity,
                    "recall_at_10_on_sample": recall}
             log("[bench] cpu baseline in %.1fs" % (time.time() - t0))
+        cfg_no = "1" if (n_rows <= 1_000_000 and DIM == 768) else ("3" if DIM == 768 else "4")
         line = {
             "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": nq * args.steps / (ms * 1e-3),
             "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if tc else "f32", "data": "synthetic",
             "config": {"workload": "exact brute-force kNN %dx%d cosine (%s data), %d-query batch, k=%d (BASELINE configs[%s])"
-                                   % (n_rows, DIM, args.data, nq, K, "1" if n_rows <= 1_000_000 else "3"),
+                                   % (n_rows, DIM, args.data, nq, K, cfg_no),
                        "recall_at_10": (cpu or {}).get("recall_at_10_on_sample", "exact by construction (unchecked: --no-cpu-baseline)"),
                        "unresolved_queries": unresolved, "fallback_queries_e2e": counters.get("fallback_queries"),
                        "engine": "tcgen05 bf16 scan + fp32 rescore" if tc else "fp32 CUDA-core scan",

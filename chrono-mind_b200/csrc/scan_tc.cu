@@ -373,6 +373,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       top.min_pos = 0;
       top.kth = -INFINITY;
       uint32_t slot_next = 0, slots_left = 0;
+      uint32_t npend = 0;
+      float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, pend3 = 0.0f;
       for (uint32_t t = t0; t < t1; ++t) {
         float tau = INFINITY;  // padding queries: nothing passes
         if (q_valid && a.join) {
@@ -443,9 +445,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                   my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)(row0 + c + i);
                 ++slot_next;
                 --slots_left;
-                if (!listed && top.insert(s)) {
-                  improved = true;
-                  tau = fmaxf(tau, top.kth - 2.0f * kEps);
+                // The running top-k is NOT updated per hit: an O(k) insert inside this divergent loop stalls the whole
+                // warp for one lane's hit (32x the cost at k = 100). Scores that would improve it are parked in
+                // registers and inserted after the tile by all lanes together; only a full park (threshold still
+                // converging: hits are frequent) is flushed in place, four inserts at a time.
+                if (!listed && (top.filled < top.k || s > top.kth)) {
+                  if (npend == 4) {
+                    improved |= top.insert(pend0);
+                    improved |= top.insert(pend1);
+                    improved |= top.insert(pend2);
+                    improved |= top.insert(pend3);
+                    npend = 0;
+                    if (top.filled == top.k) tau = fmaxf(tau, top.kth - 2.0f * kEps);
+                  }
+                  if (npend == 0) pend0 = s;
+                  else if (npend == 1) pend1 = s;
+                  else if (npend == 2) pend2 = s;
+                  else pend3 = s;
+                  ++npend;
                 }
               }
             }
@@ -475,8 +492,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           acc = 0;
           acc_phase ^= 1;
         }
+        // parked scores -> running top-k (all lanes insert together: the cost is the busiest lane's, not the sum)
+        if (npend > 0) improved |= top.insert(pend0);
+        if (npend > 1) improved |= top.insert(pend1);
+        if (npend > 2) improved |= top.insert(pend2);
+        if (npend > 3) improved |= top.insert(pend3);
+        npend = 0;
         // publish the lower bound s_(k) - 2 eps for the other clusters working on this query
-        if (improved && q_valid) atomicMax(&a.tau_key[q], total_key(top.kth - 2.0f * kEps));
+        if (improved && q_valid && top.filled == top.k) atomicMax(&a.tau_key[q], total_key(top.kth - 2.0f * kEps));
       }
       // reserved but unused candidate slots: mark empty
       while (slots_left) {
