@@ -535,6 +535,8 @@ def main():
                     "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
                     "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
                     "scores_per_s_per_gpu": (nq * (n_rows / world) / (kern_avg_ms * 1e-3)) if kern_avg_ms > 0 else None,
+                    "note": None if DIM >= 256 else "short rows: one or two UMMA k-steps per tile, the TMEM-epilogue select bounds "
+                                                    "this shape (SURVEY.md H6); read scores_per_s_per_gpu, not frac",
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback of B200_PROFILING.md"}
         cpu = None
