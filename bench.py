@@ -37,6 +37,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def quiet_nccl_stdout():
+    """stdout carries ONE JSON line: NCCL's log goes to stderr, and its bare version banner (printed to stdout at
+    NCCL_DEBUG=VERSION) is dropped; an explicit NCCL_DEBUG=INFO/TRACE from the caller is kept."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def measured_traffic(kernel, **match):
     """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this configuration."""
     try:
@@ -186,7 +194,7 @@ def run_hnsw(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
     n_rows, nq = args.rows, args.queries
     efs = sorted({int(e) for e in args.efs.split(",")} | {args.ef})
@@ -414,7 +422,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
+        quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
