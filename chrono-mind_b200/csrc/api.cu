@@ -19,6 +19,7 @@ namespace cm {
 static thread_local std::string tl_error;
 static thread_local cm_counters tl_counters;
 static thread_local bool tl_used_tc = false;  // the last exact search on this thread ran the tensor-core scan
+static thread_local uint32_t tl_scan_worst_chunk = 0;  // most queries one chunk of that search sent to the fallback
 static std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string& msg) { tl_error = msg; }
@@ -143,8 +144,10 @@ constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited tabl
 constexpr size_t kDistWorkspaceBytes = 1ull << 30;  // fp32 scan: distance block [QB][n] floats
 constexpr uint32_t kFlagCap = 512;             // queries per call the in-stream fp32 fallback can absorb
 constexpr uint32_t kFlagChunk = 64;            // ... in fp32 scans of this many queries (empty chunks exit at once)
-// ws->small layout (bytes): 0 HNSW counters (8 x u64) | 64 rescored_total u64 | 72 flag_count u32 |
-// 128 work_counter u32 | 192 bad_row u32 | 256 flag_list (kFlagCap x u32)
+// ws->small layout (bytes): 0 HNSW counters (8 x u64) | per query chunk: 64 rescored u64, 72 flag_count u32 |
+// per call: 80 rescored total u64, 88 flagged total u32, 92 most flagged in one chunk u32 |
+// 128 work_counter / pair_count u32 | 192 bad_row u32 | 256 flag_list (kFlagCap x u32)
+constexpr uint32_t kTcQueryChunk = 32768;      // queries per tensor-core scan (bounds the candidate buffer: 1 GB at k <= 16)
 constexpr size_t kSmallBytes = 256 + kFlagCap * 4;
 
 static void free_device(DeviceIndex& d) {
@@ -252,7 +255,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   uint32_t* cand_cnt = tau_key + nq_pad;
   uint8_t* small = ws->small.as<uint8_t>();
   CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
-  CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));
+  CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));  // this chunk's counters
   CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, nullptr, false, s));
   ScanTcLaunch sl;
   sl.q_bf16 = ws->qbf16.p;
@@ -285,8 +288,11 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   CM_CUDA(launch_rescore(d, rl, s));
   // Flagged queries (candidate overflow / too few survivors): exact fp32 scan, in stream, no host round trip.
   CM_CUDA(launch_gather_rows(pq.qn, pq.ld, rl.flag_list, rl.flag_count, kFlagCap, ws->qflag.as<float>(), s));
-  return exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
-                         rl.flag_count, s);
+  cm_status st = exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
+                                 rl.flag_count, s);
+  if (st != CM_OK) return st;
+  CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, s));  // chunk counters -> call totals
+  return CM_OK;
 }
 
 // Exact top-`k` by (distance, handle) into ids/dist [nq][k] (device).
@@ -307,7 +313,18 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
     return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;
-  if (use_tc) return exact_topk_tc(idx, ws, pq, nq, k, ids, dist, s, approx);
+  if (use_tc) {
+    CM_CUDA(ws->small.ensure(kSmallBytes));
+    CM_CUDA(cudaMemsetAsync(ws->small.as<uint8_t>() + 80, 0, 16, s));  // call totals
+    for (uint32_t q0 = 0; q0 < nq; q0 += kTcQueryChunk) {  // bounded candidate buffer for very large batches
+      const uint32_t nb = std::min(kTcQueryChunk, nq - q0);
+      PreparedQueries part = pq;
+      part.qn = pq.qn + (size_t)q0 * pq.ld;
+      cm_status st = exact_topk_tc(idx, ws, part, nb, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, s, approx);
+      if (st != CM_OK) return st;
+    }
+    return CM_OK;
+  }
   return exact_topk_fp32(idx, ws, pq.qn, pq.ld, pq.degenerate, nq, k, ids, dist, nullptr, nullptr, s);
 }
 
@@ -473,10 +490,13 @@ static void fetch_scan_counters(Workspace* ws) {
   if (!ws->small.p) return;
   unsigned long long r = 0;
   uint32_t f = 0;
-  if (cudaMemcpy(&r, ws->small.as<uint8_t>() + 64, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
-  if (cudaMemcpy(&f, ws->small.as<uint8_t>() + 72, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  uint32_t worst = 0;
+  if (cudaMemcpy(&r, ws->small.as<uint8_t>() + 80, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (cudaMemcpy(&f, ws->small.as<uint8_t>() + 88, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (cudaMemcpy(&worst, ws->small.as<uint8_t>() + 92, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return;
   tl_counters.rescored += r;
   tl_counters.fallback_queries += f;
+  tl_scan_worst_chunk = worst;
 }
 
 static void fetch_hnsw_counters(Workspace* ws) {
@@ -1064,7 +1084,7 @@ static cm_status search_exact_host(const cm_index* idx, const float* q, uint32_t
   CM_CUDA(cudaStreamSynchronize(hc.s));
   if (tl_used_tc) {
     fetch_scan_counters(lease.ws);
-    if (tl_counters.fallback_queries > kFlagCap) {
+    if (tl_scan_worst_chunk > kFlagCap) {
       // More queries needed the fp32 fallback than the in-stream path absorbs: redo the batch on the fp32 engine.
       PreparedQueries pq;
       pq.qn = lease.ws->qn.as<float>();

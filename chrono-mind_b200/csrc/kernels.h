@@ -51,6 +51,8 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
                               uint32_t ldx, float* D, uint64_t ldD, const uint32_t* active_count, uint32_t active_base,
                               cudaStream_t s, const ContextEpilogue* ce = nullptr);
 cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
+// tensor-core scan bookkeeping: fold one query chunk's {rescored, flagged} into the call totals
+cudaError_t launch_fold_scan_counters(const void* chunk, void* total, cudaStream_t s);
 
 // k smallest (distance, handle) per row of D, tombstones dropped.
 // qmap/active_count (optional, device): row b of D belongs to output row qmap[b]; rows with

@@ -339,6 +339,22 @@ cudaError_t launch_gather_rows(const float* src, uint32_t ld, const uint32_t* li
   return cudaGetLastError();
 }
 
+// Per-chunk counters of the tensor-core scan {rescored u64, flagged u32} folded into the call's totals
+// {rescored u64, flagged u32, most flagged in one chunk u32}.
+__global__ void k_fold_scan_counters(const unsigned char* chunk, unsigned char* total) {
+  const unsigned long long r = *reinterpret_cast<const unsigned long long*>(chunk);
+  const uint32_t f = *reinterpret_cast<const uint32_t*>(chunk + 8);
+  *reinterpret_cast<unsigned long long*>(total) += r;
+  *reinterpret_cast<uint32_t*>(total + 8) += f;
+  uint32_t* worst = reinterpret_cast<uint32_t*>(total + 12);
+  if (f > *worst) *worst = f;
+}
+cudaError_t launch_fold_scan_counters(const void* chunk, void* total, cudaStream_t s) {
+  k_fold_scan_counters<<<1, 1, 0, s>>>((const unsigned char*)chunk, (unsigned char*)total);
+  count_launch();
+  return cudaGetLastError();
+}
+
 __global__ void k_fill(float* p, uint64_t n, float v) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }

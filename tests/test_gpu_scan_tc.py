@@ -123,3 +123,15 @@ def test_tc_scan_more_flagged_queries_than_one_fallback_chunk():
     wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 10, mode="prepared")
     assert c["fallback_queries"] == 200
     assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+
+
+def test_tc_scan_batches_larger_than_one_query_chunk():
+    """70,000 queries (> the 32,768-query chunk that bounds the candidate buffer): chunks are scanned back to back in
+    one call; counters are the call's totals."""
+    data, q = datasets.uniform_dataset(20000, 70000, 32, 77)
+    st = store(data)
+    ids, d = st.search_exact(q, 5)
+    c = last_counters()
+    wi, wd = oracle.brute_force(oracle.preprocess_rows(data), q, 5, mode="prepared", threads=16)
+    assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+    assert c["fallback_queries"] == 0 and c["rescored"] >= 70000 * 5
