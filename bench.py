@@ -225,6 +225,10 @@ def run_hnsw(args, rank, world, local_rank):
     out_i = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     out_s = torch.empty((nq, K), dtype=torch.float32).pin_memory()
 
+    rows_per_rank = (nq + world - 1) // world
+    q_gather = torch.empty((world * rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
+    q_slice = torch.empty((rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
+
     def merged(ids, d, length):
         if world == 1:
             return ids, d
@@ -255,7 +259,12 @@ def run_hnsw(args, rank, world, local_rank):
         """ChronoMind::search through host buffers."""
         if world == 1:
             return st.search(q_host[i % 2].numpy(), K, now=now, ef_search=ef, temporal_weight=W, base_decay_rate=BASE)
-        qd = q_host[i % 2].to(dev, non_blocking=True)
+        qh = q_host[i % 2]                                               # 1/N of the batch per rank over PCIe,
+        lo = min(nq, rank * rows_per_rank)                               # the slices all-gathered over NVLink
+        hi = min(nq, lo + rows_per_rank)
+        q_slice[:hi - lo].copy_(qh[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(q_gather, q_slice)
+        qd = q_gather[:nq]
         pool = max(ef, 3 * K)                                            # OVERSAMPLE, src/store.rs:40,323
         pi, pd = st.search_index_cuda(qd, pool, pool)
         mi, md = merged(pi, pd, pool)                                    # global top-ef first (SURVEY.md §8e) ...

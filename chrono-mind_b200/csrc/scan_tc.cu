@@ -25,6 +25,12 @@
 // If a query's candidate buffer overflows, or fewer than min(k, live) candidates survive (NaN/Inf queries),
 // K2 flags the query and it is re-run through the fp32 scan — never silently degraded.
 //
+// The same kernel serves two more callers:
+//   * GPU-assisted graph construction (cm_index_build_graph_gpu): corpus against itself in query batches, K2 in
+//     `approx` mode (top-k by bf16 score, no exact rescore — the host re-measures every candidate);
+//   * consolidate's all-pairs similarity test (cm_similar_pairs): `join` mode — Q == X, one fixed threshold, only
+//     tiles on or above the diagonal, pairs (query < row) appended to one list.
+//
 // Kernel organisation (persistent, one CTA per SM, clusters of 2 = one CTA pair per TPC, 8 warps per CTA):
 //   warp 0  TMA producer (one lane, both CTAs) — ring of {Q tile 128x64, X tile 128x64} bf16, 32 KB per stage
 //           per CTA; the pair's loads all complete on the LEADER's full barrier
