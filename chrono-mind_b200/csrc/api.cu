@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <thread>
@@ -1115,8 +1116,16 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
   const uint32_t M = (uint32_t)idx->config.index.max_connections;
   uint32_t C = n_candidates ? n_candidates : (uint32_t)std::min<uint64_t>(idx->config.index.ef_construction, 64);
   C = std::min(std::max(C, M + 1), 127u);
+  const bool timing = getenv("CM_BUILD_TIMING") != nullptr;  // stage times on stderr (diagnostics)
+  auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_stage = now_s();
+  auto lap = [&](const char* what) {
+    if (timing) std::fprintf(stderr, "[build_graph_gpu] %-28s %.3f s\n", what, now_s() - t_stage);
+    t_stage = now_s();
+  };
   std::vector<std::vector<uint32_t>> members;
   layer_members(n, idx->config.index, layer_seed, &members);
+  lap("layer draw");
   std::vector<LayerCandidates> layers(members.size());
   for (size_t layer = 0; layer < members.size(); ++layer) {
     LayerCandidates& lc = layers[layer];
@@ -1136,12 +1145,14 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
         std::memcpy(&tmp->x[i * dim], &idx->x[(uint64_t)lc.members[i] * dim], (size_t)dim * 4);
     }
     cm_status st = cm_index_upload(tmp, device);
+    if (layer == 0) lap("layer 0 upload");
     const uint32_t batch = 16384;
     std::vector<float> dist_scratch((size_t)std::min<uint64_t>(batch, nm) * k);
     for (uint64_t q0 = 0; st == CM_OK && q0 < nm; q0 += batch) {
       const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nm - q0);
       st = search_exact_host(tmp, tmp->x.data() + q0 * dim, nb, dim, k, &lc.ids[q0 * k], dist_scratch.data(), /*approx=*/true);
     }
+    if (layer == 0) lap("layer 0 self-join");
     if (layer == 0) tmp->x.swap(idx->x);
     cm_index_free(tmp);
     if (st != CM_OK) return st;
@@ -1149,7 +1160,9 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
       for (uint32_t& v : lc.ids)
         if (v != CM_NO_ID) v = lc.members[v];
   }
+  lap("upper layers (all)");
   build_graph_from_candidates(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
+  lap("host select + link");
   return CM_OK;
 }
 

@@ -380,7 +380,7 @@ void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params
 // EVERY node of a layer come from one exact all-pairs kNN over the layer's members on the tensor cores (the K1 scan
 // with the corpus as its own query set, bf16-ranked — see cm_index_build_graph_gpu in api.cu). The host then does
 // what the reference does with candidates: exact distances, `select_diverse(cands, M)` (:205-240) for the node's
-// own list, and `add_backlink` with overflow re-selection (:246-280) for the reverse edges. Layers and the entry
+// own list, and `add_backlink`'s rule (:246-280) for the reverse edges, batched per target. Layers and the entry
 // point are the reference's (:126-132, :351-371). The graph is not the one sequential insertion would build (no
 // GPU/CPU build can be, the reference's own concurrent build is order dependent, :21-26) but satisfies
 // `check_invariants` and is searched by the CPU oracle and the device alike.
@@ -448,10 +448,46 @@ void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const
       std::memcpy(l, s.result.data(), s.result.size() * sizeof(uint32_t));
       *deg = (uint32_t)s.result.size();
     });
-    // phase B: reverse edges (per-node locks; overflowing lists are re-selected like the reference's)
+    // phase B: reverse edges, batched per target. `add_backlink` (:246-280) appends u to v's list and, when the
+    // list overflows, re-selects it from (list + u) sorted by distance to v; replaying that one edge at a time
+    // re-selects a popular node many times over. All edges into v are known here, so v's list is selected ONCE
+    // from own(v) + every u with v in own(u): same selection rule, same caps, no locks (each node writes only its
+    // own list), and a result that does not depend on thread interleaving.
+    std::vector<uint32_t> slot_of(n, CM_NO_ID);  // handle -> position in lc.members
+    for (uint64_t i = 0; i < nm; ++i) slot_of[lc.members[i]] = (uint32_t)i;
+    std::vector<uint32_t> in_start(nm + 1, 0);
+    for (uint64_t i = 0; i < nm; ++i)
+      for (uint32_t j = 0; j < own_deg[i]; ++j) ++in_start[slot_of[own[i * b.M + j]] + 1];
+    for (uint64_t i = 0; i < nm; ++i) in_start[i + 1] += in_start[i];
+    std::vector<uint32_t> incoming(in_start[nm]);
+    {
+      std::vector<uint32_t> fill(in_start.begin(), in_start.end() - 1);
+      for (uint64_t i = 0; i < nm; ++i)  // ascending source handle within each target
+        for (uint32_t j = 0; j < own_deg[i]; ++j) incoming[fill[slot_of[own[i * b.M + j]]]++] = lc.members[i];
+    }
+    const uint32_t cap = b.cap(layer);
     parallel_range(nm, threads, [&](uint64_t i, Scratch& s) {
-      const uint32_t u = lc.members[i];
-      for (uint32_t j = 0; j < own_deg[i]; ++j) b.add_backlink(own[i * b.M + j], u, layer, s);
+      const uint32_t v = lc.members[i];
+      uint32_t* deg;
+      uint32_t* l = b.list_ptr(v, layer, &deg);
+      // own list first, then the sources not already in it (what appending in handle order would leave)
+      s.nbuf.clear();
+      for (uint32_t j = 0; j < own_deg[i]; ++j) s.nbuf.push_back(own[i * b.M + j]);
+      for (uint32_t e = in_start[i]; e < in_start[i + 1]; ++e) {
+        const uint32_t u = incoming[e];
+        if (std::find(s.nbuf.begin(), s.nbuf.begin() + own_deg[i], u) == s.nbuf.begin() + own_deg[i]) s.nbuf.push_back(u);
+      }
+      if (s.nbuf.size() <= cap) {
+        std::memcpy(l, s.nbuf.data(), s.nbuf.size() * sizeof(uint32_t));
+        *deg = (uint32_t)s.nbuf.size();
+        return;
+      }
+      s.with_d.clear();
+      for (uint32_t u : s.nbuf) s.with_d.push_back(pack(dist_prepared(b.row(u), b.row(v), dim), u));
+      std::sort(s.with_d.begin(), s.with_d.end());
+      b.select_diverse(s.with_d.data(), s.with_d.size(), cap, s);
+      std::memcpy(l, s.result.data(), s.result.size() * sizeof(uint32_t));
+      *deg = (uint32_t)s.result.size();
     });
   }
   // raise_entry under in-order insertion (:351-371): the first handle that reaches the highest layer
