@@ -535,7 +535,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 //   3. evaluate distance_prepared exactly for that prefix (octet per candidate, reference lane order) and
 //      sort by (distance, handle).
 // ---------------------------------------------------------------------------------------------------------
-constexpr uint32_t RS_THREADS = 64;
+constexpr uint32_t RS_THREADS = 128;
 constexpr uint32_t RS_ROWS = 16;     // most rows gathered per copy round (RS_THREADS / 4); fewer when rows are long
 constexpr uint32_t RS2_MAX = 512;    // candidates re-scored per query
 
@@ -771,7 +771,9 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.approx = l.approx ? 1u : 0u;
   const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
   const size_t other = (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
-  a.rows = RS_ROWS;
+  // ~24 KB of row buffer (8 rows of 768 floats; a typical query re-scores ~15-30 rows = 2-4 rounds) keeps 4 CTAs per
+  // SM; the kernel is latency-bound per CTA, so queries in flight matter more than rounds.
+  a.rows = std::min<uint32_t>(RS_ROWS, std::max<uint32_t>(4u, (uint32_t)((24u * 1024u + row_stride - 1) / row_stride)));
   while (a.rows > 1 && a.rows * row_stride + other > 200 * 1024) --a.rows;   // very long rows: fewer per round
   const size_t smem = a.rows * row_stride + other;
   {  // per device, so set on every launch (microseconds)
