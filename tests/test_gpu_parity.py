@@ -249,6 +249,23 @@ def _correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, w, base):
     return out
 
 
+def test_temporal_search_with_tensor_core_pool():
+    """`cm_search_temporal(exact=1)` on a corpus large enough for the tensor-core engine: the exact pool of
+    ef = max(ef_search, 3k) = 64 candidates comes from K1/K2, then the fused rerank."""
+    data, q = datasets.embedding_dataset(20000, 130, 0xFEED)
+    cfg = default_config(dimensions=768, ef_search=64, temporal_weight=0.3)
+    ts_s, ts_n, dec = datasets.temporal_attrs(20000, 4, NOW[0])
+    st = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec).upload(0)
+    ids, score, dist = st.search(q, 10, now=NOW, exact=True, want_dist=True)
+    assert last_counters()["exact_engine"] == 2
+    pi, pd = oracle.brute_force(oracle.preprocess_rows(data, threads=8), q, 64, mode="prepared", threads=8)
+    wi, ws = oracle.rerank_pool(pi, pd, 10, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1])
+    same = ids == wi
+    assert same.mean() > 0.999
+    assert np.allclose(score[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert np.array_equal(bits(score), bits(_correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, 0.3, 0.1)))
+
+
 @pytest.mark.parametrize("exact", [False, True])
 def test_temporal_search_matches_oracle(exact):
     """ChronoMind::search (src/store.rs:321-346): pool = max(ef_search, 3k) candidates, combined_score, stable
