@@ -310,7 +310,9 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   // Rows with NaN/Inf components order by f32::total_cmp in the reference; the threshold select cannot
   // reproduce that, so such an index always takes the fp32 scan.
   bool tc_ok = !pq.degenerate && idx->all_finite && scan_tc_supported(d, k);
-  bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && nq >= 64 && d.n >= 8192);
+  // auto: the tensor-core scan wins from one query up once the corpus is a few thousand rows (1M rows, 1 query:
+  // ~0.7 ms against ~3 ms for the fp32 scan + select); tiny corpora stay on the fp32 engine.
+  bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && d.n >= 8192);
   if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
     return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;

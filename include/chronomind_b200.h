@@ -253,7 +253,7 @@ cm_status cm_metric_distance_prepared_dev(const void* a, const void* b, uint64_t
 const char* cm_metric_name(void);
 
 /* ---- tuning / diagnostics ------------------------------------------------------------------------------ */
-/* Exact-scan engine: 0 = auto (tensor-core scan when the problem is large enough), 1 = force the fp32
+/* Exact-scan engine: 0 = auto (tensor-core scan for corpora of 8192 rows or more), 1 = force the fp32
  * CUDA-core scan, 2 = force the tcgen05 scan + fp32 rescore. */
 cm_status cm_set_exact_engine(cm_index* idx, int engine);
 cm_status cm_last_counters(cm_counters* out); /* thread-local */
