@@ -1,10 +1,11 @@
 """`query` front-end of the reference CLI (`chronomind query`, src/main.rs:47-69,195-230) on the GPU engine.
 
     python -m chronomind_b200 query --file store.chrono --vector "[0.1, 0.2, 0.3, 0.4]" [--limit 10]
-                                    [--context LABEL] [--normalize] [--device 0] [--seed S] [--threads T]
+                                    [--context LABEL] [--normalize] [--device 0] [--seed S] [--threads T] [--build gpu|host]
 
-Loads the snapshot (`load_snapshot`, src/persistence.rs:73-123), rebuilds the HNSW graph on the host exactly as the
-reference's load does (or reads the `<file>.graph` sidecar when present), uploads to the GPU and prints the reference
+Loads the snapshot (`load_snapshot`, src/persistence.rs:73-123), rebuilds the HNSW graph — GPU-assisted by default,
+`--build host` replays the reference's one-by-one insertion — or reads the `<file>.graph` sidecar when present,
+uploads to the GPU and prints the reference
 CLI's lines. There is no CPU search path: without a CUDA device the command fails.
 """
 from __future__ import annotations
@@ -42,7 +43,10 @@ def query_command(args) -> int:
         if os.path.exists(sidecar):
             st.load_graph(sidecar)
         elif not args.context:                       # search_in_context never touches the index
-            st.build_graph(args.seed, args.threads)
+            if args.build == "gpu":                   # candidates from the device's all-pairs kNN, linking on the host
+                st.build_graph_gpu(args.seed, args.device, args.threads)
+            else:                                     # the reference's load path: LockFreeHnsw::insert, one by one
+                st.build_graph(args.seed, max(1, args.threads))
         st.upload(args.device)
         q = parse_vector(args.vector)
         if args.normalize:
@@ -76,7 +80,8 @@ def main(argv=None) -> int:
     q.add_argument("-n", "--normalize", action="store_true")
     q.add_argument("--device", type=int, default=0)
     q.add_argument("--seed", type=int, default=0x5EED, help="layer seed of the rebuilt graph (the reference draws a random one)")
-    q.add_argument("--threads", type=int, default=1)
+    q.add_argument("--threads", type=int, default=0, help="host threads for the graph build (0: all cores)")
+    q.add_argument("--build", default="gpu", choices=["gpu", "host"], help="graph construction when no <file>.graph sidecar exists")
     args = ap.parse_args(argv)
     return query_command(args)
 
