@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionstart(session):
+    """The product library is built in-tree by `__graft_entry__.build()` (git-ignored, so a fresh checkout has none).
+    Build it here when it is missing so the suite can run on its own; the engine itself never builds or falls back."""
+    lib = os.path.join(ROOT, "chrono-mind_b200", "libchronomind_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "chrono-mind_b200", "csrc"), "-j8", "-s"])
