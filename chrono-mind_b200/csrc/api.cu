@@ -1172,6 +1172,43 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
 // as a threshold self-join: the tensor-core scan with the corpus as its own query set emits the pairs whose bf16
 // score can exceed the threshold, the exact `metric.similarity` on the raw rows decides. Pairs (i < j, both live),
 // ascending (i, j). *count receives the number found; at most `cap` are written.
+// The host half of the GPU-assisted construction on caller-supplied candidates (any kNN source): layer `l` holds
+// `widths[l]` candidate handles for each member of that layer, members in ascending handle order (the layer draw of
+// (n, params, seed): cm_index_layer_members). Used by cm_index_build_graph_gpu's tests without a device.
+cm_status cm_index_build_graph_from_candidates(cm_index* idx, uint64_t layer_seed, int threads, uint32_t n_layers,
+                                               const uint32_t* const* cand_ids, const uint32_t* widths) {
+  if (!idx || (n_layers && (!cand_ids || !widths))) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::vector<uint32_t>> members;
+  layer_members(idx->n, idx->config.index, layer_seed, &members);
+  if (members.size() != n_layers) return fail(CM_ERR_INVALID_ARGUMENT, "layer count does not match the layer draw of this seed");
+  std::vector<LayerCandidates> layers(members.size());
+  for (size_t l = 0; l < members.size(); ++l) {
+    layers[l].members.swap(members[l]);
+    layers[l].width = widths[l];
+    const size_t cnt = layers[l].members.size() * (size_t)widths[l];
+    if (cnt && !cand_ids[l]) return fail(CM_ERR_INVALID_ARGUMENT, "null candidate array");
+    layers[l].ids.assign(cand_ids[l], cand_ids[l] + cnt);
+    for (uint32_t v : layers[l].ids)
+      if (v != CM_NO_ID && v >= idx->n) return fail(CM_ERR_INVALID_ARGUMENT, "candidate handle out of range");
+  }
+  build_graph_from_candidates(idx->x.data(), idx->n, idx->dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
+  return CM_OK;
+}
+
+// Members (ascending handles) of layer `layer` under the layer draw of (slots, params, seed); returns the count and
+// writes at most `cap` handles. *n_layers (optional) receives the number of layers.
+uint64_t cm_index_layer_members(const cm_index* idx, uint64_t layer_seed, uint32_t layer, uint32_t* out, uint64_t cap,
+                                uint32_t* n_layers) {
+  if (!idx) return 0;
+  std::vector<std::vector<uint32_t>> members;
+  layer_members(idx->n, idx->config.index, layer_seed, &members);
+  if (n_layers) *n_layers = (uint32_t)members.size();
+  if (layer >= members.size()) return 0;
+  for (uint64_t i = 0; i < members[layer].size() && i < cap; ++i) out[i] = members[layer][i];
+  return members[layer].size();
+}
+
 cm_status cm_similar_pairs(const cm_index* idx, float threshold, uint32_t* out_i, uint32_t* out_j, float* out_sim,
                            uint64_t cap, uint64_t* count) {
   if (!idx || !count) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");

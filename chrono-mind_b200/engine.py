@@ -65,6 +65,8 @@ ABI = {
     "cm_index_remove": (_i, [_vp, _u32, C.POINTER(_i)]),
     "cm_index_build_graph": (_i, [_vp, _u64, _i]),
     "cm_index_build_graph_gpu": (_i, [_vp, _u64, _i, _i, _u32]),
+    "cm_index_build_graph_from_candidates": (_i, [_vp, _u64, _i, _u32, _vp, _vp]),
+    "cm_index_layer_members": (_u64, [_vp, _u64, _u32, _vp, _u64, C.POINTER(_u32)]),
     "cm_index_set_shard": (_i, [_vp, _u32, _u32]),
     "cm_index_upload": (_i, [_vp, _i]),
     "cm_index_free": (None, [_vp]),
@@ -250,6 +252,28 @@ class ChronoMindB200:
     def build_graph_gpu(self, layer_seed: int = 0x5EED, device: int = 0, threads: int = 0, n_candidates: int = 0):
         """GPU-assisted construction: per-layer all-pairs kNN candidates on the device, select/link on the host."""
         _check(native().cm_index_build_graph_gpu(self._h, layer_seed & (2 ** 64 - 1), device, threads, n_candidates))
+        return self
+
+    def layer_members(self, layer_seed: int):
+        """Per layer, the handles that drew at least that layer (ascending) for `layer_seed`."""
+        nl = C.c_uint32(0)
+        native().cm_index_layer_members(self._h, layer_seed & (2 ** 64 - 1), 0, None, 0, C.byref(nl))
+        out = []
+        for layer in range(nl.value):
+            cnt = int(native().cm_index_layer_members(self._h, layer_seed & (2 ** 64 - 1), layer, None, 0, None))
+            buf = np.empty(cnt, dtype=np.uint32)
+            native().cm_index_layer_members(self._h, layer_seed & (2 ** 64 - 1), layer, _ptr(buf), cnt, None)
+            out.append(buf)
+        return out
+
+    def build_graph_from_candidates(self, layer_seed: int, candidates, threads: int = 0):
+        """Host half of the GPU-assisted construction: `candidates[l]` is a [members_l, width_l] uint32 array of
+        candidate handles for the members of layer l (order of `layer_members`)."""
+        cands = [np.ascontiguousarray(c, dtype=np.uint32) for c in candidates]
+        ptrs = (C.c_void_p * len(cands))(*[c.ctypes.data for c in cands])
+        widths = np.array([c.shape[1] if c.ndim == 2 else 0 for c in cands], dtype=np.uint32)
+        _check(native().cm_index_build_graph_from_candidates(self._h, layer_seed & (2 ** 64 - 1), threads, len(cands),
+                                                             C.cast(ptrs, C.c_void_p), _ptr(widths)))
         return self
 
     def save_graph(self, path):

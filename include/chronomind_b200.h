@@ -130,6 +130,16 @@ cm_status cm_index_build_graph(cm_index* idx, uint64_t layer_seed, int threads);
  * concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. */
 cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates);
 
+/* The host half of the GPU-assisted construction on caller-supplied candidates (any kNN source): `cand_ids[l]` holds
+ * `widths[l]` candidate handles (CM_NO_ID padded; the member itself is skipped) for each member of layer l, members in
+ * ascending handle order as cm_index_layer_members reports them for the same seed. */
+cm_status cm_index_build_graph_from_candidates(cm_index* idx, uint64_t layer_seed, int threads, uint32_t n_layers,
+                                               const uint32_t* const* cand_ids, const uint32_t* widths);
+/* Members of `layer` under the layer draw (`random_layer`, src/index/lockfree_hnsw.rs:126-132, ticket == handle) of
+ * this index for `layer_seed`: returns the count, writes at most `cap` handles; *n_layers (optional) = layers drawn. */
+uint64_t cm_index_layer_members(const cm_index* idx, uint64_t layer_seed, uint32_t layer, uint32_t* out, uint64_t cap,
+                                uint32_t* n_layers);
+
 /* Sharding by vector id (generalises `join_handle`/`split`, src/index/sharded_rwlock.rs:54-66):
  * this index holds the rows whose global handle = local * shard_count + shard_rank. Only affects the ids the
  * merge kernel emits. Default (0, 1). */

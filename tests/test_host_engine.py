@@ -204,3 +204,36 @@ def test_attr_validation():
         st.set_attrs(decay_rate=np.array([0.1, -1.0, 0.0], np.float32))    # src/types.rs:112-118
     st.set_attrs(deleted=np.array([0, 1, 0], np.uint8))
     assert len(st) == 2 and st.slots == 3
+
+
+def test_graph_from_knn_candidates_is_sound_and_searchable(tmp_path):
+    """The host half of the GPU-assisted construction (select_diverse + batched reverse edges over per-layer kNN
+    candidates), fed here with the oracle's exact kNN instead of the device's: same layer draw and entry as the
+    insertion builder, check_invariants clean, and the CPU oracle searching THAT graph reaches the recall gate."""
+    data, q = datasets.embedding_dataset(3000, 40, 0xCAFE, dim=64)
+    cfg = default_config(dimensions=64, ef_construction=100)
+    seed = 0xCAFE
+    ref = ChronoMindB200.from_matrix(data, cfg).build_graph(seed, 1)
+    st = ChronoMindB200.from_matrix(data, cfg)
+    prepared = oracle.preprocess_rows(data)
+    members = st.layer_members(seed)
+    assert len(members[0]) == 3000 and all(len(members[l]) >= len(members[l + 1]) for l in range(len(members) - 1))
+    cands = []
+    for m in members:
+        k = min(49, len(m))
+        ids, _ = oracle.brute_force(prepared[m], prepared[m], k, mode="prepared", threads=4)   # local ids within the layer
+        cands.append(np.where(ids == 0xFFFFFFFF, 0xFFFFFFFF, m[np.minimum(ids, len(m) - 1)]).astype(np.uint32))
+    st.build_graph_from_candidates(seed, cands, threads=4)
+    assert st.check_invariants() == 0
+    assert st.entry() == ref.entry()
+    assert [st.top_layer(i) for i in range(0, 3000, 37)] == [ref.top_layer(i) for i in range(0, 3000, 37)]
+    assert all(len(st.neighbors(i, 0)) <= 32 for i in range(0, 3000, 11))
+    p = str(tmp_path / "g.cmg")
+    st.save_graph(p)
+    orc = oracle.OracleHnsw(16, 100, 50, seed)
+    orc.import_graph(prepared, oracle.read_graph_sidecar(p))
+    assert orc.check_invariants() == 0
+    got, _, _, _ = orc.search_batch(q, 64, 10, threads=4)
+    want, _ = oracle.brute_force(prepared, q, 10, mode="prepared")
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(got.tolist(), want.tolist())])
+    assert recall >= 0.95, recall
