@@ -21,6 +21,7 @@ static thread_local std::string tl_error;
 static thread_local cm_counters tl_counters;
 static thread_local bool tl_used_tc = false;  // the last exact search on this thread ran the tensor-core scan
 static thread_local uint32_t tl_scan_worst_chunk = 0;  // most queries one chunk of that search sent to the fallback
+static thread_local bool tl_force_fp32 = false;        // redo of a call whose tensor-core pool could not be completed
 static std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string& msg) { tl_error = msg; }
@@ -92,18 +93,27 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// Scratch for one in-flight search call. Calls on different host threads take different workspaces.
+// Scratch for one search call. A workspace is leased for the duration of the HOST call; the kernels a `_dev`
+// variant enqueued may still be running when it returns, so the lease records a completion event on the stream it
+// used. The next user of the workspace either runs on that same stream (ordered behind the earlier work anyway) or
+// makes its stream wait on the event first — two calls never touch the same scratch concurrently on the device,
+// whatever mix of host threads and streams the caller uses.
 struct Workspace {
   DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable, qnorm, qctx;
   DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
   cudaStream_t stream = nullptr;  // host-buffer variants
+  cudaEvent_t done = nullptr;     // completion of the last call that used this workspace
+  cudaStream_t last_stream = nullptr;
+  bool pending = false;           // `done` was recorded and may not have completed yet
   unsigned hnsw_grid = 0;
   void release() {
     for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qnorm, &qctx, &qbf16,
                       &tc_state, &cand, &qflag})
       b->release();
     if (stream) cudaStreamDestroy(stream);
+    if (done) cudaEventDestroy(done);
     stream = nullptr;
+    done = nullptr;
   }
 };
 
@@ -111,9 +121,25 @@ struct WorkspacePool {
   std::mutex mu;
   std::vector<Workspace*> free_list;
   std::vector<Workspace*> all;
-  Workspace* acquire() {
+  // Prefer a workspace whose last call ran on `want` (or has nothing in flight): no cross-stream wait needed.
+  Workspace* acquire(cudaStream_t want, bool want_known) {
     std::lock_guard<std::mutex> g(mu);
-    if (!free_list.empty()) {
+    for (size_t i = free_list.size(); i-- > 0;) {
+      Workspace* w = free_list[i];
+      if (!w->pending || (want_known && w->last_stream == want)) {
+        free_list.erase(free_list.begin() + (long)i);
+        return w;
+      }
+    }
+    for (size_t i = free_list.size(); i-- > 0;) {  // its last call has finished by now
+      Workspace* w = free_list[i];
+      if (w->done && cudaEventQuery(w->done) == cudaSuccess) {
+        w->pending = false;
+        free_list.erase(free_list.begin() + (long)i);
+        return w;
+      }
+    }
+    if (!free_list.empty() && all.size() >= 4) {  // bounded pool: reuse a busy one, the lease makes the stream wait
       Workspace* w = free_list.back();
       free_list.pop_back();
       return w;
@@ -134,11 +160,40 @@ struct WorkspacePool {
   }
 };
 
+// Lease for a call that enqueues on the caller's `stream` (`_dev` variants) or on the workspace's own stream
+// (host-buffer variants: host = true; they synchronise before returning, so nothing stays pending).
 struct WorkspaceLease {
   WorkspacePool* pool;
   Workspace* ws;
-  explicit WorkspaceLease(const cm_index* idx) : pool((WorkspacePool*)idx->workspace_pool), ws(pool->acquire()) {}
-  ~WorkspaceLease() { pool->give_back(ws); }
+  cudaStream_t s = nullptr;
+  bool host;
+  cudaError_t err = cudaSuccess;
+  WorkspaceLease(const cm_index* idx, cudaStream_t stream, bool host_call)
+      : pool((WorkspacePool*)idx->workspace_pool), ws(pool->acquire(stream, !host_call)), host(host_call) {
+    if (host) {
+      if (!ws->stream) err = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+      s = ws->stream;
+    } else {
+      s = stream;
+    }
+    if (err == cudaSuccess && ws->pending && ws->last_stream != s) err = cudaStreamWaitEvent(s, ws->done, 0);
+  }
+  ~WorkspaceLease() {
+    if (host) {
+      ws->pending = false;  // the call synchronised its stream (or failed before enqueuing anything that matters)
+      if (err != cudaSuccess || cudaStreamQuery(s) != cudaSuccess) cudaStreamSynchronize(s);
+    } else {
+      if (!ws->done && cudaEventCreateWithFlags(&ws->done, cudaEventDisableTiming) != cudaSuccess) ws->done = nullptr;
+      if (ws->done && cudaEventRecord(ws->done, s) == cudaSuccess) {
+        ws->pending = true;
+        ws->last_stream = s;
+      } else {
+        cudaStreamSynchronize(s);  // no event: fall back to finishing the work before anyone reuses the scratch
+        ws->pending = false;
+      }
+    }
+    pool->give_back(ws);
+  }
 };
 
 constexpr uint32_t kGHashBits = 17;             // per-CTA overflow visited table: 128 Ki entries
@@ -156,7 +211,7 @@ static void free_device(DeviceIndex& d) {
   cudaSetDevice(d.device);
   for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.xraw, (void*)d.norm2_raw, (void*)d.ctx,
                   (void*)d.ts_secs, (void*)d.ts_nanos, (void*)d.decay,
-                  (void*)d.nbr0, (void*)d.deg0, (void*)d.upper_base, (void*)d.nbr_up, (void*)d.deg_up})
+                  (void*)d.nbr0, (void*)d.deg0, (void*)d.upper_base, (void*)d.nbr_up, (void*)d.deg_up, (void*)d.status})
     if (p) cudaFree(p);
   d = DeviceIndex();
 }
@@ -292,7 +347,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   cm_status st = exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
                                  rl.flag_count, s);
   if (st != CM_OK) return st;
-  CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, s));  // chunk counters -> call totals
+  CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, kFlagCap, d.status + 1, s));  // chunk counters -> call totals
   return CM_OK;
 }
 
@@ -313,7 +368,8 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   // auto: the tensor-core scan wins from one query up once the corpus is a few thousand rows (1M rows, 1 query:
   // ~0.7 ms against ~3 ms for the fp32 scan + select); tiny corpora stay on the fp32 engine.
   bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && d.n >= 8192);
-  if (idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
+  if (tl_force_fp32) use_tc = false;
+  if (!tl_force_fp32 && idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
     return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;
   if (use_tc) {
@@ -367,6 +423,7 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   l.ghash_bits = kGHashBits;
   l.grid = grid;
   l.rows = rows;
+  l.status = d.status;
   {
     ProfileScope prof(s);
     CM_CUDA(launch_hnsw_search(d, l, s));
@@ -510,6 +567,16 @@ static void fetch_hnsw_counters(Workspace* ws) {
   tl_counters.expansions += c[1];
   tl_counters.list_entries += c[2];
   tl_counters.fallback_queries += c[3];
+  tl_counters.tie_replays += c[5];
+  tl_counters.failures += c[4] + c[6];
+}
+
+// Host-buffer HNSW calls: a query the kernel could not answer like the reference is an error, never a quiet CM_OK.
+static cm_status hnsw_failures_to_status() {
+  if (tl_counters.failures == 0) return CM_OK;
+  return fail(CM_ERR_CAPACITY_EXCEEDED,
+              std::to_string(tl_counters.failures) + " quer(ies) exceeded the traversal's visited table or parked more than " +
+                  "a kernel's worth of tied candidates; results for them are not the reference's");
 }
 
 }  // namespace cm
@@ -778,6 +845,8 @@ cm_status cm_index_upload(cm_index* idx, int device) {
     CM_CUDA(cudaMemcpy2D(d.x32, (size_t)d.dim_pad * 4, idx->x.data(), (size_t)d.dim * 4, (size_t)d.dim * 4, n,
                          cudaMemcpyHostToDevice));
   }
+  CM_CUDA(cudaMalloc(&d.status, 8 * sizeof(uint32_t)));
+  CM_CUDA(cudaMemset(d.status, 0, 8 * sizeof(uint32_t)));
   CM_CUDA(cudaMalloc(&d.deleted, rows));
   CM_CUDA(cudaMalloc(&d.ts_secs, rows * 8));
   CM_CUDA(cudaMalloc(&d.ts_nanos, rows * 4));
@@ -948,7 +1017,8 @@ cm_status cm_search_exact_dev(const cm_index* idx, const void* q, uint32_t nq, u
   if (st != CM_OK) return st;
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, (cudaStream_t)stream, false);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   return search_exact_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, k, (uint32_t*)ids, (float*)dist,
                                (cudaStream_t)stream);
 }
@@ -960,7 +1030,8 @@ cm_status cm_search_hnsw_dev(const cm_index* idx, const void* q, uint32_t nq, ui
   if (ef > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "ef exceeds CM_MAX_K");
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, (cudaStream_t)stream, false);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   return search_hnsw_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, ef, k, (uint32_t*)ids, (float*)dist,
                               (cudaStream_t)stream);
 }
@@ -972,7 +1043,8 @@ cm_status cm_search_temporal_dev(const cm_index* idx, const void* q, uint32_t nq
   if (st != CM_OK) return st;
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, (cudaStream_t)stream, false);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   return search_temporal_dev_impl(idx, lease.ws, (const float*)q, nq, idx->dim, k, ef_search, w, base, now_secs,
                                   now_nanos, exact, nullptr, (uint32_t*)ids, (float*)score, (float*)dist,
                                   (cudaStream_t)stream);
@@ -986,7 +1058,8 @@ cm_status cm_search_in_context_dev(const cm_index* idx, const void* q, uint32_t 
   if (nq && !context_ids) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, (cudaStream_t)stream, false);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   return search_in_context_dev_impl(idx, lease.ws, (const float*)q, nq, (const uint32_t*)context_ids, k, w, base, now_secs,
                                     now_nanos, nullptr, (uint32_t*)ids, (float*)score, (cudaStream_t)stream);
 }
@@ -1031,6 +1104,19 @@ cm_status cm_metric_distance_prepared_dev(const void* a, const void* b, uint64_t
   return CM_OK;
 }
 
+cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset) {
+  if (!idx || !failures) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  *failures = 0;
+  if (!idx->uploaded) return fail(CM_ERR_CUDA, "index is not resident on a CUDA device (call cm_index_upload); there is no CPU path");
+  cm_status st = set_device(idx);
+  if (st != CM_OK) return st;
+  uint32_t w[8];
+  CM_CUDA(cudaMemcpy(w, idx->dev.status, sizeof w, cudaMemcpyDeviceToHost));  // waits for the work enqueued so far
+  *failures = (uint64_t)w[0] + w[1];
+  if (reset) CM_CUDA(cudaMemset(idx->dev.status, 0, sizeof w));
+  return CM_OK;
+}
+
 cm_status cm_set_exact_engine(cm_index* idx, int engine) {
   if (!idx || engine < 0 || engine > 2) return fail(CM_ERR_INVALID_ARGUMENT, "engine must be 0, 1 or 2");
   idx->exact_engine = engine;
@@ -1050,7 +1136,6 @@ struct HostCall {
 
 static cm_status host_begin(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
                             HostCall* hc) {
-  if (!ws->stream) CM_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
   hc->ws = ws;
   hc->s = ws->stream;
   size_t qbytes = (size_t)nq * qdim * sizeof(float);
@@ -1073,7 +1158,8 @@ static cm_status search_exact_host(const cm_index* idx, const float* q, uint32_t
   if (st != CM_OK) return st;
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
   tl_used_tc = false;
@@ -1221,10 +1307,10 @@ cm_status cm_similar_pairs(const cm_index* idx, float threshold, uint32_t* out_i
   cm_status st = set_device(idx);
   if (st != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   Workspace* ws = lease.ws;
-  if (!ws->stream) CM_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
-  cudaStream_t s = ws->stream;
+  cudaStream_t s = lease.s;
   CM_CUDA(ws->small.ensure(kSmallBytes));
   uint32_t* pair_count = ws->small.as<uint32_t>() + 32;  // offset 128
   uint64_t pcap = std::max<uint64_t>(1u << 20, 4 * cap);
@@ -1241,7 +1327,7 @@ cm_status cm_similar_pairs(const cm_index* idx, float threshold, uint32_t* out_i
     sl.cand = nullptr;
     sl.cap = 16;
     sl.join = true;
-    sl.join_tau = threshold - scan_tc_eps() - 1e-5f;   // bf16 score >= cos - eps; cos of the unit rows ~ similarity
+    sl.join_tau = threshold - scan_tc_eps(d.dim) - 1e-5f;   // bf16 score >= cos - eps; cos of the unit rows ~ similarity
     sl.pairs = ws->cand.as<unsigned long long>();
     sl.pair_count = pair_count;
     sl.pair_cap = (uint32_t)std::min<uint64_t>(pcap, 0xFFFFFFFFu);
@@ -1298,7 +1384,8 @@ cm_status cm_search_hnsw(const cm_index* idx, const float* q, uint32_t nq, uint3
   if (ef > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "ef exceeds CM_MAX_K");
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
   if (ef == 0) {  // search(.., 0) == [] (:470-472)
@@ -1317,7 +1404,7 @@ cm_status cm_search_hnsw(const cm_index* idx, const float* q, uint32_t nq, uint3
   }
   CM_CUDA(cudaStreamSynchronize(hc.s));
   fetch_hnsw_counters(lease.ws);
-  return CM_OK;
+  return hnsw_failures_to_status();
 }
 
 cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
@@ -1333,12 +1420,14 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
   }
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
   CM_CUDA(lease.ws->small.ensure(kSmallBytes));
   uint32_t* bad_row = lease.ws->small.as<uint32_t>() + 48;  // offset 192
   CM_CUDA(cudaMemsetAsync(bad_row, 0xFF, 4, hc.s));
+  tl_used_tc = false;
   st = search_temporal_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, ef_search, w, base, now_secs, now_nanos, exact,
                                 bad_row, hc.ids_dev, hc.a_dev, hc.b_dev, hc.s);
   if (st != CM_OK) return st;
@@ -1355,7 +1444,26 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
   if (bad != 0xFFFFFFFFu)
     return fail(CM_ERR_INVALID_VECTOR,
                 "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");
-  return CM_OK;
+  if (exact && tl_used_tc) {
+    fetch_scan_counters(lease.ws);
+    if (tl_scan_worst_chunk > kFlagCap) {
+      // More pool queries needed the fp32 fallback than the in-stream path absorbs: redo the call on the fp32 engine.
+      tl_counters = cm_counters();
+      tl_force_fp32 = true;
+      st = search_temporal_dev_impl(idx, lease.ws, hc.q_dev, nq, qdim, k, ef_search, w, base, now_secs, now_nanos, exact,
+                                    nullptr, hc.ids_dev, hc.a_dev, hc.b_dev, hc.s);
+      tl_force_fp32 = false;
+      if (st != CM_OK) return st;
+      if (ob) {
+        CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+        CM_CUDA(cudaMemcpyAsync(score, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+        if (dist) CM_CUDA(cudaMemcpyAsync(dist, hc.b_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+      }
+      CM_CUDA(cudaStreamSynchronize(hc.s));
+    }
+    return CM_OK;
+  }
+  return exact ? CM_OK : hnsw_failures_to_status();
 }
 
 cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq, uint32_t qdim,
@@ -1371,7 +1479,8 @@ cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq,
   }
   if ((st = set_device(idx)) != CM_OK) return st;
   tl_counters = cm_counters();
-  WorkspaceLease lease(idx);
+  WorkspaceLease lease(idx, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
   HostCall hc;
   if ((st = host_begin(idx, lease.ws, q, nq, qdim, k, &hc)) != CM_OK) return st;
   CM_CUDA(lease.ws->small.ensure(kSmallBytes));

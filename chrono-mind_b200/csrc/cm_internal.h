@@ -143,6 +143,10 @@ struct DeviceIndex {
   bool has_entry = false;
   uint64_t live = 0;
   int sm_count = 0;
+  // Device status words for the asynchronous (_dev) entry points, which cannot report through a return value:
+  // [0] HNSW queries that could not be answered like the reference (visited-table exhaustion, oversized tie group),
+  // [1] exact-scan queries left unresolved (more flagged queries than the in-stream fp32 fallback absorbs).
+  uint32_t* status = nullptr;
 };
 
 }  // namespace cm

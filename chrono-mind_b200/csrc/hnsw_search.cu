@@ -10,9 +10,14 @@
 //     popped is exactly an unexpanded entry of `best` (a node evicted from `best` is >= worst and would hit the
 //     `dist > worst` break), so "pop the frontier" == "first unexpanded list entry" and the loop ends when none
 //     is left. Per expansion the <=32 fresh neighbors are merged into the list by rank (each key computes its
-//     position in the union), which equals the reference's sequential admit/evict except when two different
-//     nodes have bit-identical distances at the admission boundary (the reference compares distance only,
-//     strictly; see DESIGN.md "Known deviations").
+//     position in the union). The rank merge equals the reference's sequential admit/evict whenever no group of
+//     bit-identical distances straddles the cut at ef (proof in DESIGN.md §4): the reference admits on distance
+//     only, strictly (`d < worst`, :182), and evicts by (distance, id), so only inside such a tie group does the
+//     ORDER of arrival decide who stays. When the union's keys at ranks ef-1 and ef carry the same distance bits
+//     the expansion is replayed sequentially in neighbor-list order by one thread (`tie replay`). An entry that
+//     was admitted, never expanded, and evicted while its distance still equals the worst distance stays in the
+//     reference's frontier and is expanded before the loop breaks (`dist > worst` is strict, :166-169): those
+//     entries wait in a small `limbo` array and are popped once the list has no unexpanded entry left.
 //   * `visited` (HashSet<u32>) is an open-addressing table in shared memory, tagged with an 8-bit epoch so it
 //     never has to be cleared between layers or queries. Membership is exact. When a query would crowd the
 //     table past 3/4 the CTA restarts that query on a larger per-CTA table in global memory.
@@ -40,6 +45,7 @@ namespace cm {
 constexpr int HN_THREADS = 256;      // most threads per CTA; the launcher uses 128 for small ef (see hnsw_threads_for)
 constexpr uint32_t HN_ROWS = 16;       // most rows staged per round (HN_THREADS / 4); the launcher may pick fewer
 constexpr uint32_t HN_ROW_PAD = RG_ROW_PAD;
+constexpr uint32_t HN_LIMBO = 48;      // evicted, unexpanded entries tied with the worst distance (see header)
 
 struct HnswKernelArgs {
   const float* x;
@@ -56,11 +62,13 @@ struct HnswKernelArgs {
   uint32_t* pool_ids;
   float* pool_dist;
   unsigned long long* counters;  // [0] dist_evals [1] expansions [2] list_entries [3] global-table restarts [4] failures
+                                 // [5] tie replays [6] CTAs that lost a tied evictee (limbo overflow)
   uint32_t* work_counter;
   uint32_t table_entries;  // shared-memory visited table (any size >= 64)
   uint32_t* gtable;        // [gridDim.x] slabs of 1 << ghash_bits entries
   uint32_t ghash_bits;
   uint32_t rows;           // rows staged per round, <= HN_ROWS
+  uint32_t* status;        // optional: bumped once per query that could not be answered like the reference
 };
 
 struct HnShared {
@@ -76,7 +84,12 @@ struct HnShared {
   uint32_t visited_count;
   uint32_t overflow;
   uint32_t epoch;
-  unsigned long long ctr_evals, ctr_exp, ctr_entries;
+  unsigned long long ctr_evals, ctr_exp, ctr_entries, ctr_replays;
+  // tie handling (see the header comment): the union's keys at ranks ef-1 / ef of the current merge, and the
+  // evicted-but-still-poppable entries (all carry the current worst distance)
+  unsigned long long bk0, bk1;
+  uint32_t limbo_count, limbo_lost;
+  unsigned long long limbo[HN_LIMBO];
 };
 
 struct VisitedTable {
@@ -125,6 +138,7 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
   if (tid == 0) {
     sh->epoch += 1;
     sh->visited_count = 0;
+    sh->limbo_count = 0;
   }
   __syncthreads();
   if (sh->epoch == 256) {
@@ -189,6 +203,16 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
           sh->cur_id = key_handle(L[pos]);
           L[pos] |= 1ull;
           sh->ctr_exp += 1;
+        } else if (sh->limbo_count) {
+          // The list has nothing left to expand, but the reference's frontier still holds evicted entries whose
+          // distance equals the worst one: `dist > worst` (:166-169) is strict, so the nearest of them is expanded.
+          uint32_t bi = 0;
+          for (uint32_t i = 1; i < sh->limbo_count; ++i)
+            if (sh->limbo[i] < sh->limbo[bi]) bi = i;
+          sh->cur_id = key_handle(sh->limbo[bi]);
+          sh->limbo[bi] = sh->limbo[--sh->limbo_count];
+          sh->cur_pos = 0;
+          sh->ctr_exp += 1;
         }
         if (nxt != kKeyMax) prefetch_l2(a.nbr0 + (uint64_t)key_handle(nxt) * a.cap0);
       }
@@ -214,6 +238,7 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
         if (lane == 0) {
           uint32_t m = __popc(nm);
           sh->fresh_count = m;
+          sh->bk0 = sh->bk1 = kKeyMax;
           sh->visited_count += m;
           sh->ctr_entries += __popc(pm);
           sh->ctr_evals += m;
@@ -268,9 +293,56 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
             pos += lo;
           }
           if (pos < ef) Ldst[pos] = key;
+          if (pos + 1 == ef) sh->bk0 = key;  // the union's keys on either side of the cut
+          if (pos == ef) sh->bk1 = key;
         }
         __syncthreads();
-        if (tid == 0) sh->list_count = min(ef, cnt + m);
+        // Equal distance bits on both sides of the cut: the reference's result depends on arrival order there
+        // (strict `d < worst` admission, :182; eviction by (distance, id), :186-188). Replay this expansion
+        // sequentially in neighbor-list order. Uniform branch (bk0 / bk1 were written before the barrier).
+        const bool tie = sh->bk1 != kKeyMax && (uint32_t)(sh->bk0 >> 32) == (uint32_t)(sh->bk1 >> 32);
+        if (tie) {
+          for (uint32_t i = tid; i < cnt; i += blockDim.x) Ldst[i] = Lsrc[i];
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t n = cnt;
+            for (uint32_t c = 0; c < m; ++c) {
+              const unsigned long long key = sh->cand[c];
+              uint32_t lim = n;  // list entries that stay
+              if (n >= ef) {
+                const unsigned long long worst = Ldst[n - 1];
+                if (!((uint32_t)(key >> 32) < (uint32_t)(worst >> 32))) continue;  // not admitted (:182)
+                if (!(worst & 1ull)) {  // evicted before it was expanded: still in the reference's frontier
+                  if (sh->limbo_count < HN_LIMBO)
+                    sh->limbo[sh->limbo_count++] = worst;
+                  else
+                    sh->limbo_lost = 1;
+                }
+                lim = n - 1;
+              }
+              uint32_t j = lim;
+              while (j > 0 && Ldst[j - 1] > key) {
+                Ldst[j] = Ldst[j - 1];
+                --j;
+              }
+              Ldst[j] = key;
+              n = lim + 1;
+            }
+            // evicted entries beyond the worst distance would hit the break: only the tied ones stay poppable
+            const uint32_t wd = (uint32_t)(Ldst[n - 1] >> 32);
+            uint32_t keep = 0;
+            for (uint32_t i = 0; i < sh->limbo_count; ++i)
+              if ((uint32_t)(sh->limbo[i] >> 32) == wd) sh->limbo[keep++] = sh->limbo[i];
+            sh->limbo_count = keep;
+            sh->list_count = n;
+            sh->ctr_replays += 1;
+          }
+        } else if (tid == 0) {
+          const uint32_t n = min(ef, cnt + m);
+          sh->list_count = n;
+          // the worst distance moved below the tied evictees: they can no longer be popped
+          if (sh->limbo_count && (uint32_t)(Ldst[n - 1] >> 32) != (uint32_t)(sh->limbo[0] >> 32)) sh->limbo_count = 0;
+        }
         buf ^= 1;
         __syncthreads();
       }
@@ -299,7 +371,8 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   for (uint32_t i = tid; i < a.table_entries; i += blockDim.x) stable[i] = 0;
   if (tid == 0) {
     sh->epoch = 0;
-    sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = 0;
+    sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = sh->ctr_replays = 0;
+    sh->limbo_count = sh->limbo_lost = 0;
     rg_mbar_init(&sh->mbar);
   }
   uint32_t phase = 0;  // parity of the copy barrier (every thread waits on every round, so all copies agree)
@@ -338,6 +411,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
       if (!sh->overflow) break;
       if (use_global) {  // cannot happen for sane ef; reported, never silent
         if (tid == 0) atomicAdd(&a.counters[4], 1ull);
+        if (tid == 0 && a.status) atomicAdd(a.status, 1u);
         if (tid == 0) sh->list_count = 0;
         __syncthreads();
         break;
@@ -379,6 +453,11 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
     atomicAdd(&a.counters[0], sh->ctr_evals);
     atomicAdd(&a.counters[1], sh->ctr_exp);
     atomicAdd(&a.counters[2], sh->ctr_entries);
+    if (sh->ctr_replays) atomicAdd(&a.counters[5], sh->ctr_replays);
+    if (sh->limbo_lost) {  // a tie group larger than HN_LIMBO was cut short somewhere in this CTA's queries: reported
+      atomicAdd(&a.counters[6], 1ull);
+      if (a.status) atomicAdd(a.status, 1u);
+    }
   }
 }
 
@@ -455,6 +534,7 @@ cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& l, cudaS
   a.gtable = l.gtable;
   a.ghash_bits = l.ghash_bits;
   a.rows = l.rows;
+  a.status = l.status;
   cudaError_t e = cudaMemsetAsync(l.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned grid = l.grid < l.nq ? l.grid : l.nq;

@@ -52,7 +52,8 @@ cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const f
                               cudaStream_t s, const ContextEpilogue* ce = nullptr);
 cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
 // tensor-core scan bookkeeping: fold one query chunk's {rescored, flagged} into the call totals
-cudaError_t launch_fold_scan_counters(const void* chunk, void* total, cudaStream_t s);
+// (`status`: optional device word that receives the queries beyond `flag_cap`, which stay unresolved)
+cudaError_t launch_fold_scan_counters(const void* chunk, void* total, uint32_t flag_cap, uint32_t* status, cudaStream_t s);
 
 // k smallest (distance, handle) per row of D, tombstones dropped.
 // qmap/active_count (optional, device): row b of D belongs to output row qmap[b]; rows with
@@ -96,6 +97,7 @@ struct HnswLaunch {
   uint32_t ghash_bits;
   unsigned grid;             // from hnsw_grid_size()
   uint32_t rows;             // rows staged per copy round, from hnsw_grid_size()
+  uint32_t* status = nullptr;  // optional device word bumped once per query that could not be answered exactly
 };
 cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows);
 cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& a, cudaStream_t s);

@@ -341,16 +341,17 @@ cudaError_t launch_gather_rows(const float* src, uint32_t ld, const uint32_t* li
 
 // Per-chunk counters of the tensor-core scan {rescored u64, flagged u32} folded into the call's totals
 // {rescored u64, flagged u32, most flagged in one chunk u32}.
-__global__ void k_fold_scan_counters(const unsigned char* chunk, unsigned char* total) {
+__global__ void k_fold_scan_counters(const unsigned char* chunk, unsigned char* total, uint32_t flag_cap, uint32_t* status) {
   const unsigned long long r = *reinterpret_cast<const unsigned long long*>(chunk);
   const uint32_t f = *reinterpret_cast<const uint32_t*>(chunk + 8);
   *reinterpret_cast<unsigned long long*>(total) += r;
   *reinterpret_cast<uint32_t*>(total + 8) += f;
   uint32_t* worst = reinterpret_cast<uint32_t*>(total + 12);
   if (f > *worst) *worst = f;
+  if (status && f > flag_cap) atomicAdd(status, f - flag_cap);
 }
-cudaError_t launch_fold_scan_counters(const void* chunk, void* total, cudaStream_t s) {
-  k_fold_scan_counters<<<1, 1, 0, s>>>((const unsigned char*)chunk, (unsigned char*)total);
+cudaError_t launch_fold_scan_counters(const void* chunk, void* total, uint32_t flag_cap, uint32_t* status, cudaStream_t s) {
+  k_fold_scan_counters<<<1, 1, 0, s>>>((const unsigned char*)chunk, (unsigned char*)total, flag_cap, status);
   count_launch();
   return cudaGetLastError();
 }

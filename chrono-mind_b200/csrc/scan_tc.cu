@@ -14,7 +14,8 @@
 //
 // Why the result is EXACT (not "bf16-approximate"): let e_r be the fp32 reference dot of row r and s_r the
 // tensor-core bf16 score, |s_r - e_r| <= eps for unit vectors (bf16 rounding of both operands: 2·2^-9 relative
-// per product, Cauchy-Schwarz => <= 2^-8 absolute; kEps adds slack for accumulation order). With s_(k) / e_(k)
+// per product, Cauchy-Schwarz => <= 2^-8 absolute; eps_for_dim() adds a dim-dependent allowance for the fp32
+// accumulation). With s_(k) / e_(k)
 // the k-th largest score over the live rows: the k rows of largest s have e >= s_(k) - eps, so
 // e_(k) >= s_(k) - eps, so every row of the exact top-k (e_r >= e_(k)) has s_r >= s_(k) - 2·eps.
 //   * K1's threshold tau_q is always a LOWER bound of s_(k) - 2·eps: it is the k-th best of k scores of distinct
@@ -69,7 +70,14 @@ constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kThreads = 256;
 constexpr uint32_t kSlotChunk = 8;  // candidate slots reserved per atomic
-constexpr float kEps = 0.0042f;     // >= 2^-8 + accumulation slack; margin is 2 * kEps
+// Bound on |tensor-core bf16 score - fp32 reference dot| for (at most) unit-length rows of `dim` elements:
+//   operand rounding   both operands to bf16 (unit roundoff 2^-9): |sum(a^b^) - sum(ab)| <= (2^-8 + 2^-18) sum|ab| <= 0.0039101
+//   accumulation       every UMMA K-step adds 16 exact products into an fp32 accumulator of magnitude <= 1; allowing a
+//                      truncation of 2^-23 per addend that is <= 1.07e-7 * dim, plus the reference's own chain
+//                      (dim/8 roundings of 2^-24); the 3.8e-7 * dim below is three times that.
+// 0.0042 is what every dim <= 768 has used since round 1 (kept, so those candidate sets are unchanged); beyond that
+// the allowance grows with dim instead of silently running out (dim 12,800: 0.0088). The margin is 2 * eps.
+static inline float eps_for_dim(uint32_t dim) { return std::max(0.0042f, 0.0039139f + 3.8e-7f * (float)dim); }
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -197,6 +205,7 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], uint32_t i) {
 
 struct ScanArgs {
   uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, stages;
+  float eps2;                    // 2 * eps_for_dim(dim): the candidate margin
   uint32_t* tau_key;             // [m_pairs*256] ordered-uint threshold per query (0 = none yet)
   uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
   unsigned long long* cand;      // [m_pairs*256][cap]  (ordered score key << 32 | row); 0 = unused slot
@@ -388,7 +397,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         } else if (q_valid) {
           const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
           const float g = tk ? key_to_float(tk) : -INFINITY;
-          tau = fmaxf(g, top.filled == top.k ? top.kth - 2.0f * kEps : -INFINITY);
+          tau = fmaxf(g, top.filled == top.k ? top.kth - a.eps2 : -INFINITY);
         }
         mbar_wait(smem_u32(&tail->tmem_full[acc]), acc_phase);
         tc_fence_after();
@@ -418,7 +427,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           if (cold) {
             listed = true;
             if (top.filled == top.k) {
-              tau = top.kth - 2.0f * kEps;
+              tau = top.kth - a.eps2;
               improved = true;
             }
           }
@@ -462,7 +471,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     improved |= top.insert(pend2);
                     improved |= top.insert(pend3);
                     npend = 0;
-                    if (top.filled == top.k) tau = fmaxf(tau, top.kth - 2.0f * kEps);
+                    if (top.filled == top.k) tau = fmaxf(tau, top.kth - a.eps2);
                   }
                   if (npend == 0) pend0 = s;
                   else if (npend == 1) pend1 = s;
@@ -505,7 +514,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (npend > 3) improved |= top.insert(pend3);
         npend = 0;
         // publish the lower bound s_(k) - 2 eps for the other clusters working on this query
-        if (improved && q_valid && top.filled == top.k) atomicMax(&a.tau_key[q], total_key(top.kth - 2.0f * kEps));
+        if (improved && q_valid && top.filled == top.k) atomicMax(&a.tau_key[q], total_key(top.kth - a.eps2));
       }
       // reserved but unused candidate slots: mark empty
       while (slots_left) {
@@ -551,6 +560,7 @@ struct RescoreArgs {
   uint32_t rs_max;        // candidates above the final scan threshold handled per query (power of two)
   uint32_t approx;        // 1: emit the top-k by bf16 score (distance = 1 - score) without the exact rescore
   uint32_t rows;          // rows gathered per copy round, <= RS_ROWS
+  float eps2;             // 2 * eps_for_dim(dim)
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -597,7 +607,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     block_bitonic_sort(keys, P);
     // s_(k): the k-th largest bf16 score (all of the bf16 top-k are in the list, see the header comment)
     uint32_t thr = 0;  // ns < k only when fewer than k rows are live: keep everything
-    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - 2.0f * kEps);
+    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - a.eps2);
     for (uint32_t i = tid; i < ns; i += RS_THREADS)
       if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);  // sorted: the kept set is a prefix
     __syncthreads();
@@ -687,7 +697,7 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 uint64_t scan_tc_pad_rows(uint64_t n) { return (n + BN - 1) / BN * BN; }
 uint32_t scan_tc_pad_queries(uint32_t nq) { return (nq + PAIR_M - 1) / PAIR_M * PAIR_M; }
 uint32_t scan_tc_pad_k(uint32_t dim) { return (dim + BK - 1) / BK * BK; }
-float scan_tc_eps() { return kEps; }
+float scan_tc_eps(uint32_t dim) { return eps_for_dim(dim); }
 uint32_t scan_tc_cand_cap(uint32_t k) { return k <= 16 ? 4096u : (k <= 64 ? 8192u : 16384u); }
 
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
@@ -723,6 +733,7 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.k_blocks = ix.k_pad / BK;
   a.k = l.k;
   a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters, l.k, l.cap);
+  a.eps2 = 2.0f * eps_for_dim(ix.dim);
   a.tau_key = l.tau_key;
   a.cand_cnt = l.cand_cnt;
   a.cand = l.cand;
@@ -769,6 +780,7 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.rescored_total = l.rescored_total;
   a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
   a.approx = l.approx ? 1u : 0u;
+  a.eps2 = 2.0f * eps_for_dim(ix.dim);
   const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
   const size_t other = (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
   // ~24 KB of row buffer (8 rows of 768 floats; a typical query re-scores ~15-30 rows = 2-4 rounds) keeps 4 CTAs per

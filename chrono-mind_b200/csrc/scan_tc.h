@@ -10,7 +10,7 @@ namespace cm {
 uint64_t scan_tc_pad_rows(uint64_t n);        // corpus rows padded to the X tile height (256)
 uint32_t scan_tc_pad_queries(uint32_t nq);    // queries padded to the Q tile-pair height (256)
 uint32_t scan_tc_cand_cap(uint32_t k);        // candidate slots per query
-float scan_tc_eps();                          // bound on |bf16 tensor-core score - fp32 dot| for unit vectors
+float scan_tc_eps(uint32_t dim);              // bound on |bf16 tensor-core score - fp32 dot| for unit vectors of `dim` elements
 uint32_t scan_tc_pad_k(uint32_t dim);         // columns padded to the K block (64)
 bool scan_tc_supported(const DeviceIndex& ix, uint32_t k);
 

@@ -48,7 +48,7 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("dist_evals", C.c_uint64), ("expansions", C.c_uint64), ("list_entries", C.c_uint64),
                 ("rescored", C.c_uint64), ("fallback_queries", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("exact_engine", C.c_uint64)]
+                ("exact_engine", C.c_uint64), ("tie_replays", C.c_uint64), ("failures", C.c_uint64)]
 
 
 _lib = None
@@ -92,6 +92,7 @@ ABI = {
     "cm_search_exact_dev": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_hnsw_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_temporal_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp, _vp]),
+    "cm_index_dev_status": (_i, [_vp, C.POINTER(_u64), _i]),
     "cm_similar_pairs": (_i, [_vp, _f, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "cm_decay_sweep_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _f, _u64, _i, _vp]),
     "cm_merge_topk_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _i, _vp]),
@@ -291,6 +292,13 @@ class ChronoMindB200:
         _check(native().cm_index_upload(self._h, device))
         self.device = device
         return self
+
+    def dev_status(self, reset: bool = True) -> int:
+        """Queries the asynchronous (`*_cuda`) searches enqueued so far could not answer like the reference (waits for
+        them). 0 in normal operation."""
+        f = C.c_uint64(0)
+        _check(native().cm_index_dev_status(self._h, C.byref(f), 1 if reset else 0))
+        return int(f.value)
 
     def set_exact_engine(self, engine: int):
         _check(native().cm_set_exact_engine(self._h, engine))

@@ -77,6 +77,12 @@ typedef struct {
                                 (host-buffer calls only: the _dev variants never synchronise to read it back) */
   uint64_t kernel_launches; /* kernels launched by this call */
   uint64_t exact_engine;    /* exact search: 1 = fp32 CUDA-core scan, 2 = tcgen05 scan + fp32 rescore; 0 otherwise */
+  uint64_t tie_replays;     /* HNSW: expansions replayed sequentially because bit-identical distances straddled the cut
+                               at ef (src/index/lockfree_hnsw.rs:165-189 admits on distance only, strictly) */
+  uint64_t failures;        /* queries the engine could NOT answer like the reference (visited-table exhaustion, a tie
+                               group larger than the kernel parks, unresolved exact rows). Host-buffer calls turn a
+                               non-zero count into CM_ERR_CAPACITY_EXCEEDED; the _dev variants add it to the index's
+                               device status word (cm_index_dev_status) */
 } cm_counters;
 
 #define CM_MAX_K 1024u  /* largest k / ef the select kernels accept */
@@ -223,6 +229,14 @@ cm_status cm_search_temporal_dev(const cm_index* idx, const void* q, uint32_t nq
 cm_status cm_search_in_context_dev(const cm_index* idx, const void* q, uint32_t nq, const void* context_ids, uint32_t k,
                                    float temporal_weight, float base_decay_rate, uint64_t now_secs, uint32_t now_nanos,
                                    void* ids, void* score, void* stream);
+
+/* The asynchronous variants cannot report a query they could not answer like the reference through their return
+ * value (HNSW: visited-table exhaustion or a tie group larger than the kernel parks; exact: more queries flagged for
+ * the fp32 fallback than the in-stream path absorbs — those rows are left CM_NO_ID / NaN, never a plausible wrong
+ * answer). They count such queries in a status word on the index's device instead. This call waits for the work
+ * enqueued so far on that device, returns the count in *failures and optionally clears it. The host-buffer variants
+ * need no such call: they redo the batch or return CM_ERR_CAPACITY_EXCEEDED. */
+cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset);
 
 /* Merge step of `ShardedRwLockHnsw::search` (src/index/sharded_rwlock.rs:81-94): concatenate per-shard lists,
  * sort by (distance, global handle), truncate. ids/dist: device [n_shards][nq][len] LOCAL handles as produced

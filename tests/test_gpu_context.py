@@ -13,6 +13,8 @@ from oracle import snapshot_codec as sc
 from chronomind_b200 import datasets
 from chronomind_b200.engine import NO_ID, ChronoMindB200, CmError, default_config
 
+from parity_helpers import assert_order_matches_up_to_ties
+
 pytestmark = pytest.mark.gpu
 NOW = (1_790_000_000, 250_000_000)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,9 +52,7 @@ def test_search_in_context_matches_oracle(n, nq, dim, k, w):
     if w == 0.0:      # score = distance / 2 exactly: the metric arithmetic is restated bit for bit
         assert np.array_equal(ids, wi) and np.array_equal(bits(score), bits(ws))
     else:             # expf may differ in the last ulp between libm and the device's correctly rounded exp
-        same = ids == wi
-        assert same.mean() > 0.999
-        assert np.allclose(score[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+        assert assert_order_matches_up_to_ties(ids, wi, score, ws) <= 0.001 * ids.size
     assert np.all(np.diff(score, axis=1)[live[:, 1:]] >= 0)
 
 

@@ -9,6 +9,7 @@ import oracle
 from oracle import snapshot_codec as sc
 from chronomind_b200 import datasets
 from chronomind_b200.engine import NO_ID, ChronoMindB200, CmError, Index, default_config, last_counters, native
+from parity_helpers import assert_order_matches_up_to_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -167,6 +168,59 @@ def test_hnsw_search_identical_to_oracle_on_same_graph(n, nq, dim, ef, kind, see
         assert rec >= 0.95
 
 
+def _with_duplicates(data, frac, seed):
+    """Overwrite `frac` of the rows with exact copies of earlier rows (ordinary in a memory store)."""
+    rng = np.random.default_rng(seed)
+    n = len(data)
+    dst = rng.choice(np.arange(n // 4, n), size=int(n * frac), replace=False)
+    data = data.copy()
+    data[dst] = data[rng.integers(0, n // 4, size=len(dst))]
+    return data
+
+
+@pytest.mark.parametrize("n,dim,M,frac,ef", [(3000, 8, 16, 0.2, 10), (3000, 8, 16, 0.2, 64), (4000, 16, 16, 0.05, 10),
+                                             (4000, 16, 16, 0.05, 64), (2500, 6, 4, 0.35, 24), (3000, 12, 32, 0.2, 64),
+                                             (6000, 768, 16, 0.2, 64)])
+def test_hnsw_exact_duplicates_at_the_admission_boundary(n, dim, M, frac, ef):
+    """`search_layer` admits on distance only, strictly (`d < worst`, src/index/lockfree_hnsw.rs:182), breaks on
+    `dist > worst` (:166-169) and evicts by (distance, id): with bit-identical distances on the cut at ef the order of
+    arrival decides. Corpora with 5-35 % exact duplicate rows, k = ef (the whole list is compared): ids, distance bits
+    and work counters must still be the oracle's, and the kernel must actually have taken its tie replay."""
+    rng = np.random.default_rng(n + ef)
+    base = rng.uniform(-1, 1, size=(n, dim)).astype(np.float32) if dim < 100 else datasets.embedding_dataset(n, 1, 17)[0]
+    data = _with_duplicates(base, frac, n)
+    q = np.vstack([rng.uniform(-1, 1, size=(120, dim)).astype(np.float32) if dim < 100 else datasets.embedding_dataset(n, 120, 17)[1],
+                   data[rng.integers(0, n, size=40)]])            # some queries ARE stored rows (distance-0 ties)
+    cfg = default_config(dimensions=dim, max_connections=M, ef_construction=60)
+    st, _ = make_store(data, cfg, attrs=False, graph_seed=11)
+    orc = _oracle_for(data, M, 60, 11)
+    ids, d = st.search_index(q, ef, ef)
+    c = last_counters()
+    wi, wd, _, octr = orc.search_batch(q, ef, ef)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(bits(d), bits(wd))
+    assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1]) and c["list_entries"] == int(octr[2])
+    assert c["failures"] == 0
+    if dim < 100:
+        assert c["tie_replays"] > 0, "no tie ever reached the cut: the workload does not test the replay"
+
+
+def test_hnsw_all_rows_identical():
+    """Degenerate extreme: every row is the same vector, so every distance ties. The reference fills `best` in arrival
+    order and then rejects everything (`d < worst` is never true)."""
+    data = np.tile(np.array([[0.3, -0.2, 0.9, 0.1]], np.float32), (400, 1))
+    cfg = default_config(dimensions=4, max_connections=8, ef_construction=40)
+    st, _ = make_store(data, cfg, attrs=False, graph_seed=5)
+    orc = _oracle_for(data, 8, 40, 5)
+    q = np.array([[0.3, -0.2, 0.9, 0.1], [1.0, 0.0, 0.0, 0.0]], np.float32)
+    for ef in (1, 10, 50):
+        ids, d = st.search_index(q, ef, ef)
+        c = last_counters()
+        wi, wd, _, octr = orc.search_batch(q, ef, ef)
+        assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+        assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1])
+
+
 def test_hnsw_tombstones_and_small_caps():
     """tests/recall_test.rs:166-214: delete id % 3 == 0; none leak; identical to the oracle. M=4 exercises
     list caps != 32."""
@@ -260,9 +314,7 @@ def test_temporal_search_with_tensor_core_pool():
     assert last_counters()["exact_engine"] == 2
     pi, pd = oracle.brute_force(oracle.preprocess_rows(data, threads=8), q, 64, mode="prepared", threads=8)
     wi, ws = oracle.rerank_pool(pi, pd, 10, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1])
-    same = ids == wi
-    assert same.mean() > 0.999
-    assert np.allclose(score[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert assert_order_matches_up_to_ties(ids, wi, score, ws) <= 0.001 * ids.size
     assert np.array_equal(bits(score), bits(_correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, 0.3, 0.1)))
 
 
@@ -283,16 +335,12 @@ def test_temporal_search_matches_oracle(exact):
         orc = _oracle_for(data, 16, 100, 0xFACE)
         rc, wi, ws, _ = orc.store_search_batch(q, k, 768, 64, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1], threads=8)
         assert rc == 0
-    # Rows whose neighbouring scores are separated by > 1e-5 relative must match in order exactly.
+    # Rows whose neighbouring scores are separated by > 1e-5 relative must match in order exactly; every other
+    # mismatch must sit on a near-tie of the oracle's own list.
     for r in range(len(q)):
-        gaps = np.diff(ws[r]) > 1e-5 * np.abs(ws[r][1:])
-        if gaps.all():
+        if (np.diff(ws[r]) > 1e-5 * np.abs(ws[r][1:]) + 1e-7).all():
             assert np.array_equal(ids[r], wi[r]), r
-        else:
-            assert set(ids[r].tolist()) == set(wi[r].tolist()) or True
-    same = ids == wi
-    assert same.mean() > 0.999
-    assert np.allclose(score[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert assert_order_matches_up_to_ties(ids, wi, score, ws) <= 0.001 * ids.size
     assert np.array_equal(bits(score), bits(_correctly_rounded_scores(dist, ts_s, ts_n, dec, ids, 0.3, 0.1)))
     assert np.all(np.diff(score, axis=1) >= 0)
 
@@ -413,9 +461,7 @@ def test_sharded_store_search_is_merge_then_rerank():
     assert np.array_equal(mi.cpu().numpy().view(np.uint32), gi) and np.array_equal(bits(md.cpu().numpy()), bits(gd))
     wi, ws = oracle.rerank_pool(gi, gd, k, w, base, ts_s, ts_n, dec, NOW[0], NOW[1])
     got_i, got_s = ri.cpu().numpy().view(np.uint32), rs.cpu().numpy()
-    same = got_i == wi
-    assert same.mean() > 0.999
-    assert np.allclose(got_s[same], ws[same], rtol=1e-5, atol=0.3 * 2.0 ** -24)
+    assert assert_order_matches_up_to_ties(got_i, wi, got_s, ws) <= 0.001 * wi.size
     assert np.all(np.diff(got_s, axis=1) >= 0)
 
 
@@ -478,3 +524,58 @@ def test_concurrent_callers_share_one_index():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_graph_sidecar_load_upload_search(tmp_path):
+    """a graph saved next to a snapshot is loaded into a FRESH index (no build), uploaded and searched:
+    results equal the index it was saved from and the oracle over the same sidecar."""
+    data, q = datasets.embedding_dataset(8000, 100, 0x51DE, dim=256, intrinsic=12)
+    cfg = default_config(dimensions=256, ef_construction=100)
+    built = ChronoMindB200.from_matrix(data, cfg).build_graph(0x51DE, 8).upload(0)
+    p = str(tmp_path / "graph.cmg")
+    built.save_graph(p)
+    fresh = ChronoMindB200.from_matrix(data, cfg).load_graph(p).upload(0)
+    assert fresh.check_invariants() == 0 and fresh.entry() == built.entry()
+    for h in range(0, 8000, 7):
+        for layer in range(built.top_layer(h) + 1):
+            assert np.array_equal(fresh.neighbors(h, layer), built.neighbors(h, layer))
+    orc = oracle.OracleHnsw(16, 100, 50, 0x51DE)
+    orc.import_graph(oracle.preprocess_rows(data), oracle.read_graph_sidecar(p))
+    for ef in (50, 128):
+        gi, gd = fresh.search_index(q, ef, ef)
+        c = last_counters()
+        bi, bd = built.search_index(q, ef, ef)
+        oi, od, _, octr = orc.search_batch(q, ef, ef, threads=8)
+        assert np.array_equal(gi, bi) and np.array_equal(bits(gd), bits(bd))
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+        assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1])
+    # a sidecar of another index is rejected, not searched
+    other = ChronoMindB200.from_matrix(data[:4000], cfg)
+    with pytest.raises(CmError) as e:
+        other.load_graph(p)
+    assert e.value.kind == "InvalidSnapshot"
+
+
+def test_hnsw_1m_graph_identical_to_oracle(tmp_path):
+    """BASELINE configs[2] at full size: 1M x 768 embedding-like rows, GPU-assisted graph -> sidecar -> oracle import;
+    256 queries at ef = 64 and 200 must come back with the oracle's ids, distance bits and work counters, and the
+    asynchronous status word must stay clean."""
+    gen = datasets.ChunkedCorpus("emb", 1_000_000, 768, 0x5EED)
+    data = gen.shard(0, 1)
+    q = gen.queries(256)
+    cfg = default_config(dimensions=768, ef_construction=100)
+    st = ChronoMindB200.from_matrix(data, cfg).build_graph_gpu(0x5EED, 0, 0).upload(0)
+    assert st.check_invariants() == 0
+    p = str(tmp_path / "g1m.cmg")
+    st.save_graph(p)
+    orc = oracle.OracleHnsw(16, 100, 50, 0x5EED)
+    orc.import_graph(oracle.preprocess_rows(data, threads=16), oracle.read_graph_sidecar(p))
+    del data
+    for ef in (64, 200):
+        gi, gd = st.search_index(q, ef, 10)
+        c = last_counters()
+        oi, od, _, octr = orc.search_batch(q, ef, 10, threads=16)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od)), ef
+        assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1]) and c["list_entries"] == int(octr[2])
+        assert c["failures"] == 0
+    assert st.dev_status() == 0

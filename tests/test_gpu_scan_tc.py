@@ -30,7 +30,8 @@ def store(data, deleted=None, engine=2):
                                              (3000, 40, 771, 10, "emb"), (300000, 700, 64, 10, "uni"),
                                              (200000, 257, 768, 10, "emb"), (150000, 520, 128, 50, "uni"),
                                              (400000, 300, 32, 100, "uni"), (60000, 260, 768, 100, "uni"),
-                                             (9000, 70, 4096, 10, "uni")])
+                                             (9000, 70, 4096, 10, "uni"), (8500, 40, 8192, 10, "uni"),
+                                             (8200, 24, 12800, 10, "emb")])   # longest rows the engines accept
 def test_tc_scan_is_exact(n, nq, dim, k, kind):
     if kind == "emb":
         data, q = datasets.embedding_dataset(n, nq, 0xBEEF + n, dim=dim)

@@ -105,8 +105,14 @@ def test_multi_thread_build_is_sound_and_searchable(tmp_path):
     # sidecar round trip
     st2 = ChronoMindB200.from_matrix(data, cfg).load_graph(p)
     assert st2.entry() == st.entry()
-    for i in (0, 17, 2999):
-        assert np.array_equal(st2.neighbors(i, 0), st.neighbors(i, 0))
+    assert st2.check_invariants() == 0
+    for i in range(3000):                                            # every list of every layer, byte for byte
+        assert st2.top_layer(i) == st.top_layer(i)
+        for layer in range(st.top_layer(i) + 1):
+            assert np.array_equal(st2.neighbors(i, layer), st.neighbors(i, layer)), (i, layer)
+    p2 = str(tmp_path / "g2.cmgraph")                                # save(load(save(g))) is the same file
+    st2.save_graph(p2)
+    assert open(p, "rb").read() == open(p2, "rb").read()
     with pytest.raises(CmError):
         ChronoMindB200.from_matrix(data[:100], cfg).load_graph(p)     # wrong index
 
