@@ -921,6 +921,10 @@ int cm_index_check_invariants(const cm_index* idx) {
   if (!idx || !idx->graph.built) return -1;
   return check_graph_invariants(idx->graph);
 }
+uint64_t cm_index_unreachable(const cm_index* idx) {
+  if (!idx || !idx->graph.built) return 0;
+  return count_unreachable(idx->graph);
+}
 uint64_t cm_index_entry(const cm_index* idx) { return idx && idx->graph.built ? idx->graph.entry : kEmptyEntry; }
 uint32_t cm_index_top_layer(const cm_index* idx, uint32_t handle) {
   if (!idx || !idx->graph.built || handle >= idx->n) return 0;

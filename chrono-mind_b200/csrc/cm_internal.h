@@ -71,6 +71,7 @@ struct Graph {
 void build_graph(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed, int threads,
                  Graph* g);
 int check_graph_invariants(const Graph& g);
+uint64_t count_unreachable(const Graph& g);  // layer-0 nodes the entry point cannot reach
 
 // GPU-assisted construction (hnsw_build.cpp): per layer, the members (ascending handles) and `width` candidate
 // neighbors per member (global handles, CM_NO_ID padded; may contain the member itself).

@@ -406,6 +406,107 @@ static void parallel_range(uint64_t n, int threads, F f) {
   for (auto& t : ts) t.join();
 }
 
+// seen[v] = 1 for every layer-0 node a search can arrive at: from the entry point along the edges of the top layer,
+// then, layer by layer, from everything reached above along the edges of the layer below (`LockFreeHnsw::search`
+// descends exactly like that, src/index/lockfree_hnsw.rs:481-486). Returns the number of nodes reached.
+static uint64_t mark_reachable(const Graph& g, std::vector<uint8_t>& seen) {
+  seen.assign(g.n, 0);
+  if (g.entry == kEmptyEntry || g.n == 0) return 0;
+  std::vector<uint32_t> reached{(uint32_t)g.entry}, stack;
+  seen[(uint32_t)g.entry] = 1;
+  for (uint32_t layer = (uint32_t)(g.entry >> 32) + 1; layer-- > 0;) {
+    stack = reached;  // everything reached above is a starting point on this layer
+    while (!stack.empty()) {
+      const uint32_t v = stack.back();
+      stack.pop_back();
+      uint32_t deg;
+      const uint32_t* l = g.list(v, layer, &deg);
+      for (uint32_t j = 0; j < deg; ++j)
+        if (!seen[l[j]]) seen[l[j]] = 1, reached.push_back(l[j]), stack.push_back(l[j]);
+    }
+  }
+  return reached.size();
+}
+
+// A kNN-derived graph has no connectivity guarantee: incremental insertion links every new node to something the entry
+// point already reaches and creates long-range edges while lists are still short, but all-pairs candidates only ever
+// name a node's nearest neighbors, so on clustered data layer 0 can fall apart into components the beam search cannot
+// cross. After the build every layer-0 node must be reachable the way a search moves (mark_reachable): each unreached
+// component is bridged by the reference's own means — `search_layer(ef_construction)` from the entry finds the
+// nearest REACHED nodes to an orphan u, `select_diverse` picks up to four of them, and each pick v gets the edge
+// v -> u (appended, or in place of v's farthest neighbor when the list is full; a node orphaned by that is picked up
+// by the next round). u -> v is added when u has room. Sequential and deterministic; a no-op on graphs that are already
+// connected (one walk, ~0.1 s per million nodes).
+static uint64_t repair_layer0_reachability(Builder& b) {
+  constexpr size_t kBridges = 4;  // back-links forced per bridged node
+  Graph* g = b.g;
+  const uint64_t n = b.n;
+  if (g->entry == kEmptyEntry || n == 0) return 0;
+  const uint32_t entry_id = (uint32_t)g->entry, entry_top = (uint32_t)(g->entry >> 32);
+  std::vector<uint8_t> seen;
+  std::vector<uint32_t> stack;
+  Scratch s;
+  uint64_t bridged = 0;
+  auto walk_from = [&](uint32_t start) {
+    if (seen[start]) return;
+    seen[start] = 1;
+    stack.push_back(start);
+    while (!stack.empty()) {
+      const uint32_t v = stack.back();
+      stack.pop_back();
+      const uint32_t* l = &g->nbr0[(uint64_t)v * b.cap0];
+      for (uint32_t j = 0; j < g->deg0[v]; ++j)
+        if (!seen[l[j]]) seen[l[j]] = 1, stack.push_back(l[j]);
+    }
+  };
+  for (int round = 0; round < 8; ++round) {
+    if (mark_reachable(*g, seen) == n) break;
+    uint64_t fixed_this_round = 0;
+    for (uint64_t u = 0; u < n; ++u) {
+      if (seen[u]) continue;
+      // nearest reached nodes to u: the search itself only ever visits nodes the entry reaches
+      const float* q = b.row((uint32_t)u);
+      uint32_t ep = entry_id;
+      for (uint32_t layer = entry_top; layer >= 1; --layer) ep = b.descend(q, ep, layer, s);
+      b.search_layer(q, &ep, 1, b.efC, 0, s);
+      // what `insert` would link u to: a diverse pick of the nearest reached nodes (:419-432) ...
+      s.with_d.clear();
+      for (uint64_t k : s.cands)
+        if (key_id(k) != u && seen[key_id(k)]) s.with_d.push_back(k);
+      if (s.with_d.empty()) continue;
+      b.select_diverse(s.with_d.data(), s.with_d.size(), kBridges, s);
+      const std::vector<uint32_t> picks = s.result;
+      uint32_t* lu = &g->nbr0[u * b.cap0];
+      uint32_t& du = g->deg0[u];
+      for (uint32_t v : picks) {
+        // ... and the back-link v -> u that makes u reachable, which `add_backlink` (:246-280) may drop when v's list
+        // is full: here it must stay, so it takes the place of v's farthest neighbor instead
+        uint32_t* lv = &g->nbr0[(uint64_t)v * b.cap0];
+        uint32_t& dv = g->deg0[v];
+        if (std::find(lv, lv + dv, (uint32_t)u) == lv + dv) {
+          if (dv < b.cap0) {
+            lv[dv++] = (uint32_t)u;
+          } else {
+            uint32_t far = 0;
+            uint64_t far_key = 0;
+            for (uint32_t j = 0; j < dv; ++j) {
+              const uint64_t k = pack(dist_prepared(b.row(lv[j]), b.row(v), b.dim), lv[j]);
+              if (k >= far_key) far_key = k, far = j;
+            }
+            lv[far] = (uint32_t)u;
+          }
+        }
+        if (du < b.cap0 && std::find(lu, lu + du, v) == lu + du) lu[du++] = v;
+      }
+      walk_from((uint32_t)u);  // u's whole component is reached now
+      ++fixed_this_round;
+    }
+    bridged += fixed_this_round;
+    if (fixed_this_round == 0) break;
+  }
+  return bridged;
+}
+
 void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
                                  int threads, const std::vector<LayerCandidates>& layers, Graph* g) {
   init_layout(n, p, seed, g);
@@ -428,20 +529,20 @@ void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const
     const LayerCandidates& lc = layers[layer];
     const uint64_t nm = lc.members.size();
     std::vector<uint32_t> own(nm * b.M, CM_NO_ID);
-    std::vector<uint8_t> own_deg(nm, 0);
+    std::vector<uint32_t> own_deg(nm, 0);  // max_connections has no upper bound in Config::validate
     // phase A: every member's own list from its candidates (no shared writes)
     parallel_range(nm, threads, [&](uint64_t i, Scratch& s) {
       const uint32_t u = lc.members[i];
       s.with_d.clear();
       for (uint32_t j = 0; j < lc.width; ++j) {
         uint32_t v = lc.ids[i * lc.width + j];
-        if (v == CM_NO_ID || v == u) continue;
+        if (v == CM_NO_ID || v == u || v >= n || g->top_layer[v] < layer) continue;  // only members of this layer link here
         s.with_d.push_back(pack(dist_prepared(b.row(v), b.row(u), dim), v));
       }
       std::sort(s.with_d.begin(), s.with_d.end());
       s.with_d.erase(std::unique(s.with_d.begin(), s.with_d.end()), s.with_d.end());
       b.select_diverse(s.with_d.data(), s.with_d.size(), b.M, s);
-      own_deg[i] = (uint8_t)s.result.size();
+      own_deg[i] = (uint32_t)s.result.size();
       std::memcpy(&own[i * b.M], s.result.data(), s.result.size() * sizeof(uint32_t));
       uint32_t* deg;
       uint32_t* l = b.list_ptr(u, layer, &deg);
@@ -493,7 +594,16 @@ void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const
   // raise_entry under in-order insertion (:351-371): the first handle that reaches the highest layer
   for (uint64_t i = 0; i < n; ++i)
     if (g->entry == kEmptyEntry || g->top_layer[i] > (uint32_t)(g->entry >> 32)) g->entry = ((uint64_t)g->top_layer[i] << 32) | i;
+  b.entry.store(g->entry);
+  b.mt = false;  // the repair below is sequential (and deterministic)
+  repair_layer0_reachability(b);
   g->built = true;
+}
+
+// Layer-0 nodes a search from the entry point cannot arrive at (see mark_reachable). 0 for an empty graph.
+uint64_t count_unreachable(const Graph& g) {
+  std::vector<uint8_t> seen;
+  return g.n - (g.entry == kEmptyEntry ? g.n : mark_reachable(g, seen));
 }
 
 // Members of layer `layer` (ascending handles) for the layer draw of (n, params, seed).

@@ -79,6 +79,7 @@ ABI = {
     "cm_index_importance": (_f, [_vp, _u32]),
     "cm_index_check_invariants": (_i, [_vp]),
     "cm_index_entry": (_u64, [_vp]),
+    "cm_index_unreachable": (_u64, [_vp]),
     "cm_index_top_layer": (_u32, [_vp, _u32]),
     "cm_index_neighbors": (_u32, [_vp, _u32, _u32, _vp, _u32]),
     "cm_index_vector": (_i, [_vp, _u32, _vp]),
@@ -344,6 +345,10 @@ class ChronoMindB200:
 
     def check_invariants(self) -> int:
         return int(native().cm_index_check_invariants(self._h))
+
+    def unreachable(self) -> int:
+        """Layer-0 nodes the entry point cannot reach (0: every node is searchable)."""
+        return int(native().cm_index_unreachable(self._h))
 
     def entry(self):
         w = int(native().cm_index_entry(self._h))

@@ -133,12 +133,15 @@ cm_status cm_index_build_graph(cm_index* idx, uint64_t layer_seed, int threads);
  * on CUDA device `device` (tensor-core scan, `n_candidates` nearest per node, 0 = min(ef_construction, 64), at most
  * 127); the host then applies the reference's `select_diverse` (:205-240) and `add_backlink` (:246-280) with `threads`
  * threads. Same layer draw and entry point as cm_index_build_graph; the linkage differs (as it does between any two
- * concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. */
+ * concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. Nearest-neighbor candidates
+ * alone do not guarantee a connected layer 0 (clustered data): components the entry point cannot reach are bridged
+ * afterwards (see cm_index_unreachable). */
 cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates);
 
 /* The host half of the GPU-assisted construction on caller-supplied candidates (any kNN source): `cand_ids[l]` holds
  * `widths[l]` candidate handles (CM_NO_ID padded; the member itself is skipped) for each member of layer l, members in
- * ascending handle order as cm_index_layer_members reports them for the same seed. */
+ * ascending handle order as cm_index_layer_members reports them for the same seed. Candidates that are not members
+ * of the layer are ignored. */
 cm_status cm_index_build_graph_from_candidates(cm_index* idx, uint64_t layer_seed, int threads, uint32_t n_layers,
                                                const uint32_t* const* cand_ids, const uint32_t* widths);
 /* Members of `layer` under the layer draw (`random_layer`, src/index/lockfree_hnsw.rs:126-132, ticket == handle) of
@@ -170,6 +173,11 @@ const char* cm_index_context_label(const cm_index* idx, uint32_t handle);
 float cm_index_importance(const cm_index* idx, uint32_t handle);
 /* `check_invariants` (src/index/lockfree_hnsw.rs:295-347): 0 when the built graph is sound. */
 int cm_index_check_invariants(const cm_index* idx);
+/* Layer-0 nodes a search cannot arrive at from the entry point — down through the upper layers, then along layer-0
+ * edges, as `LockFreeHnsw::search` moves (src/index/lockfree_hnsw.rs:481-486); 0 when every node is searchable. The reference's
+ * incremental insert links each new node into what the entry already reaches; the candidate-based builders bridge
+ * unreached components after linking and this reports what is left. */
+uint64_t cm_index_unreachable(const cm_index* idx);
 /* Graph readout for tests / sidecar files: entry word ((top_layer << 32) | id, ~0 when empty),
  * per-node top layer, and one neighbor list. */
 uint64_t cm_index_entry(const cm_index* idx);

@@ -243,3 +243,66 @@ def test_graph_from_knn_candidates_is_sound_and_searchable(tmp_path):
     want, _ = oracle.brute_force(prepared, q, 10, mode="prepared")
     recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(got.tolist(), want.tolist())])
     assert recall >= 0.95, recall
+
+
+def _clustered(n_clusters, per, dim, seed, spread=0.02):
+    """Tight, well separated clusters: the kNN of a row never leaves its cluster."""
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(size=(n_clusters, dim)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    x = np.repeat(centres, per, axis=0) + spread * rng.normal(size=(n_clusters * per, dim)).astype(np.float32)
+    perm = rng.permutation(len(x))
+    return x[perm].astype(np.float32), centres
+
+
+@pytest.mark.parametrize("clusters,per,width,bridging_needed", [(24, 120, 33, False), (160, 18, 65, False), (160, 18, 13, True)])
+def test_knn_graph_on_clustered_data_is_bridged_and_searchable(tmp_path, clusters, per, width, bridging_needed):
+    """Nearest-neighbor candidates alone can leave whole clusters without a way in (the reference's incremental insert
+    cannot: every new node is linked into what the entry already reaches). The candidate-based builder must bridge
+    them: no layer-0 node unreachable from the entry (the way a search moves), invariants intact, and the oracle
+    searching THAT graph meets the recall gate on queries at the cluster centres. The last case feeds fewer candidates
+    than a cluster has rows — every cluster without an upper-layer member starts out isolated — and only requires what
+    the repair guarantees: reachability."""
+    data, centres = _clustered(clusters, per, 32, 0xC1)
+    cfg = default_config(dimensions=32, ef_construction=64)
+    seed = 5
+    st = ChronoMindB200.from_matrix(data, cfg)
+    prepared = oracle.preprocess_rows(data)
+    cands = []
+    for m in st.layer_members(seed):
+        k = min(width, len(m))
+        ids, _ = oracle.brute_force(prepared[m], prepared[m], k, mode="prepared", threads=4)
+        cands.append(np.where(ids == 0xFFFFFFFF, 0xFFFFFFFF, m[np.minimum(ids, len(m) - 1)]).astype(np.uint32))
+    st.build_graph_from_candidates(seed, cands, threads=4)
+    assert st.check_invariants() == 0
+    assert st.unreachable() == 0
+    p = str(tmp_path / "c.cmg")
+    st.save_graph(p)
+    orc = oracle.OracleHnsw(16, 64, 50, seed)
+    orc.import_graph(prepared, oracle.read_graph_sidecar(p))
+    assert orc.check_invariants() == 0
+    q = centres + 0.01 * np.random.default_rng(3).normal(size=centres.shape).astype(np.float32)
+    got, _, _, _ = orc.search_batch(q, 64, 10, threads=4)
+    want, _ = oracle.brute_force(prepared, q, 10, mode="prepared")
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(got.tolist(), want.tolist())])
+    assert recall >= (0.85 if bridging_needed else 0.95), recall
+
+
+def test_candidates_outside_their_layer_are_ignored():
+    """Caller-supplied candidates are untrusted input: handles that did not draw the layer (or are out of range for
+    it) must neither corrupt memory nor create links that break invariant 7 (neighbor.top_layer >= layer)."""
+    data, _ = datasets.uniform_dataset(600, 1, 16, 9)
+    cfg = default_config(dimensions=16, max_connections=4, ef_construction=32)
+    st = ChronoMindB200.from_matrix(data, cfg)
+    members = st.layer_members(77)
+    assert len(members) >= 2
+    rng = np.random.default_rng(1)
+    cands = [rng.integers(0, 600, size=(len(m), 12)).astype(np.uint32) for m in members]   # any handle, any layer
+    st.build_graph_from_candidates(77, cands, threads=2)
+    assert st.check_invariants() == 0
+    for layer, m in enumerate(members[1:], start=1):
+        inside = set(m.tolist())
+        for h in m[:50]:
+            assert set(st.neighbors(int(h), layer).tolist()) <= inside
+    with pytest.raises(CmError):
+        st.build_graph_from_candidates(77, [np.full((len(m), 3), 600, np.uint32) for m in members])   # out of range
