@@ -684,11 +684,36 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   if (st != CM_OK) return st;
   uint64_t n = snap.memories.size();
   uint32_t dim = (uint32_t)snap.config.dimensions;
-  if (n > kArenaCapacity)
-    return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
+  // Replay `store.insert` record by record in file order (src/persistence.rs:117-119, src/store.rs:226-264):
+  // validate, then the capacity check (distinct ids), then the handle bookkeeping — a repeated id publishes the new
+  // handle and tombstones the one it replaces. The first failing record decides the error, as in the reference.
+  std::vector<uint8_t> deleted(n, 0);
+  uint64_t live = n;
+  {
+    std::unordered_map<std::string, uint32_t> by_id;
+    by_id.reserve(n * 2);
+    for (uint64_t i = 0; i < n; ++i) {
+      if ((st = validate_snapshot_memory(snap, i)) != CM_OK) return st;
+      const SnapshotMemory& m = snap.memories[i];
+      auto it = by_id.find(m.id);
+      if (it != by_id.end()) {
+        deleted[it->second] = 1;
+        live--;
+        it->second = (uint32_t)i;
+      } else {
+        if (by_id.size() >= snap.config.max_memories)
+          return fail(CM_ERR_CAPACITY_EXCEEDED, "store is at capacity (" + std::to_string(snap.config.max_memories) + " memories)");
+        by_id.emplace(m.id, (uint32_t)i);
+      }
+      if (i + 1 > kArenaCapacity)  // `VectorIndex::insert` -> None (src/index/arena.rs:114-118)
+        return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
+    }
+  }
   cm_index* idx = new_index(snap.config, n, dim);
+  idx->deleted = std::move(deleted);
+  idx->live = live;
   idx->x.resize(n * (uint64_t)dim);
-  const float* src = snap.vectors.data();
+  const float* src = snap.vectors.data();  // every record has exactly `dim` floats now: offsets are i * dim
   float* dst = idx->x.data();
   std::atomic<bool> finite{true};
   std::atomic<bool>* fin = &finite;
@@ -704,36 +729,18 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   {
     std::unordered_map<std::string, uint32_t> ctx_of;
     for (uint64_t i = 0; i < n; ++i) {
-      idx->importance[i] = snap.memories[i].importance;
-      auto it = ctx_of.find(snap.memories[i].context);
+      const SnapshotMemory& m = snap.memories[i];
+      idx->importance[i] = m.importance;
+      idx->ext_ids[i] = m.id;
+      idx->ts_secs[i] = m.ts_secs;
+      idx->ts_nanos[i] = m.ts_nanos;
+      idx->decay[i] = m.decay_rate;
+      auto it = ctx_of.find(m.context);
       if (it == ctx_of.end()) {
-        it = ctx_of.emplace(snap.memories[i].context, (uint32_t)idx->ctx_labels.size()).first;
-        idx->ctx_labels.push_back(snap.memories[i].context);
+        it = ctx_of.emplace(m.context, (uint32_t)idx->ctx_labels.size()).first;
+        idx->ctx_labels.push_back(m.context);
       }
       idx->ctx[i] = it->second;
-    }
-  }
-  // Replay ChronoMind::insert's handle bookkeeping (src/store.rs:226-264): a repeated id publishes the new
-  // handle and tombstones the one it replaces; capacity counts distinct ids.
-  std::unordered_map<std::string, uint32_t> by_id;
-  by_id.reserve(n * 2);
-  for (uint64_t i = 0; i < n; ++i) {
-    const SnapshotMemory& m = snap.memories[i];
-    idx->ext_ids[i] = m.id;
-    idx->ts_secs[i] = m.ts_secs;
-    idx->ts_nanos[i] = m.ts_nanos;
-    idx->decay[i] = m.decay_rate;
-    auto it = by_id.find(m.id);
-    if (it != by_id.end()) {
-      idx->deleted[it->second] = 1;
-      idx->live--;
-      it->second = (uint32_t)i;
-    } else {
-      if (by_id.size() >= snap.config.max_memories) {
-        cm_index_free(idx);
-        return fail(CM_ERR_CAPACITY_EXCEEDED, "store is at capacity (" + std::to_string(snap.config.max_memories) + " memories)");
-      }
-      by_id.emplace(m.id, (uint32_t)i);
     }
   }
   idx->raw = std::move(snap.vectors);

@@ -93,6 +93,7 @@ void preprocess_row(const float* v, uint32_t n, float* out);
 struct SnapshotMemory {
   std::string id;
   uint64_t data_offset;  // into SnapshotData::vectors (floats)
+  uint64_t data_len;     // floats in the record (== config.dimensions once validated)
   uint64_t ts_secs;
   uint32_t ts_nanos;
   float importance;
@@ -106,10 +107,11 @@ struct SnapshotMemory {
 struct SnapshotData {
   cm_config config;
   std::vector<SnapshotMemory> memories;
-  std::vector<float> vectors;  // memories.size() * config.dimensions, file order
+  std::vector<float> vectors;  // the records' data back to back, file order (data_offset / data_len)
 };
 // Returns CM_OK or the status load_snapshot would map to; message via set_error().
-cm_status read_snapshot(const char* path, SnapshotData* out);
+cm_status read_snapshot(const char* path, SnapshotData* out);  // decode + Config::validate only
+cm_status validate_snapshot_memory(const SnapshotData& snap, uint64_t i);  // Memory::validate of record i
 cm_status validate_config(const cm_config& c);
 
 // ---------------------------------------------------------------------------------------------------------

@@ -615,6 +615,10 @@ cudaError_t launch_rerank(const uint32_t* pool_ids, const float* pool_dist, uint
                           float* out_dist, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint32_t P = next_pow2(pool < 32 ? 32 : pool);
+  if ((size_t)P * 8 > 48 * 1024) {  // pools beyond 4096 need the opt-in shared-memory window (per device)
+    cudaError_t e = cudaFuncSetAttribute(k_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)P * 8));
+    if (e != cudaSuccess) return e;
+  }
   k_rerank<<<nq, 128, (size_t)P * 8, s>>>(pool_ids, pool_dist, pool, P, k, (const unsigned long long*)ts_secs, ts_nanos,
                                           decay, w, base, now_secs, now_nanos, out_ids, out_score, out_dist);
   count_launch();

@@ -195,21 +195,12 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
     if (!c.str(&m.id) || !valid_utf8(m.id)) return ser("bad memory id string");
     uint64_t len = c.u64();
     if (!c.ok || len > c.left / 4) return ser("vector length exceeds body size");
+    // decode first, judge later: bincode reads the whole body before `load_snapshot` inserts anything, so a
+    // truncated tail is a Serialization error even when an earlier record would fail validation
     m.data_offset = out->vectors.size();
-    if (len == cfg.dimensions) {
-      out->vectors.resize(m.data_offset + len);
-      c.take(out->vectors.data() + m.data_offset, len * 4);
-    } else {
-      // Memory::validate (src/types.rs:97-102) as applied by store.insert during load.
-      char buf[96];
-      std::snprintf(buf, sizeof buf, "invalid dimensions: got %llu, expected %llu", (unsigned long long)len,
-                    (unsigned long long)cfg.dimensions);
-      // validate_config runs first in the reference (ChronoMind::new precedes the inserts).
-      cm_status cs = validate_config(cfg);
-      if (cs != CM_OK) return cs;
-      set_error(buf);
-      return CM_ERR_INVALID_DIMENSIONS;
-    }
+    m.data_len = len;
+    out->vectors.resize(m.data_offset + len);
+    c.take(out->vectors.data() + m.data_offset, len * 4);
     m.ts_secs = c.u64();
     m.ts_nanos = c.u32();
     m.importance = c.f32();
@@ -230,28 +221,39 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   }
   // bincode::deserialize tolerates trailing bytes.
 
-  cm_status cs = validate_config(cfg);  // ChronoMind::new (src/store.rs:188)
-  if (cs != CM_OK) return cs;
-  for (uint64_t i = 0; i < out->memories.size(); ++i) {  // Memory::validate (src/types.rs:93-121)
-    const SnapshotMemory& m = out->memories[i];
-    if (m.id.empty()) {
-      set_error("invalid vector data: id must not be empty");
+  return validate_config(cfg);  // ChronoMind::new (src/store.rs:188) — before any insert
+}
+
+// `Memory::validate` (src/types.rs:93-121) for record i, in the reference's order of checks. `load_snapshot` applies it
+// through `store.insert` record by record (src/persistence.rs:117-119), interleaved with the capacity check — the
+// caller replays that order.
+cm_status validate_snapshot_memory(const SnapshotData& snap, uint64_t i) {
+  const SnapshotMemory& m = snap.memories[i];
+  const cm_config& cfg = snap.config;
+  if (m.id.empty()) {
+    set_error("invalid vector data: id must not be empty");
+    return CM_ERR_INVALID_VECTOR;
+  }
+  if (m.data_len != cfg.dimensions) {
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "invalid dimensions: got %llu, expected %llu", (unsigned long long)m.data_len,
+                  (unsigned long long)cfg.dimensions);
+    set_error(buf);
+    return CM_ERR_INVALID_DIMENSIONS;
+  }
+  const float* v = snap.vectors.data() + m.data_offset;
+  for (uint64_t j = 0; j < cfg.dimensions; ++j)
+    if (!std::isfinite(v[j])) {
+      set_error("invalid vector data: vector " + m.id + " contains NaN or infinite components");
       return CM_ERR_INVALID_VECTOR;
     }
-    const float* v = out->vectors.data() + m.data_offset;
-    for (uint64_t j = 0; j < cfg.dimensions; ++j)
-      if (!std::isfinite(v[j])) {
-        set_error("invalid vector data: vector " + m.id + " contains NaN or infinite components");
-        return CM_ERR_INVALID_VECTOR;
-      }
-    if (!std::isfinite(m.importance) || m.importance < 0.0f || m.importance > 1.0f) {
-      set_error("invalid importance value: must be within [0.0, 1.0]");
-      return CM_ERR_INVALID_IMPORTANCE;
-    }
-    if (!std::isfinite(m.decay_rate) || m.decay_rate < 0.0f) {
-      set_error("invalid vector data: vector " + m.id + " has an invalid decay rate");
-      return CM_ERR_INVALID_VECTOR;
-    }
+  if (!std::isfinite(m.importance) || m.importance < 0.0f || m.importance > 1.0f) {
+    set_error("invalid importance value: must be within [0.0, 1.0]");
+    return CM_ERR_INVALID_IMPORTANCE;
+  }
+  if (!std::isfinite(m.decay_rate) || m.decay_rate < 0.0f) {
+    set_error("invalid vector data: vector " + m.id + " has an invalid decay rate");
+    return CM_ERR_INVALID_VECTOR;
   }
   return CM_OK;
 }

@@ -197,6 +197,39 @@ def test_snapshot_errors_map_to_reference_variants(tmp_path):       # tests/pers
     assert e.value.kind == "CapacityExceeded"
 
 
+def test_snapshot_error_precedence_follows_load_order(tmp_path):
+    """`load_snapshot` decodes the WHOLE body first (src/persistence.rs:114), then inserts record by record, each insert
+    validating before its capacity check (src/store.rs:226-252): a truncated tail beats an invalid record, and among
+    records the first failing one in file order decides."""
+    import zlib
+
+    def load(b):
+        p = str(tmp_path / "y.bin")
+        open(p, "wb").write(b)
+        return ChronoMindB200.from_snapshot(p)
+
+    def kind_of(blob):
+        with pytest.raises(CmError) as e:
+            load(blob)
+        return e.value.kind
+
+    m = _sample_memories()
+    m[3].data = m[3].data[:3]                            # wrong length in record 3 ...
+    blob = sc.encode_snapshot(sc.Config(dimensions=4), m)
+    assert kind_of(blob) == "InvalidDimensions"
+    body = blob[12:-9]                                   # ... but a truncated tail is found first, while decoding
+    assert kind_of(blob[:8] + struct.pack("<I", zlib.crc32(body)) + body) == "Serialization"
+    m = _sample_memories()
+    m[7].importance = 1.5                                # record 7 invalid, capacity (5) runs out at record 5
+    assert kind_of(sc.encode_snapshot(sc.Config(dimensions=4, max_memories=5), m)) == "CapacityExceeded"
+    m[2].importance = -0.5                               # an earlier invalid record wins over the capacity error
+    assert kind_of(sc.encode_snapshot(sc.Config(dimensions=4, max_memories=5), m)) == "InvalidImportance"
+    m = _sample_memories()
+    m[1].id = ""                                         # id check precedes the dimension check within a record
+    m[1].data = m[1].data[:2]
+    assert kind_of(sc.encode_snapshot(sc.Config(dimensions=4), m)) == "InvalidVector"
+
+
 def test_snapshot_empty_store(tmp_path):
     p = str(tmp_path / "e.chrono")
     sc.write_snapshot(p, sc.Config(dimensions=3), [])
