@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — queries/sec of the batched exact search (BASELINE.json configs[1]) on N B200s.
+"""bench.py — queries/sec at recall@10 >= 0.95 of the batched search path (BASELINE.json) on N B200s.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload exact|hnsw]
 
-One "step" = one pass of the hot path over one 10,000-query batch against the 1,000,000 x 768 cosine corpus
-(k = 10, recall@10 = 1.0 by construction: the scan is exact). N > 1 (launched under torchrun, one rank per GPU)
-shards the corpus by vector id (global = local * N + rank, src/index/sharded_rwlock.rs:54-66), every rank scans
-its shard for the whole batch, the per-shard top-k lists are all-gathered over NCCL and merged on the device
-("scaling": "strong": the corpus is fixed, per-GPU work shrinks with N).
+One "step" = one pass of the hot path over one 10,000-query batch against the 1,000,000 x 768 cosine corpus (k = 10).
+The JSON line's headline (`value`, `e2e`, `roofline`) is the exact scan of BASELINE configs[1] (tcgen05 bf16 scan + fp32
+rescore, recall@10 = 1.0 by construction). The same line carries an `hnsw` block for configs[2]: the GPU-assisted
+graph of the same corpus, the batched traversal swept over ef, recall@10 against the exact scan, achieved HBM
+bandwidth on algorithmic bytes, and the FRONTIER point — the smallest ef whose recall@10 reaches 0.95.
 
-`--impl reference` times the reference algorithm's CPU form of the same path (the oracle's brute-force scan —
-the Rust crate cannot be built in this image) on the host cores, on a bounded query sample.
+N > 1 (launched under torchrun, one rank per GPU) shards the corpus by vector id (global = local * N + rank,
+src/index/sharded_rwlock.rs:54-66); every rank searches its shard for the whole batch, the per-shard top-k lists are
+all-gathered over NCCL and merged on the device ("scaling": "strong": the corpus is fixed).
+
+`--impl reference` times the reference's PRODUCTION read path on the host cores: `LockFreeHnsw::search`
+(src/index/lockfree_hnsw.rs:469-495; the oracle port — the Rust crate cannot be built in this image) over the same
+graph, at the smallest ef that reaches recall@10 >= 0.95, queries split statically over all host threads
+(benches/comparison.rs:125-139). Its brute-force scan (tests/recall_test.rs:70-79) is reported beside it.
 """
 import argparse
 import json
@@ -31,10 +37,22 @@ N_QUERIES = 10_000
 K = 10
 SEED = 0x5EED
 QUERY_BATCHES = 4          # distinct query batches rotated through the steps
+METRIC = "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k"
+DEFAULT_EFS = "16,20,24,28,32,40,48,64,128,200"
+NOW = (1_790_000_000, 0)
+TEMPORAL_W, BASE_DECAY = 0.3, 0.1
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def workload_string(n_rows, dim, data, nq, k):
+    """The TASK both arms run (identical in the `ours` and `reference` lines); the engine that serves it is named in
+    `config.engine`."""
+    cfg_no = "1 and 2" if (n_rows <= 1_000_000 and dim == 768) else ("3" if dim == 768 else "4")
+    return ("kNN search %dx%d cosine (%s data), %d-query batch, k=%d, recall@%d>=0.95 (BASELINE configs[%s])"
+            % (n_rows, dim, data, nq, k, k, cfg_no))
 
 
 def quiet_nccl_stdout():
@@ -43,6 +61,13 @@ def quiet_nccl_stdout():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 def measured_traffic(kernel, **match):
@@ -106,125 +131,274 @@ def cpu_scan_streaming(gen, q, k, threads, cache=None):
     return out_ids, bits.astype(np.uint32).view(np.float32), scan_s
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+def recall_at_k(got, want):
+    return float(np.mean([len(set(a) & set(b)) / want.shape[1] for a, b in zip(got.tolist(), want.tolist())]))
 
-    def __init__(self, gpu_index):
+
+def frontier_ef(per_ef, gate=0.95):
+    """Smallest ef whose recall@10 reaches the gate (the metric's operating point); None when none does."""
+    ok = sorted(int(e) for e, r in per_ef.items() if r["recall_at_10"] >= gate)
+    return ok[0] if ok else None
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / power / throttle reasons sampled DURING the timed regions, in-process through NVML every 5 ms
+    (a 0.25 s region yields ~50 samples); falls back to polling nvidia-smi when NVML cannot be loaded."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index, uuid=None):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+        self.gpu, self.uuid = gpu_index, uuid
+        self.rows, self._stop_evt, self._active = [], threading.Event(), threading.Event()
+        self.h = self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            if uuid:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                   # noqa: BLE001
+            log("[bench] NVML unavailable (%r): sampling nvidia-smi instead" % (e,))
+            self.nvml = None
+
+    def region(self, on):
+        """Only samples taken while a timed region is open are kept."""
+        (self._active.set if on else self._active.clear)()
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            return sm, self.max_sm, float(n.nvmlDeviceGetPowerUsage(self.h)) / 1000.0, mask
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        mask = sum(bit for (name, bit), v in zip(self.REASONS, p[3:7]) if v.lower().startswith("active"))
+        return float(p[0]), float(p[1]), float(p[2]), mask
 
     def run(self):
         while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+            if self._active.is_set():
+                try:
+                    self.rows.append(self._sample())
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.005 if self.nvml is not None else 0.05)
+            else:
+                self._stop_evt.wait(0.002)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.rows[0][1],
+                "reasons": [name for name, bit in self.REASONS if mask & bit],
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows),
+                "source": "nvml (in-process, 5 ms period, timed regions only)" if self.nvml is not None else "nvidia-smi"}
 
 
+def graph_cache_path(n_rows, dim, data, efc, rank, world):
+    """Both arms search the SAME graph. The GPU-assisted build is deterministic, so either arm can rebuild it; whichever
+    runs first on a box also leaves the sidecar here so the other one can skip the build."""
+    return "/tmp/chronomind_bench_%dx%d_%s_efc%d_seed%x_shard%dof%d.cmg" % (n_rows, dim, data, efc, SEED, rank, world)
+
+
+def build_or_load_graph(st, args, path, seed, device, threads, have_cuda):
+    """(how, seconds). GPU-assisted build when a device is there, the host replay of `LockFreeHnsw::insert` otherwise."""
+    from chronomind_b200.engine import CmError
+    t0 = time.time()
+    if not args.no_graph_cache and os.path.exists(path):
+        try:
+            st.load_graph(path)
+            return "sidecar %s (written by the other arm's build on this box)" % path, time.time() - t0
+        except CmError as e:
+            log("[bench] stale graph sidecar ignored: %s" % e)
+    if have_cuda and args.build == "gpu":
+        st.build_graph_gpu(seed, device, threads)
+        how = "gpu-assisted (all-pairs kNN candidates on the device, select/link on the host)"
+    else:
+        st.build_graph(seed, threads)
+        how = "host (LockFreeHnsw::insert restatement, %d threads)" % threads
+    secs = time.time() - t0
+    if not args.no_graph_cache:
+        try:
+            st.save_graph(path + ".tmp%d" % os.getpid())
+            os.replace(path + ".tmp%d" % os.getpid(), path)
+        except Exception as e:                                   # noqa: BLE001
+            log("[bench] could not cache the graph sidecar: %r" % (e,))
+    return how, secs
+
+
+def oracle_on_same_graph(st, shard, efc, threads):
+    """The CPU oracle over exactly the graph the engine searches (sidecar export -> import)."""
+    import oracle
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "graph.cmg")
+        st.save_graph(path)
+        g = oracle.read_graph_sidecar(path)
+    orc = oracle.OracleHnsw(16, efc, 50, SEED)
+    orc.import_graph(oracle.preprocess_rows(shard, threads=threads), g)
+    return orc
+
+
+def cpu_hnsw_best_qps(orc, qs, ef, k, threads, passes=3):
+    """`best_qps` (benches/external.rs:118-124): best of `passes` timed passes after one untimed."""
+    orc.search_batch(qs[:max(64, len(qs) // 8)], ef, k, threads=threads)
+    best, res = None, None
+    for _ in range(passes):
+        t1 = time.perf_counter()
+        res = orc.search_batch(qs, ef, k, threads=threads)
+        dt = time.perf_counter() - t1
+        best = dt if best is None else min(best, dt)
+    return len(qs) / best, best, res
+
+
+# =====================================================================================================================
+# --impl reference
+# =====================================================================================================================
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's own CPU form of the path. The Rust crate cannot be built in this image, so
-    this times the oracle port of its brute-force scan on all host threads, a bounded query sample per step."""
+    """The reference's own CPU implementation of the path on this box's host cores. Production read path = HNSW
+    (`LockFreeHnsw::search` under `ChronoMind::search`), so THAT is `value`; the brute-force scan the reference uses as
+    ground truth is reported beside it."""
     if rank != 0:
         return
+    import oracle
+    from chronomind_b200.engine import ChronoMindB200, default_config
     threads = os.cpu_count() or 1
     n_rows, nq = args.rows, args.queries
-    gen = make_corpus(args.data, n_rows)
-    queries = gen.queries(nq)
-    sample = min(args.cpu_sample or 2 * threads, nq)
-    cache = {} if n_rows * DIM * 4 <= 8e9 else None      # hold the prepared corpus when it fits (the index does)
-    for _ in range(min(args.warmup, 1)):
-        cpu_scan_streaming(gen, queries[:sample], K, threads, cache)
+    t_start = time.time()
+    try:
+        import torch
+        have_cuda = torch.cuda.is_available()
+    except Exception:
+        have_cuda = False
+    shard, queries_all, gen = make_data(n_rows, nq * QUERY_BATCHES, args.data, 0, 1)
+    cfg = default_config(dimensions=DIM, ef_construction=args.efc)
+    st = ChronoMindB200.from_matrix(shard, cfg)
+    how, build_s = build_or_load_graph(st, args, graph_cache_path(n_rows, DIM, args.data, args.efc, 0, 1), SEED, 0, threads, have_cuda)
+    log("[bench] reference arm graph: %s in %.1fs, invariants=%d" % (how, build_s, st.check_invariants()))
+    orc = oracle_on_same_graph(st, shard, args.efc, threads)
+    prepared_cache = {}
+    # operating point: smallest ef with recall@10 >= 0.95 against the reference's own brute force, on a bounded sample
+    rs = min(args.recall_sample, nq)
+    t0 = time.time()
+    truth, _, bf_secs = cpu_scan_streaming(gen, queries_all[:rs], K, threads, prepared_cache if n_rows * DIM * 4 <= 8e9 else None)
+    brute_qps = rs / bf_secs
+    log("[bench] brute force (ground truth) on %d queries: %.1f q/s (%.1fs)" % (rs, brute_qps, time.time() - t0))
+    sweep = {}
+    ef_star = None
+    for ef in ([args.ef] if args.ef else sorted({int(e) for e in args.efs.split(",")})):
+        if ef < K:
+            continue
+        ids, _, _, _ = orc.search_batch(queries_all[:rs], ef, K, threads=threads)
+        sweep[str(ef)] = {"recall_at_10": recall_at_k(ids, truth)}
+        if ef_star is None and sweep[str(ef)]["recall_at_10"] >= 0.95:
+            ef_star = ef
+            break
+    if ef_star is None:
+        ef_star = max(int(e) for e in sweep)
+    del prepared_cache
+    sample = min(args.cpu_sample or 2000, nq)                     # SEARCH_OPS-sized slices (benches/comparison.rs:35)
+    for s in range(args.warmup):
+        orc.search_batch(queries_all[(s * sample) % max(1, nq - sample):][:sample], ef_star, K, threads=threads)
     total = 0.0
     for s in range(args.steps):
-        q = queries[(s * sample) % max(1, nq - sample):][:sample]
-        total += cpu_scan_streaming(gen, q, K, threads, cache)[2]
+        q = queries_all[(s * sample) % max(1, len(queries_all) - sample):][:sample]
+        t1 = time.perf_counter()
+        orc.search_batch(q, ef_star, K, threads=threads)
+        total += time.perf_counter() - t1
     qps = sample * args.steps / total
+    rec = sweep.get(str(ef_star), {}).get("recall_at_10")
     line = {
-        "impl": "reference", "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": qps,
-        "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "exact brute-force kNN %dx%d cosine (%s), %d-query batch, k=%d (BASELINE configs[1])" % (n_rows, DIM, args.data, nq, K),
-                   "recall_at_10": 1.0, "engine": "CPU scan of the reference algorithm (oracle port, AVX2+FMA)"},
+        "config": {"workload": workload_string(n_rows, DIM, args.data, nq, K),
+                   "engine": "CPU LockFreeHnsw::search (oracle port, AVX2+FMA), ef=%d = smallest ef with recall@10 >= 0.95, %d host threads"
+                             % (ef_star, threads),
+                   "recall_at_10": rec, "ef": ef_star, "ef_sweep_recall": sweep,
+                   "graph": how, "graph_build_s": build_s, "brute_force_qps": brute_qps,
+                   "brute_force_note": "tests/recall_test.rs:70-79 linear scan, the reference's ground-truth helper (not its serving path)",
+                   "setup_s": time.time() - t_start},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": "%d queries per step x %d steps against the full %d x %d corpus (scan time only)" % (sample, args.steps, n_rows, DIM)},
+                         "sample": "%d-query slices of the %d-query batch per step x %d steps, ef=%d, same graph as the GPU arm"
+                                   % (sample, nq, args.steps, ef_star)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def _preprocess_mt(corpus, threads):
-    import oracle
-    return oracle.preprocess_rows(corpus, threads=threads)
-
-
-def run_hnsw(args, rank, world, local_rank):
-    """BASELINE configs[2]: batched HNSW search (one small CTA per query, rows gathered by the copy engine) + temporal
-    rerank, w = 0.3, on the graph the host builder constructs over the synthetic corpus (the snapshot carries no graph,
-    SURVEY.md F2).
-      value = queries/s of `VectorIndex::search(q, ef)` + take(10) at --ef, device resident, with recall@10 against the
-              exact scan reported beside it. N > 1: every rank searches ITS shard's graph (independent HNSW sub-graph per
-              shard, rows by id mod N), lists all-gathered over NCCL and merged by (distance, global handle).
-      e2e   = `ChronoMind::search` semantics with HOST buffers: H2D of the queries, HNSW pool of ef candidates,
-              (N > 1: all-gather + merge to the GLOBAL top-ef,) temporal rerank, D2H of [nq][10] handles and scores."""
+# =====================================================================================================================
+# --impl ours
+# =====================================================================================================================
+def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from chronomind_b200 import datasets, engine, sharding
     from chronomind_b200.engine import ChronoMindB200, default_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    peaks = load_peaks()
+    threads_all = os.cpu_count() or 1
+    threads = max(1, threads_all // world)
     n_rows, nq = args.rows, args.queries
-    efs = sorted({int(e) for e in args.efs.split(",")} | {args.ef})
-    shard, queries_all, gen = make_data(n_rows, nq * 2, args.data, rank, world)
-    now = (1_790_000_000, 0)
-    W, BASE = 0.3, 0.1
-    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, now[0])          # indexed by GLOBAL handle
+    want_hnsw = not args.no_hnsw and DIM == 768
+    if args.workload == "hnsw" and not want_hnsw:
+        raise SystemExit("--workload hnsw needs the 768-d corpus and the HNSW block")
+    want_exact = args.workload == "exact" or want_hnsw          # the exact scan is also the ground truth of the HNSW block
+
+    shard, queries_all, gen = make_data(n_rows, nq * QUERY_BATCHES, args.data, rank, world)
+    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, NOW[0])              # indexed by GLOBAL handle
+    t0 = time.time()
     cfg = default_config(dimensions=DIM, ef_construction=args.efc)
-    threads = max(1, (os.cpu_count() or 1) // world)
     st = ChronoMindB200.from_matrix(shard, cfg, sharding.shard_attrs(ts_s, rank, world), sharding.shard_attrs(ts_n, rank, world),
                                     sharding.shard_attrs(decay, rank, world)).set_shard(rank, world)
-    t0 = time.time()
-    if args.build == "gpu":
-        st.build_graph_gpu(SEED + rank, local_rank, threads)
-    else:
-        st.build_graph(SEED + rank, threads)
-    build_s = time.time() - t0
-    log("[bench] rank %d %s graph build: %d rows, M=16 efC=%d, %d threads, %.1fs (%.0f inserts/s), invariants=%d"
-        % (rank, args.build, shard.shape[0], args.efc, threads, build_s, shard.shape[0] / build_s, st.check_invariants()))
+    graph_how = graph_s = None
+    if want_hnsw:
+        graph_how, graph_s = build_or_load_graph(st, args, graph_cache_path(n_rows, DIM, args.data, args.efc, rank, world),
+                                                 SEED + rank, local_rank, threads, True)
+        log("[bench] rank %d graph: %s, %d rows, M=16 efC=%d, %.1fs, invariants=%d unreachable=%d"
+            % (rank, graph_how, shard.shape[0], args.efc, graph_s, st.check_invariants(), st.unreachable()))
     st.upload(local_rank)
-    g_ts_s = torch.from_numpy(ts_s.view(np.int64)).to(dev)
-    g_ts_n = torch.from_numpy(ts_n.view(np.int32)).to(dev)
-    g_decay = torch.from_numpy(decay).to(dev)
-    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(2)]
+    st.set_exact_engine(args.engine)
+    log("[bench] rank %d: index of %d rows resident on cuda:%d in %.1fs" % (rank, len(st), local_rank, time.time() - t0))
+
+    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(QUERY_BATCHES)]
     q_dev = [q.to(dev) for q in q_host]
     ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
     dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    out_i = torch.empty((nq, K), dtype=torch.int32).pin_memory()
-    out_s = torch.empty((nq, K), dtype=torch.float32).pin_memory()
-
+    out_ids_host = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    out_dist_host = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+    # N > 1: every rank needs the whole batch on its GPU. Each rank copies 1/N of it from pinned host memory over
+    # ITS PCIe link and the slices are all-gathered over NVLink (30.7 MB at 10k x 768) — the node's aggregate host
+    # bandwidth instead of N full copies.
     rows_per_rank = (nq + world - 1) // world
     q_gather = torch.empty((world * rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
     q_slice = torch.empty((rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
@@ -235,44 +409,18 @@ def run_hnsw(args, rank, world, local_rank):
         ig, dg = sharding.allgather_lists(ids, d)
         return engine.merge_topk_cuda(ig, dg, length)
 
+    def gather_queries(i):
+        qh = q_host[i % QUERY_BATCHES]
+        lo = min(nq, rank * rows_per_rank)
+        hi = min(nq, lo + rows_per_rank)
+        q_slice[:hi - lo].copy_(qh[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(q_gather, q_slice)
+        return q_gather[:nq]
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    truth = [merged(*st.search_exact_cuda(q, K), K)[0].cpu().numpy().view(np.uint32) for q in q_dev]   # exact ground truth
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs") or 6650.0
-
-    def recall(got, want):
-        return float(np.mean([len(set(a) & set(b)) / K for a, b in zip(got.tolist(), want.tolist())]))
-
-    def step_device(i, ef):
-        st.search_index_cuda(q_dev[i % 2], ef, K, ids_l, dist_l)
-        return merged(ids_l, dist_l, K)
-
-    def step_e2e(i, ef):
-        """ChronoMind::search through host buffers."""
-        if world == 1:
-            return st.search(q_host[i % 2].numpy(), K, now=now, ef_search=ef, temporal_weight=W, base_decay_rate=BASE)
-        qh = q_host[i % 2]                                               # 1/N of the batch per rank over PCIe,
-        lo = min(nq, rank * rows_per_rank)                               # the slices all-gathered over NVLink
-        hi = min(nq, lo + rows_per_rank)
-        q_slice[:hi - lo].copy_(qh[lo:hi], non_blocking=True)
-        dist.all_gather_into_tensor(q_gather, q_slice)
-        qd = q_gather[:nq]
-        pool = max(ef, 3 * K)                                            # OVERSAMPLE, src/store.rs:40,323
-        pi, pd = st.search_index_cuda(qd, pool, pool)
-        mi, md = merged(pi, pd, pool)                                    # global top-ef first (SURVEY.md §8e) ...
-        ri, rs, _ = engine.rerank_cuda(mi, md, K, g_ts_s, g_ts_n, g_decay, W, BASE, now)   # ... then the temporal blend
-        out_i.copy_(ri, non_blocking=True)
-        out_s.copy_(rs, non_blocking=True)
-        torch.cuda.synchronize()
-        return out_i, out_s
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -280,104 +428,282 @@ def run_hnsw(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    per_ef, head = {}, None
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(local_rank, uuid) if rank == 0 else None
     if sampler:
         sampler.start()
-    for ef in efs:
-        for i in range(args.warmup):
-            step_device(i, ef)
+
+    def timed_device(step_fn, warmup, steps):
+        """W untimed + K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream, max over
+        ranks. Returns (ms, result of the last step, kernels launched, (dominant-kernel ms, launches))."""
+        res = None
+        for i in range(warmup):
+            step_fn(i)
         barrier()
         engine.profile_enable(True)
         engine.profile_read()
         launches0 = engine.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if sampler:
+            sampler.region(True)
         ev0.record()
-        for i in range(args.steps):
-            res = step_device(args.warmup + i, ef)
+        for i in range(steps):
+            res = step_fn(warmup + i)
         ev1.record()
         barrier()
+        if sampler:
+            sampler.region(False)
         ms = max_over_ranks(ev0.elapsed_time(ev1))
         launches = engine.launch_count() - launches0
-        kernel_ms, kernel_n = engine.profile_read()
+        prof = engine.profile_read()
         engine.profile_enable(False)
-        last = (args.warmup + args.steps - 1) % 2
-        got = res[0].cpu().numpy().view(np.uint32)
-        for i in range(min(args.warmup, 2)):
-            step_e2e(i, ef)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            step_e2e(args.warmup + i, ef)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        # work counters of this rank's shard (== the CPU oracle's at equal ef on the same graph: tests/test_gpu_parity.py)
-        st.search_index(q_host[last].numpy(), ef, K)
-        c = engine.last_counters()
-        bytes_per_batch = c["dist_evals"] * DIM * 4 + c["list_entries"] * 4 + nq * DIM * 4
-        kern_avg = kernel_ms / max(kernel_n, 1)
-        r = {"ef": ef, "qps": nq * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "recall_at_10": recall(got, truth[last]),
-             "dist_evals_per_query": c["dist_evals"] / nq, "expansions_per_query": c["expansions"] / nq,
-             "algorithmic_bytes_per_query": bytes_per_batch / nq, "kernel_ms_avg": kern_avg,
-             "achieved_gbs": bytes_per_batch / (kern_avg * 1e-3) / 1e9 if kern_avg > 0 else None,
-             "hbm_frac": bytes_per_batch / (kern_avg * 1e-3) / 1e9 / hbm_peak if kern_avg > 0 else None,
-             "temporal_e2e_qps": nq * args.steps / e2e_s, "gpu_launches": launches, "visited_table_restarts": c["fallback_queries"]}
-        per_ef[str(ef)] = r
-        if rank == 0:
-            log("[bench] hnsw ef=%d: %s" % (ef, json.dumps(r)))
-        if ef == args.ef:
-            head = r
-    clocks = sampler.stop() if sampler else None
+        return ms, res, launches, prof
 
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        import oracle
-        import tempfile
-        t0 = time.time()
-        sample = args.cpu_sample or 64 * threads
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "graph.cmg")
-            st.save_graph(path)
-            g = oracle.read_graph_sidecar(path)
-        orc = oracle.OracleHnsw(16, args.efc, 50, SEED)
-        orc.import_graph(_preprocess_mt(shard, threads), g)
-        qs = queries_all[:sample]
-        orc.search_batch(qs, args.ef, K, threads=threads)
-        best = None
-        for _ in range(3):                                   # best_qps (benches/external.rs:118-124)
-            t1 = time.perf_counter()
-            oi, od, _, octr = orc.search_batch(qs, args.ef, K, threads=threads)
-            dt = time.perf_counter() - t1
-            best = dt if best is None else min(best, dt)
-        gi, gd = st.search_index(qs, args.ef, K)
-        parity = bool(np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32)))
-        cpu = {"value": sample / best, "unit": "queries/s", "cores": threads, "kind": "port",
-               "sample": "%d queries, ef=%d, same graph (sidecar import), best of 3 passes (%.2fs each)" % (sample, args.ef, best),
-               "parity_on_sample": parity, "dist_evals_per_query": float(octr[0]) / sample}
-        log("[bench] cpu baseline in %.1fs: %s" % (time.time() - t0, cpu))
-    if rank == 0:
-        line = {
-            "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": head["qps"], "unit": "queries/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, ef=%d, M=16 efC=%d host-built graph%s "
-                                   "(BASELINE configs[2]); temporal rerank w=0.3 in the e2e leg"
-                                   % (n_rows, DIM, args.data, nq, K, args.ef, args.efc, "" if world == 1 else " per shard, %d shards by id" % world),
-                       "recall_at_10": head["recall_at_10"], "per_ef": per_ef, "graph_build": args.build, "graph_build_s": build_s,
-                       "graph_build_inserts_per_s": shard.shape[0] / build_s, "build_threads": threads,
-                       "parallelism": "1 GPU" if world == 1 else "independent HNSW sub-graph per shard on %d GPUs, NCCL allgather + device merge (+ rerank of the global top-ef in e2e)" % world,
-                       "l2": "%.2f GB fp32 rows per GPU gathered at random: larger than L2; 2 query batches rotated" % (n_rows / world * DIM * 4 / 1e9)},
-            "e2e": {"value": head["temporal_e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
-            "gpu_launches": head["gpu_launches"],
+    def timed_host(step_fn, warmup, steps):
+        for i in range(min(warmup, 2)):
+            step_fn(i)
+        barrier()
+        if sampler:
+            sampler.region(True)
+        t0 = time.perf_counter()
+        out = None
+        for i in range(steps):
+            out = step_fn(warmup + i)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        if sampler:
+            sampler.region(False)
+        return max_over_ranks(secs), out
+
+    # ---- exact scan (configs[1]; ground truth of everything else) ---------------------------------------------------
+    exact = None
+    truth = None
+    if want_exact:
+        def step_device(i):
+            """Inputs resident in HBM; result stays on the device."""
+            st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_l, dist_l)
+            return merged(ids_l, dist_l, K)
+
+        def step_e2e(i):
+            """Public API with HOST buffers: H2D of the query batch and D2H of the result inside the step."""
+            if world == 1:
+                return st.search_exact(q_host[i % QUERY_BATCHES].numpy(), K)
+            st.search_exact_cuda(gather_queries(i), K, ids_l, dist_l)
+            mi, md = merged(ids_l, dist_l, K)
+            if rank == 0:                                   # the caller reads the merged result once
+                out_ids_host.copy_(mi, non_blocking=True)
+                out_dist_host.copy_(md, non_blocking=True)
+            torch.cuda.synchronize()
+            return out_ids_host, out_dist_host
+
+        ms, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, args.warmup, args.steps)
+        last_batch = (args.warmup + args.steps - 1) % QUERY_BATCHES
+        dev_ids = res[0].cpu().numpy().view(np.uint32).copy()      # what the timed device path returned last
+        dev_dist = res[1].cpu().numpy().copy()
+        unresolved_status = st.dev_status()                        # queries the async path could not resolve (0 normally)
+        e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps)
+        counters = engine.last_counters() if world == 1 else {}    # of the last host-buffer call (the e2e leg)
+        truth = [None] * QUERY_BATCHES
+        truth[last_batch] = dev_ids
+        tc = (counters.get("exact_engine") == 2) if world == 1 else (args.engine != 1 and shard.shape[0] >= 8192 and K <= 128)
+        unresolved = int((dev_ids[:, 0] == 0xFFFFFFFF).sum() + np.isnan(dev_dist[:, 0]).sum())
+        flops_per_launch = 2.0 * nq * shard.shape[0] * DIM * args.steps / max(kernel_n, 1)
+        kern_avg_ms = kernel_ms / max(kernel_n, 1)
+        achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+        burst = peaks.get("bf16_tflops") or 1650.0
+        sustained = peaks.get("bf16_tflops_sustained") or 1400.0
+        exact = {
+            "ms": ms, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
+            "dev_ids": dev_ids, "dev_dist": dev_dist, "last_batch": last_batch, "tc": tc, "unresolved": unresolved + unresolved_status,
+            "counters": counters,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+                         "frac": (achieved / burst) if achieved else None,
+                         "frac_burst": (achieved / burst) if achieved else None,
+                         "frac_sustained": (achieved / sustained) if achieved else None, "peak_sustained": sustained,
+                         "traffic": measured_traffic("scan_tc_kernel", rows=n_rows, queries=nq, n_gpus=world, data=args.data) if tc else None,
+                         "traffic_unit": "DRAM bytes per launch (ncu); algorithmic minimum = one pass over the bf16 corpus + queries = %d"
+                                         % (shard.shape[0] * DIM * 2 + nq * DIM * 2),
+                         "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
+                         "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
+                         "algorithmic_flop_per_launch": flops_per_launch,
+                         "scores_per_s_per_gpu": (nq * shard.shape[0] / (kern_avg_ms * 1e-3)) if kern_avg_ms > 0 else None,
+                         "note": None if DIM >= 256 else "short rows: one or two UMMA k-steps per tile, the TMEM-epilogue select bounds "
+                                                         "this shape (SURVEY.md H6); read scores_per_s_per_gpu, not frac",
+                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: the timed region is a fraction of a second); "
+                                         "frac_sustained uses bf16_tflops_sustained") if peaks else "fallback of B200_PROFILING.md"}}
+        if rank == 0:
+            log("[bench] exact: %.0f q/s device, %.0f q/s e2e, K1 %.0f TFLOP/s; counters of the last e2e call: %s; unresolved: %d"
+                % (exact["qps"], exact["e2e_qps"], achieved or 0, counters, exact["unresolved"]))
+
+    # ---- HNSW block (configs[2]) -------------------------------------------------------------------------------------
+    hnsw = None
+    if want_hnsw:
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        g_ts_s = torch.from_numpy(ts_s.view(np.int64)).to(dev)
+        g_ts_n = torch.from_numpy(ts_n.view(np.int32)).to(dev)
+        g_decay = torch.from_numpy(decay).to(dev)
+        efs = sorted({int(e) for e in args.efs.split(",")} | ({args.ef} if args.ef else set()))
+        efs = [e for e in efs if e >= K]
+        nb = 2                                                       # query batches rotated by the HNSW legs
+        for b in range(nb):                                          # exact ground truth for the batches used
+            if truth is None or truth[b] is None:
+                t_ids = merged(*st.search_exact_cuda(q_dev[b], K), K)[0].cpu().numpy().view(np.uint32)
+                if truth is None:
+                    truth = [None] * QUERY_BATCHES
+                truth[b] = t_ids
+        h_steps, h_warm = max(3, min(args.steps, args.hnsw_steps)), min(args.warmup, 3)
+        per_ef = {}
+        for ef in efs:
+            def step_device(i, ef=ef):
+                st.search_index_cuda(q_dev[i % nb], ef, K, ids_l, dist_l)
+                return merged(ids_l, dist_l, K)
+
+            def step_e2e_index(i, ef=ef):
+                """`VectorIndex::search(q, ef)` + take(10) through host buffers — the call the reference arm times."""
+                return st.search_index(q_host[i % nb].numpy(), ef, K)
+
+            def step_e2e_temporal(i, ef=ef):
+                """`ChronoMind::search` through host buffers: pool of max(ef, 3k), (N > 1: merge to the global pool,)
+                fused temporal rerank w = 0.3."""
+                if world == 1:
+                    return st.search(q_host[i % nb].numpy(), K, now=NOW, ef_search=ef, temporal_weight=TEMPORAL_W, base_decay_rate=BASE_DECAY)
+                pool = max(ef, 3 * K)                                    # OVERSAMPLE, src/store.rs:40,323
+                pi, pd = st.search_index_cuda(gather_queries(i), pool, pool)
+                mi, md = merged(pi, pd, pool)                            # global top-ef first (SURVEY.md §8e) ...
+                ri, rs_, _ = engine.rerank_cuda(mi, md, K, g_ts_s, g_ts_n, g_decay, TEMPORAL_W, BASE_DECAY, NOW)   # ... then the blend
+                out_ids_host.copy_(ri, non_blocking=True)
+                out_dist_host.copy_(rs_, non_blocking=True)
+                torch.cuda.synchronize()
+                return out_ids_host, out_dist_host
+
+            ms, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, h_warm, h_steps)
+            last = (h_warm + h_steps - 1) % nb
+            got = res[0].cpu().numpy().view(np.uint32)
+            e2e_t, _ = timed_host(step_e2e_temporal, 1, 3)
+            e2e_i = None
+            if world == 1:
+                e2e_i, _ = timed_host(step_e2e_index, 1, 3)
+                c = engine.last_counters()                               # of the last host-buffer index search == one batch
+            else:
+                st.search_index(q_host[last].numpy(), ef, K)
+                c = engine.last_counters()
+            bytes_per_batch = c["dist_evals"] * DIM * 4 + c["list_entries"] * 4 + nq * DIM * 4
+            kern_avg = kernel_ms / max(kernel_n, 1)
+            per_ef[str(ef)] = {
+                "ef": ef, "qps": nq * h_steps / (ms * 1e-3), "ms_per_step": ms / h_steps, "recall_at_10": recall_at_k(got, truth[last]),
+                "dist_evals_per_query": c["dist_evals"] / nq, "expansions_per_query": c["expansions"] / nq,
+                "algorithmic_bytes_per_query": bytes_per_batch / nq, "kernel_ms_avg": kern_avg,
+                "achieved_gbs": bytes_per_batch / (kern_avg * 1e-3) / 1e9 if kern_avg > 0 else None,
+                "hbm_frac": bytes_per_batch / (kern_avg * 1e-3) / 1e9 / hbm_peak if kern_avg > 0 else None,
+                "e2e_index_qps": (nq * 3 / e2e_i) if e2e_i else None, "e2e_temporal_qps": nq * 3 / e2e_t,
+                "gpu_launches_per_step": launches / h_steps, "visited_table_restarts": c["fallback_queries"],
+                "tie_replays": c.get("tie_replays", 0), "failures": c.get("failures", 0)}
+            if rank == 0:
+                log("[bench] hnsw ef=%d: %s" % (ef, json.dumps(per_ef[str(ef)])))
+        ef_star = args.ef or frontier_ef(per_ef) or max(efs)
+        head = per_ef[str(ef_star)]
+        hnsw = {
+            "workload": "HNSW batched search %dx%d cosine (%s), %d-query batch, k=%d, M=16 efC=%d graph%s (BASELINE configs[2]); "
+                        "temporal rerank w=%.1f in e2e_temporal" % (n_rows, DIM, args.data, nq, K, args.efc,
+                                                                      "" if world == 1 else " per shard, %d shards by id" % world, TEMPORAL_W),
+            "frontier": {"ef": ef_star, "rule": "smallest measured ef with recall@10 >= 0.95 against the exact scan", "qps": head["qps"],
+                         "recall_at_10": head["recall_at_10"], "e2e_index_qps": head["e2e_index_qps"],
+                         "e2e_temporal_qps": head["e2e_temporal_qps"], "hbm_frac": head["hbm_frac"]},
+            "per_ef": per_ef, "steps_per_ef": h_steps, "warmup_per_ef": h_warm,
+            "graph_build": graph_how, "graph_build_s": graph_s, "graph_build_inserts_per_s": (shard.shape[0] / graph_s) if graph_s else None,
+            "build_threads": threads,
             "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
-                         "traffic": measured_traffic("k_hnsw_search", rows=n_rows, queries=nq, n_gpus=world, data=args.data, ef=args.ef),
+                         "ef": ef_star,
+                         "traffic": measured_traffic("k_hnsw_search", rows=n_rows, queries=nq, n_gpus=world, data=args.data, ef=ef_star),
                          "traffic_unit": "DRAM bytes per launch (ncu) vs algorithmic %d" % int(head["algorithmic_bytes_per_query"] * nq),
                          "kernel": "k_hnsw_search (rank 0's shard)", "kernel_ms_avg": head["kernel_ms_avg"],
                          "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
-            "cpu_baseline": cpu, "clocks": clocks,
-        }
+            "l2": "%.2f GB fp32 rows per GPU gathered at random: larger than L2; %d query batches rotated" % (shard.shape[0] * DIM * 4 / 1e9, nb)}
+    clocks = sampler.stop() if sampler else None
+
+    # ---- CPU baseline + parity of the timed results (rank 0, N = 1) --------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = {"unit": "queries/s", "cores": threads_all, "kind": "port"}
+        t0 = time.time()
+        if exact is not None:
+            # the reference's brute force on a sample of the TIMED batch: parity check of the timed device result
+            sample = min(args.cpu_sample or 256, nq)
+            lb = exact["last_batch"]
+            qs = queries_all[lb * nq:lb * nq + sample]
+            wi, wd, secs = cpu_scan_streaming(gen, qs, K, threads_all)
+            gi, gd = exact["dev_ids"][:sample], exact["dev_dist"][:sample]
+            cpu.update({"brute_force_qps": sample / secs,
+                        "brute_force_sample": "%d of the %d queries of the last timed batch against the full %dx%d corpus (%.1fs of scan time)"
+                                              % (sample, nq, n_rows, DIM, secs),
+                        "parity_on_sample": bool(np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32))),
+                        "recall_at_10_on_sample": recall_at_k(gi, wi)})
+            if DIM != 768:
+                log("[bench] note: unit vectors, so the L2 ranking of BASELINE configs[4] is this cosine ranking "
+                    "(|a-b|^2 = 2(1 - a.b)); the reference has no L2 metric (SURVEY.md F3)")
+        if hnsw is not None and world == 1:
+            # the reference's production path on the same graph, at the frontier ef
+            orc = oracle_on_same_graph(st, shard, args.efc, threads_all)
+            ef_star = hnsw["frontier"]["ef"]
+            hs = min(args.cpu_hnsw_sample, nq)
+            qs = queries_all[:hs]
+            qps, best, (oi, od, _, octr) = cpu_hnsw_best_qps(orc, qs, ef_star, K, threads_all)
+            gi, gd = st.search_index(qs, ef_star, K)
+            gc = engine.last_counters()
+            par = {str(ef_star): bool(np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+                                      and gc["dist_evals"] == int(octr[0]) and gc["expansions"] == int(octr[1]))}
+            for ef in (64, 200):
+                oi2, od2, _, octr2 = orc.search_batch(qs[:512], ef, K, threads=threads_all)
+                gi2, gd2 = st.search_index(qs[:512], ef, K)
+                gc2 = engine.last_counters()
+                par[str(ef)] = bool(np.array_equal(gi2, oi2) and np.array_equal(gd2.view(np.uint32), od2.view(np.uint32))
+                                    and gc2["dist_evals"] == int(octr2[0]) and gc2["expansions"] == int(octr2[1]))
+            cpu.update({"value": qps, "engine": "LockFreeHnsw::search (oracle port) at the frontier ef=%d on the same graph" % ef_star,
+                        "sample": "%d queries, ef=%d, same graph (sidecar export -> oracle import), best of 3 passes (%.3fs each)"
+                                  % (hs, ef_star, best),
+                        "hnsw_parity_ids_dists_counters": par, "dist_evals_per_query": float(octr[0]) / hs})
+            hnsw["cpu_baseline"] = {k: cpu[k] for k in ("value", "sample", "hnsw_parity_ids_dists_counters")}
+        elif exact is not None:
+            cpu.update({"value": cpu["brute_force_qps"], "sample": cpu["brute_force_sample"], "engine": "brute force (oracle port)"})
+        log("[bench] cpu baseline + parity in %.1fs: %s" % (time.time() - t0, cpu))
+
+    if rank == 0:
+        wl = workload_string(n_rows, DIM, args.data, nq, K)
+        common = {"metric": METRIC, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic"}
+        if args.workload == "exact":
+            line = dict(common, value=exact["qps"], ms_per_step=exact["ms"] / args.steps, dtype="bf16" if exact["tc"] else "f32",
+                        config={"workload": wl, "engine": ("tcgen05 bf16 scan + fp32 rescore (exact: recall@10 = 1.0)" if exact["tc"]
+                                                           else "fp32 CUDA-core scan (exact)"),
+                                "recall_at_10": (cpu or {}).get("recall_at_10_on_sample", "exact by construction (unchecked: --no-cpu-baseline)"),
+                                "unresolved_queries": exact["unresolved"], "fallback_queries_e2e": exact["counters"].get("fallback_queries"),
+                                "rescored_per_query_e2e": (exact["counters"].get("rescored", 0) / nq) if exact["counters"] else None,
+                                "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
+                                "l2": "inputs larger than L2: %.2f GB bf16 corpus per GPU streamed per step; %d query batches rotated"
+                                      % (shard.shape[0] * DIM * 2 / 1e9, QUERY_BATCHES)},
+                        e2e={"value": exact["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
+                        gpu_launches=exact["launches"], roofline=exact["roofline"])
+        else:
+            f = hnsw["frontier"]
+            head = hnsw["per_ef"][str(f["ef"])]
+            line = dict(common, value=head["qps"], ms_per_step=head["ms_per_step"], dtype="f32", steps=hnsw["steps_per_ef"],
+                        warmup=hnsw["warmup_per_ef"],
+                        config={"workload": wl, "engine": "batched HNSW traversal at ef=%d (frontier)" % f["ef"], "recall_at_10": head["recall_at_10"],
+                                "parallelism": "1 GPU" if world == 1 else "independent HNSW sub-graph per shard on %d GPUs, NCCL allgather + device merge" % world,
+                                "l2": hnsw["l2"]},
+                        e2e={"value": head["e2e_index_qps"] or head["e2e_temporal_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4,
+                             "d2h_bytes_per_step": nq * K * 8},
+                        gpu_launches=int(head["gpu_launches_per_step"] * hnsw["steps_per_ef"]), roofline=hnsw["roofline"])
+        line["cpu_baseline"] = cpu
+        line["clocks"] = clocks
+        if hnsw is not None:
+            line["hnsw"] = hnsw
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -393,19 +719,24 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="corpus rows (default: the metric's 1,000,000)")
     ap.add_argument("--queries", type=int, default=N_QUERIES)
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 fp32 CUDA-core scan, 2 tcgen05 scan + rescore")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0: 2 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the brute-force parity sample (0: 256) / per reference step (0: 2000)")
+    ap.add_argument("--cpu-hnsw-sample", type=int, default=2048, help="queries timed through the CPU HNSW oracle in the ours arm")
+    ap.add_argument("--recall-sample", type=int, default=256, help="reference arm: queries whose brute-force truth picks the operating ef")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW block (graph build + ef sweep)")
+    ap.add_argument("--no-graph-cache", action="store_true", help="neither read nor write the /tmp graph sidecar")
     ap.add_argument("--workload", default="exact", choices=["exact", "hnsw"],
-                    help="exact: BASELINE configs[1] (the metric's workload); hnsw: configs[2], batched HNSW + temporal rerank")
-    ap.add_argument("--ef", type=int, default=128, help="hnsw: the ef the headline value is quoted at")
-    ap.add_argument("--efs", default="64,128,200", help="hnsw: every ef measured (reported under config.per_ef)")
-    ap.add_argument("--efc", type=int, default=100, help="hnsw: ef_construction of the host-built graph")
+                    help="which leg is the line's headline: exact (BASELINE configs[1], the metric's workload) or hnsw (configs[2])")
+    ap.add_argument("--ef", type=int, default=0, help="hnsw: quote the headline at this ef instead of the recall frontier")
+    ap.add_argument("--efs", default=DEFAULT_EFS, help="hnsw: every ef measured (reported under hnsw.per_ef)")
+    ap.add_argument("--hnsw-steps", type=int, default=10, help="timed steps per ef of the sweep")
+    ap.add_argument("--efc", type=int, default=100, help="hnsw: ef_construction of the graph")
     ap.add_argument("--data", default="emb", choices=["emb", "uniform"])
     ap.add_argument("--dim", type=int, default=DIM, help="vector dimension (default 768; 32 with --k 100 is BASELINE configs[4])")
     ap.add_argument("--k", type=int, default=K, help="neighbors per query (default 10)")
-    ap.add_argument("--build", default="host", choices=["host", "gpu"],
-                    help="hnsw: graph construction — host (LockFreeHnsw::insert restatement, all cores) or gpu-assisted "
-                         "(all-pairs kNN candidates on the device, select/link on the host)")
+    ap.add_argument("--build", default="gpu", choices=["host", "gpu"],
+                    help="hnsw: graph construction — gpu-assisted (all-pairs kNN candidates on the device, select/link on the "
+                         "host) or host (LockFreeHnsw::insert restatement, all cores)")
     args = ap.parse_args()
 
     DIM, K = args.dim, args.k            # the workload shape is module state for the helpers above
@@ -416,187 +747,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.workload == "hnsw":
-        run_hnsw(args, rank, world, local_rank)
-        return
-
-    import torch
-    import torch.distributed as dist
-    from chronomind_b200 import engine, sharding
-    from chronomind_b200.engine import ChronoMindB200, default_config
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl_stdout()
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
-
-    n_rows, nq = args.rows, args.queries
-    shard, queries_all, gen = make_data(n_rows, nq * QUERY_BATCHES, args.data, rank, world)
-    t0 = time.time()
-    st = ChronoMindB200.from_matrix(shard, default_config(dimensions=DIM)).set_shard(rank, world).upload(local_rank)
-    st.set_exact_engine(args.engine)
-    log("[bench] rank %d: index of %d rows resident on cuda:%d in %.1fs" % (rank, len(st), local_rank, time.time() - t0))
-
-    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(QUERY_BATCHES)]
-    q_dev = [q.to(dev) for q in q_host]
-    ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
-    dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    out_ids_host = torch.empty((nq, K), dtype=torch.int32).pin_memory()
-    out_dist_host = torch.empty((nq, K), dtype=torch.float32).pin_memory()
-
-    def step_device(i):
-        """Inputs resident in HBM; result stays on the device."""
-        st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_l, dist_l)
-        if world > 1:
-            ids_g, dist_g = sharding.allgather_lists(ids_l, dist_l)
-            return engine.merge_topk_cuda(ids_g, dist_g, K)
-        return ids_l, dist_l
-
-    # N > 1: every rank needs the whole batch on its GPU. Each rank copies 1/N of it from pinned host memory over
-    # ITS PCIe link and the slices are all-gathered over NVLink (30.7 MB at 10k x 768) — the node's aggregate host
-    # bandwidth instead of N full copies.
-    rows_per_rank = (nq + world - 1) // world
-    q_gather = torch.empty((world * rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
-    q_slice = torch.empty((rows_per_rank, DIM), dtype=torch.float32, device=dev) if world > 1 else None
-
-    def step_e2e(i):
-        """Public API with HOST buffers: H2D of the query batch and D2H of the result inside the step."""
-        if world == 1:
-            return st.search_exact(q_host[i % QUERY_BATCHES].numpy(), K)
-        qh = q_host[i % QUERY_BATCHES]
-        lo = min(nq, rank * rows_per_rank)
-        hi = min(nq, lo + rows_per_rank)
-        q_slice[:hi - lo].copy_(qh[lo:hi], non_blocking=True)
-        dist.all_gather_into_tensor(q_gather, q_slice)
-        st.search_exact_cuda(q_gather[:nq], K, ids_l, dist_l)
-        ids_g, dist_g = sharding.allgather_lists(ids_l, dist_l)
-        mi, md = engine.merge_topk_cuda(ids_g, dist_g, K)
-        if rank == 0:                                   # the caller reads the merged result once
-            out_ids_host.copy_(mi, non_blocking=True)
-            out_dist_host.copy_(md, non_blocking=True)
-        torch.cuda.synchronize()
-        return out_ids_host, out_dist_host
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
-    engine.profile_enable(True)
-    engine.profile_read()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = engine.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        res = step_device(args.warmup + i)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    last_batch = (args.warmup + args.steps - 1) % QUERY_BATCHES
-    dev_ids = res[0].cpu().numpy().view(np.uint32).copy()      # what the timed device path returned last
-    dev_dist = res[1].cpu().numpy().copy()
-    launches = engine.launch_count() - launches0
-    kernel_ms, kernel_n = engine.profile_read()
-    engine.profile_enable(False)
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-
-    # ---- end-to-end through the host-buffer API -----------------------------------------------------------------
-    for i in range(min(args.warmup, 2)):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = step_e2e(args.warmup + i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        counters = engine.last_counters()                      # of the last host-buffer call (the e2e leg)
-        tc = counters.get("exact_engine") == 2
-        unresolved = int((dev_ids[:, 0] == 0xFFFFFFFF).sum() + np.isnan(dev_dist[:, 0]).sum())
-        log("[bench] counters of the last e2e call: %s; unresolved rows in the timed device result: %d" % (counters, unresolved))
-        flops_per_launch = 2.0 * nq * (n_rows / world) * DIM * args.steps / max(kernel_n, 1)
-        kern_avg_ms = kernel_ms / max(kernel_n, 1)
-        achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if achieved else None,
-                    "traffic": measured_traffic("scan_tc_kernel", rows=n_rows, queries=nq, n_gpus=world, data=args.data) if tc else None,
-                    "traffic_unit": "DRAM bytes per launch (ncu); algorithmic minimum = one pass over the bf16 corpus + queries = %d" % (n_rows // world * DIM * 2 + nq * DIM * 2),
-                    "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
-                    "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
-                    "scores_per_s_per_gpu": (nq * (n_rows / world) / (kern_avg_ms * 1e-3)) if kern_avg_ms > 0 else None,
-                    "note": None if DIM >= 256 else "short rows: one or two UMMA k-steps per tile, the TMEM-epilogue select bounds "
-                                                    "this shape (SURVEY.md H6); read scores_per_s_per_gpu, not frac",
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                    if peaks else "fallback of B200_PROFILING.md"}
-        cpu = None
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sample = args.cpu_sample or 2 * threads
-            t0 = time.time()
-            # the oracle's scan of the sample: the CPU number AND the parity check of the TIMED device result
-            # (last step's batch)
-            qs = queries_all[last_batch * nq:last_batch * nq + sample]
-            wi, wd, secs = cpu_scan_streaming(gen, qs, K, threads)
-            qps = sample / secs
-            gi, gd = dev_ids[:sample], dev_dist[:sample]
-            parity = bool(np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)))
-            recall = float(np.mean([len(set(a) & set(b)) / K for a, b in zip(gi.tolist(), wi.tolist())]))
-            if DIM != 768:
-                log("[bench] note: unit vectors, so the L2 ranking of BASELINE configs[4] is this cosine ranking "
-                    "(|a-b|^2 = 2(1 - a.b)); the reference has no L2 metric (SURVEY.md F3)")
-            cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                   "sample": "%d of the %d queries against the full %dx%d corpus, one pass (%.1fs of scan time)"
-                             % (sample, nq, n_rows, DIM, secs), "parity_on_sample": parity,
-                   "recall_at_10_on_sample": recall}
-            log("[bench] cpu baseline in %.1fs" % (time.time() - t0))
-        cfg_no = "1" if (n_rows <= 1_000_000 and DIM == 768) else ("3" if DIM == 768 else "4")
-        line = {
-            "metric": "queries/sec at recall@10>=0.95, 1Mx768 cosine, batch 10k", "value": nq * args.steps / (ms * 1e-3),
-            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if tc else "f32", "data": "synthetic",
-            "config": {"workload": "exact brute-force kNN %dx%d cosine (%s data), %d-query batch, k=%d (BASELINE configs[%s])"
-                                   % (n_rows, DIM, args.data, nq, K, cfg_no),
-                       "recall_at_10": (cpu or {}).get("recall_at_10_on_sample", "exact by construction (unchecked: --no-cpu-baseline)"),
-                       "unresolved_queries": unresolved, "fallback_queries_e2e": counters.get("fallback_queries"),
-                       "engine": "tcgen05 bf16 scan + fp32 rescore" if tc else "fp32 CUDA-core scan",
-                       "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
-                       "l2": "inputs larger than L2: %.2f GB bf16 corpus per GPU streamed per step; %d query batches rotated" % (n_rows / world * DIM * 2 / 1e9, QUERY_BATCHES)},
-            "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4,
-                    "d2h_bytes_per_step": nq * K * 8},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -31,3 +31,17 @@ def test_total_keys_order_is_total_cmp():
     d = np.array([[-0.0, 0.0, 1.5, -2.0, np.inf]], np.float32)
     k = bench.total_keys(d, np.zeros_like(d, dtype=np.uint32))
     assert list(np.argsort(k[0])) == [3, 0, 1, 2, 4]
+
+
+def test_frontier_is_the_smallest_ef_that_meets_the_recall_gate():
+    per_ef = {"16": {"recall_at_10": 0.91}, "24": {"recall_at_10": 0.949}, "32": {"recall_at_10": 0.97},
+              "64": {"recall_at_10": 0.99}}
+    assert bench.frontier_ef(per_ef) == 32
+    assert bench.frontier_ef({"16": {"recall_at_10": 0.5}}) is None
+
+
+def test_both_arms_name_the_same_workload():
+    """The driver compares the `config.workload` strings of the two arms: the task is one string, engines differ."""
+    a = bench.workload_string(1_000_000, 768, "emb", 10_000, 10)
+    assert "1000000x768" in a and "recall@10>=0.95" in a and "configs[1 and 2]" in a
+    assert bench.workload_string(10_000_000, 768, "emb", 10_000, 10).endswith("configs[3])")
