@@ -406,8 +406,8 @@ def run_ours(args, rank, world, local_rank):
     def merged(ids, d, length):
         if world == 1:
             return ids, d
-        ig, dg = sharding.allgather_lists(ids, d)
-        return engine.merge_topk_cuda(ig, dg, length)
+        # one packed (distance, local handle) array per rank over NVLink, merged by (distance, global handle)
+        return engine.merge_topk_keys_cuda(sharding.allgather_keys(engine.pack_topk_cuda(ids, d)), length)
 
     def gather_queries(i):
         qh = q_host[i % QUERY_BATCHES]

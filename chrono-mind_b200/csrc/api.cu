@@ -21,6 +21,7 @@ static thread_local std::string tl_error;
 static thread_local cm_counters tl_counters;
 static thread_local bool tl_used_tc = false;  // the last exact search on this thread ran the tensor-core scan
 static thread_local uint32_t tl_scan_worst_chunk = 0;  // most queries one chunk of that search sent to the fallback
+static thread_local bool tl_scan_bounded = false;       // ... and that fallback was the bounded (kFlagCap) one
 static thread_local bool tl_force_fp32 = false;        // redo of a call whose tensor-core pool could not be completed
 static std::atomic<uint64_t> g_launches{0};
 
@@ -252,10 +253,15 @@ struct PreparedQueries {
   const float* qn = nullptr;
   uint32_t ld = 0;
   bool degenerate = false;
+  bool bf16_ready = false;  // ws->qbf16 already holds the scan-layout bf16 copy of ALL nq rows (fused K0)
 };
 
+// Would an exact search of k neighbors on this index take the tensor-core scan? (one predicate for the fused query
+// preparation and for exact_topk)
+static bool exact_uses_tc(const cm_index* idx, bool degenerate, uint32_t k);
+
 static cm_status prepare_queries(const cm_index* idx, Workspace* ws, const float* q_dev, uint32_t nq, uint32_t qdim,
-                                 uint32_t* bad_row, cudaStream_t s, PreparedQueries* out) {
+                                 uint32_t* bad_row, cudaStream_t s, PreparedQueries* out, bool want_bf16 = false) {
   const DeviceIndex& d = idx->dev;
   out->degenerate = qdim != d.dim;
   out->ld = d.dim_pad;
@@ -264,8 +270,16 @@ static cm_status prepare_queries(const cm_index* idx, Workspace* ws, const float
     return CM_OK;
   }
   CM_CUDA(ws->qn.ensure((size_t)std::max(nq, 1u) * d.dim_pad * sizeof(float)));
-  CM_CUDA(launch_preprocess_rows(q_dev, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
   out->qn = ws->qn.as<float>();
+  if (want_bf16 && nq && prepare_queries_fused_supported(q_dev, d.dim)) {
+    // one pass: normalise + bf16 copy in the scan layout (every 32,768-query chunk is a whole number of tile pairs)
+    const uint32_t nq_pad = scan_tc_pad_queries(nq);
+    CM_CUDA(ws->qbf16.ensure((size_t)nq_pad * d.k_pad * 2));
+    CM_CUDA(launch_prepare_queries(q_dev, nq, d.dim, ws->qn.as<float>(), d.dim_pad, ws->qbf16.p, nq_pad, d.k_pad, bad_row, s));
+    out->bf16_ready = true;
+    return CM_OK;
+  }
+  CM_CUDA(launch_preprocess_rows(q_dev, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
   return CM_OK;
 }
 
@@ -296,25 +310,38 @@ static cm_status exact_topk_fp32(const cm_index* idx, Workspace* ws, const float
 }
 
 // tcgen05 bf16 scan + exact fp32 rescore (+ in-stream fp32 fallback for flagged queries). See scan_tc.cu.
-static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t nq, uint32_t k,
-                               uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
+static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const PreparedQueries& pq, uint32_t q_off, uint32_t nq,
+                               uint32_t k, uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
   const DeviceIndex& d = idx->dev;
   const uint32_t nq_pad = scan_tc_pad_queries(nq);
   tl_used_tc = true;
-  CM_CUDA(ws->qbf16.ensure((size_t)nq_pad * d.k_pad * 2));
+  if (!pq.bf16_ready) CM_CUDA(ws->qbf16.ensure((size_t)nq_pad * d.k_pad * 2));
   CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
   const uint32_t cap = scan_tc_cand_cap(k);
   CM_CUDA(ws->cand.ensure((size_t)nq_pad * cap * 8));
   CM_CUDA(ws->small.ensure(kSmallBytes));
-  CM_CUDA(ws->qflag.ensure((size_t)kFlagCap * d.dim_pad * 4));
+  // Flagged queries (candidate overflow / too few survivors) are re-run through the exact fp32 scan in the same
+  // stream. Normal shapes: ONE cooperative launch that handles any number of them (returns at once when there are
+  // none). Rows too long for its 16-query tile: the chunked fp32 engine, bounded by kFlagCap per call.
+  const bool one_launch = (size_t)(d.dim & ~7u) * 16 * sizeof(float) <= 200 * 1024;
+  tl_scan_bounded = !one_launch;
+  const size_t qc_bytes = (fallback_exact_query_bytes(d.dim_pad) + 255) & ~(size_t)255;
+  if (one_launch)
+    CM_CUDA(ws->qflag.ensure(qc_bytes + (size_t)nq_pad * 4));
+  else
+    CM_CUDA(ws->qflag.ensure((size_t)kFlagCap * d.dim_pad * 4));
   uint32_t* tau_key = ws->tc_state.as<uint32_t>();
   uint32_t* cand_cnt = tau_key + nq_pad;
   uint8_t* small = ws->small.as<uint8_t>();
   CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
   CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));  // this chunk's counters
-  CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, nullptr, false, s));
+  const void* q_bf16 = ws->qbf16.p;
+  if (pq.bf16_ready)
+    q_bf16 = static_cast<const uint8_t*>(ws->qbf16.p) + (size_t)q_off * d.k_pad * 2;  // this chunk of the fused copy
+  else
+    CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, nullptr, false, s));
   ScanTcLaunch sl;
-  sl.q_bf16 = ws->qbf16.p;
+  sl.q_bf16 = q_bf16;
   sl.nq = nq;
   sl.k = k;
   sl.tau_key = tau_key;
@@ -338,17 +365,34 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   rl.dist = dist;
   rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
   rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
-  rl.flag_list = reinterpret_cast<uint32_t*>(small + 256);
-  rl.flag_cap = kFlagCap;
+  rl.flag_list = one_launch ? reinterpret_cast<uint32_t*>(ws->qflag.as<uint8_t>() + qc_bytes) : reinterpret_cast<uint32_t*>(small + 256);
+  rl.flag_cap = one_launch ? nq : kFlagCap;
   rl.approx = approx;
   CM_CUDA(launch_rescore(d, rl, s));
-  // Flagged queries (candidate overflow / too few survivors): exact fp32 scan, in stream, no host round trip.
-  CM_CUDA(launch_gather_rows(pq.qn, pq.ld, rl.flag_list, rl.flag_count, kFlagCap, ws->qflag.as<float>(), s));
-  cm_status st = exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
-                                 rl.flag_count, s);
-  if (st != CM_OK) return st;
-  CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, kFlagCap, d.status + 1, s));  // chunk counters -> call totals
+  if (one_launch) {
+    CM_CUDA(ws->D.ensure(fallback_exact_dist_bytes(d.n)));
+    CM_CUDA(launch_fallback_exact(pq.qn, pq.ld, rl.flag_list, rl.flag_count, ws->qflag.as<float>(), d.x32, d.n, d.dim, d.dim_pad,
+                                  ws->D.as<float>(), d.deleted, k, ids, dist, d.sm_count, s));
+  } else {
+    CM_CUDA(launch_gather_rows(pq.qn, pq.ld, rl.flag_list, rl.flag_count, kFlagCap, ws->qflag.as<float>(), s));
+    cm_status st = exact_topk_fp32(idx, ws, ws->qflag.as<float>(), pq.ld, false, kFlagCap, k, ids, dist, rl.flag_list,
+                                   rl.flag_count, s);
+    if (st != CM_OK) return st;
+  }
+  // chunk counters -> call totals; queries beyond what the fallback absorbed are counted in the status word
+  CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, one_launch ? 0xFFFFFFFFu : kFlagCap, d.status + 1, s));
   return CM_OK;
+}
+
+static bool exact_uses_tc(const cm_index* idx, bool degenerate, uint32_t k) {
+  const DeviceIndex& d = idx->dev;
+  // Rows with NaN/Inf components order by f32::total_cmp in the reference; the threshold select cannot
+  // reproduce that, so such an index always takes the fp32 scan.
+  const bool tc_ok = !degenerate && idx->all_finite && d.n > 0 && scan_tc_supported(d, k);
+  if (tl_force_fp32) return false;
+  // auto: the tensor-core scan wins from one query up once the corpus is a few thousand rows (1M rows, 1 query:
+  // ~0.7 ms against ~3 ms for the fp32 scan + select); tiny corpora stay on the fp32 engine.
+  return idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && d.n >= 8192);
 }
 
 // Exact top-`k` by (distance, handle) into ids/dist [nq][k] (device).
@@ -362,13 +406,8 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
     return CM_OK;
   }
   tl_counters.dist_evals += (uint64_t)nq * d.n;
-  // Rows with NaN/Inf components order by f32::total_cmp in the reference; the threshold select cannot
-  // reproduce that, so such an index always takes the fp32 scan.
   bool tc_ok = !pq.degenerate && idx->all_finite && scan_tc_supported(d, k);
-  // auto: the tensor-core scan wins from one query up once the corpus is a few thousand rows (1M rows, 1 query:
-  // ~0.7 ms against ~3 ms for the fp32 scan + select); tiny corpora stay on the fp32 engine.
-  bool use_tc = idx->exact_engine == 2 ? tc_ok : (idx->exact_engine == 0 && tc_ok && d.n >= 8192);
-  if (tl_force_fp32) use_tc = false;
+  const bool use_tc = exact_uses_tc(idx, pq.degenerate, k);
   if (!tl_force_fp32 && idx->exact_engine == 2 && !tc_ok && !pq.degenerate)
     return fail(CM_ERR_INVALID_ARGUMENT, "tensor-core scan needs k <= 128 and a corpus without NaN/Inf components");
   tl_counters.exact_engine = use_tc ? 2 : 1;
@@ -379,7 +418,7 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
       const uint32_t nb = std::min(kTcQueryChunk, nq - q0);
       PreparedQueries part = pq;
       part.qn = pq.qn + (size_t)q0 * pq.ld;
-      cm_status st = exact_topk_tc(idx, ws, part, nb, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, s, approx);
+      cm_status st = exact_topk_tc(idx, ws, part, q0, nb, k, ids + (size_t)q0 * k, dist + (size_t)q0 * k, s, approx);
       if (st != CM_OK) return st;
     }
     return CM_OK;
@@ -455,7 +494,7 @@ static cm_status strided_copy(void* dst, size_t dpitch, const void* src, size_t 
 static cm_status search_exact_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, uint32_t qdim,
                                        uint32_t k, uint32_t* ids, float* dist, cudaStream_t s, bool approx = false) {
   PreparedQueries pq;
-  cm_status st = prepare_queries(idx, ws, q, nq, qdim, nullptr, s, &pq);
+  cm_status st = prepare_queries(idx, ws, q, nq, qdim, nullptr, s, &pq, exact_uses_tc(idx, qdim != idx->dev.dim, k));
   if (st != CM_OK) return st;
   return exact_topk(idx, ws, pq, nq, k, ids, dist, s, approx);
 }
@@ -482,7 +521,7 @@ static cm_status search_temporal_dev_impl(const cm_index* idx, Workspace* ws, co
   if (ef64 > CM_MAX_K) return fail(CM_ERR_INVALID_ARGUMENT, "max(ef_search, 3k) exceeds CM_MAX_K");
   uint32_t ef = (uint32_t)ef64;
   PreparedQueries pq;
-  cm_status st = prepare_queries(idx, ws, q, nq, qdim, bad_row, s, &pq);
+  cm_status st = prepare_queries(idx, ws, q, nq, qdim, bad_row, s, &pq, exact && exact_uses_tc(idx, qdim != d.dim, ef));
   if (st != CM_OK) return st;
   if (exact) {
     CM_CUDA(ws->pool_ids.ensure((size_t)std::max(nq, 1u) * ef * 4));
@@ -1081,7 +1120,25 @@ cm_status cm_merge_topk_dev(const void* ids, const void* dist, uint32_t n_shards
     return fail(CM_ERR_INVALID_ARGUMENT, "bad merge arguments");
   if ((uint64_t)n_shards * len > 16384) return fail(CM_ERR_INVALID_ARGUMENT, "n_shards * len exceeds 16384");
   CM_CUDA(cudaSetDevice(device));
-  CM_CUDA(launch_merge_topk((const uint32_t*)ids, (const float*)dist, n_shards, nq, len, out_len, (uint32_t*)out_ids,
+  CM_CUDA(launch_merge_topk((const uint32_t*)ids, (const float*)dist, nullptr, n_shards, nq, len, out_len, (uint32_t*)out_ids,
+                            (float*)out_dist, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_pack_topk_dev(const void* ids, const void* dist, uint64_t count, void* out_keys, int device, void* stream) {
+  if (count && (!ids || !dist || !out_keys)) return fail(CM_ERR_INVALID_ARGUMENT, "null buffer");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_pack_topk((const uint32_t*)ids, (const float*)dist, count, (unsigned long long*)out_keys, (cudaStream_t)stream));
+  return CM_OK;
+}
+
+cm_status cm_merge_topk_keys_dev(const void* keys, uint32_t n_shards, uint32_t nq, uint32_t len, uint32_t out_len,
+                                 void* out_ids, void* out_dist, int device, void* stream) {
+  if (!keys || !out_ids || !out_dist || n_shards == 0 || len == 0 || out_len == 0)
+    return fail(CM_ERR_INVALID_ARGUMENT, "bad merge arguments");
+  if ((uint64_t)n_shards * len > 16384) return fail(CM_ERR_INVALID_ARGUMENT, "n_shards * len exceeds 16384");
+  CM_CUDA(cudaSetDevice(device));
+  CM_CUDA(launch_merge_topk(nullptr, nullptr, (const unsigned long long*)keys, n_shards, nq, len, out_len, (uint32_t*)out_ids,
                             (float*)out_dist, (cudaStream_t)stream));
   return CM_OK;
 }
@@ -1184,7 +1241,7 @@ static cm_status search_exact_host(const cm_index* idx, const float* q, uint32_t
   CM_CUDA(cudaStreamSynchronize(hc.s));
   if (tl_used_tc) {
     fetch_scan_counters(lease.ws);
-    if (tl_scan_worst_chunk > kFlagCap) {
+    if (tl_scan_bounded && tl_scan_worst_chunk > kFlagCap) {
       // More queries needed the fp32 fallback than the in-stream path absorbs: redo the batch on the fp32 engine.
       PreparedQueries pq;
       pq.qn = lease.ws->qn.as<float>();
@@ -1457,7 +1514,7 @@ cm_status cm_search_temporal(const cm_index* idx, const float* q, uint32_t nq, u
                 "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");
   if (exact && tl_used_tc) {
     fetch_scan_counters(lease.ws);
-    if (tl_scan_worst_chunk > kFlagCap) {
+    if (tl_scan_bounded && tl_scan_worst_chunk > kFlagCap) {
       // More pool queries needed the fp32 fallback than the in-stream path absorbs: redo the call on the fp32 engine.
       tl_counters = cm_counters();
       tl_force_fp32 = true;

@@ -15,6 +15,13 @@ void count_launch();  // bumps the process-wide and the thread-local launch coun
 cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, float* out,
                                    uint32_t ld_out, uint32_t* bad_row, cudaStream_t s);
 
+// K0 fused with the bf16 cast for query batches: out [n][ld_out] fp32 prepared rows (columns [dim, ld_out) zeroed) and
+// out16 [n_pad16][k_pad] bf16 (zero padded rows and columns) in one pass. Needs dim % 4 == 0, 16-byte aligned x and
+// rows short enough for 16 of them in shared memory (prepare_queries_fused_supported); x must not alias out.
+bool prepare_queries_fused_supported(const float* x, uint32_t dim);
+cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, float* out, uint32_t ld_out, void* out16,
+                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s);
+
 // fp32 -> bf16 copy of prepared rows into the tensor-core scan layout [n_pad][k_pad] (zero padded).
 // mask_rows (corpus copies): tombstoned rows (deleted[row] != 0) and padding rows score NaN in the scan.
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
@@ -72,8 +79,11 @@ cudaError_t launch_decay_sweep(float* importance, unsigned long long* decayed_th
                                cudaStream_t s);
 
 // K5 — shard merge (src/index/sharded_rwlock.rs:81-94).
-cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
-                              uint32_t out_len, uint32_t* out_ids, float* out_dist, cudaStream_t s);
+// Input either as (ids, dist) arrays or as `packed` keys (launch_pack_topk), [n_shards][nq][len] local handles.
+cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, const unsigned long long* packed, uint32_t n_shards,
+                              uint32_t nq, uint32_t len, uint32_t out_len, uint32_t* out_ids, float* out_dist,
+                              cudaStream_t s);
+cudaError_t launch_pack_topk(const uint32_t* ids, const float* dist, uint64_t n, unsigned long long* out, cudaStream_t s);
 
 // K4 — rerank tail of ChronoMind::search (src/store.rs:327-344, 395-415).
 cudaError_t launch_rerank(const uint32_t* pool_ids, const float* pool_dist, uint32_t nq, uint32_t pool, uint32_t k,
@@ -102,7 +112,17 @@ struct HnswLaunch {
 cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows);
 cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& a, cudaStream_t s);
 
-// Fallback plumbing of the tensor-core scan: copy the flagged queries' prepared rows into a compact matrix.
+// In-stream fp32 fallback of the tensor-core scan: one cooperative launch re-runs the *flag_count queries listed in
+// flag_list through the bit-exact scan + select and overwrites their rows of ids/dist [nq][k]; an immediate return
+// when nothing is flagged. qc: scratch of fallback_exact_query_bytes(ldq), D: scratch of fallback_exact_dist_bytes(n).
+size_t fallback_exact_dist_bytes(uint64_t n);
+size_t fallback_exact_query_bytes(uint32_t ldq);
+cudaError_t launch_fallback_exact(const float* qn, uint32_t ldq, const uint32_t* flag_list, const uint32_t* flag_count,
+                                  float* qc, const float* x, uint64_t n, uint32_t dim, uint32_t ldx, float* D,
+                                  const uint8_t* deleted, uint32_t k, uint32_t* ids, float* dist, int sm_count,
+                                  cudaStream_t s);
+
+// Copy the rows named by a device list into a compact matrix.
 cudaError_t launch_gather_rows(const float* src, uint32_t ld, const uint32_t* list, const uint32_t* count,
                                uint32_t cap, float* dst, cudaStream_t s);
 

@@ -3,6 +3,7 @@
 //
 // All of this is HBM/ALU work on CUDA cores (no GEMM shape is forced onto it); the tensor-core scan lives
 // in scan_tc.cu and the graph traversal in hnsw_search.cu.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -82,6 +83,117 @@ cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uin
   // In-place use is only safe when the strides match: a CTA reads all of its 32 rows (first loop) before any of
   // them is written (second loop, after a barrier), and no other CTA touches those rows.
   k_preprocess_rows<<<(unsigned)((n + 31) / 32), PP_THREADS, 0, s>>>(x, n, dim, ld_in, out, ld_out, bad_row);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0 for query batches, fused with the bf16 cast of the tensor-core scan: one pass over the queries instead of two
+// kernels (preprocess, then cast) that each stream them through HBM, and no per-tile barrier chain.
+// CTA = 16 rows. Each row (dim * 4 bytes, dim % 4 == 0) is landed whole in shared memory by ONE bulk copy
+// (cp.async.bulk, all 16 in flight at once); lane r then walks row r sequentially with LDS.128 — the reference's
+// scalar `map(|x| x * x).sum()` order, separately rounded multiply and add — and all 256 threads write the
+// normalised fp32 row and its bf16 copy (zero padded to the scan's [nq_pad][k_pad] layout). The row stride of
+// dim * 4 + 16 bytes puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t PQ_ROWS = 16;
+constexpr int PQ_THREADS = 256;
+
+__global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __restrict__ x, uint32_t n, uint32_t dim,
+                                                                float* __restrict__ out, uint32_t ld_out,
+                                                                __nv_bfloat16* __restrict__ out16, uint32_t n_pad16,
+                                                                uint32_t k_pad, uint32_t* bad_row) {
+  extern __shared__ __align__(128) unsigned char pq_smem[];  // PQ_ROWS x row_stride
+  __shared__ unsigned long long mbar;
+  __shared__ float norms[PQ_ROWS];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t row_bytes = dim * 4, row_stride = row_bytes + 16;
+  const uint32_t row0 = blockIdx.x * PQ_ROWS;
+  const uint32_t cnt = row0 < n ? min(PQ_ROWS, n - row0) : 0;  // blocks past n only zero the bf16 padding rows
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (cnt) {
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * row_bytes) : "memory");
+    if (tid < cnt) {
+      const float* src = x + (uint64_t)(row0 + tid) * dim;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(pq_smem + (size_t)tid * row_stride)), "l"(src), "r"(row_bytes), "r"(bar)
+          : "memory");
+    }
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+      if (spin > (1u << 24)) __trap();
+    }
+    if (tid < cnt) {  // sequential sum of squares, element order (src/metric.rs:209)
+      const float4* r4 = reinterpret_cast<const float4*>(pq_smem + (size_t)tid * row_stride);
+      float s = 0.0f;
+      for (uint32_t t = 0; t < dim / 4; ++t) {
+        const float4 v = r4[t];
+        s = __fadd_rn(s, __fmul_rn(v.x, v.x));
+        s = __fadd_rn(s, __fmul_rn(v.y, v.y));
+        s = __fadd_rn(s, __fmul_rn(v.z, v.z));
+        s = __fadd_rn(s, __fmul_rn(v.w, v.w));
+      }
+      norms[tid] = __fsqrt_rn(s);
+    }
+  }
+  __syncthreads();
+  // write phase: thread t handles element pairs (bf16x2 stores); 16 threads per row would under-use the CTA, so
+  // all 256 threads sweep the rows one after the other
+  const uint32_t pairs16 = k_pad / 2;
+  for (uint32_t r = 0; r < PQ_ROWS; ++r) {
+    const uint32_t row = row0 + r;
+    if (row >= n_pad16 && row >= n) break;
+    const bool live = r < cnt;
+    const float nr = live ? norms[r] : 0.0f;
+    const bool degenerate = nr <= 1.1920929e-7f;  // f32::EPSILON: left unchanged
+    const float* rs = reinterpret_cast<const float*>(pq_smem + (size_t)r * row_stride);
+    for (uint32_t p = tid; p < pairs16; p += PQ_THREADS) {
+      const uint32_t c = 2 * p;
+      float a = 0.0f, b = 0.0f;
+      if (live) {
+        if (c < dim) a = rs[c];
+        if (c + 1 < dim) b = rs[c + 1];
+        // validate_query (src/store.rs:386-390): remember the first row with a NaN/Inf component
+        if (bad_row && (!isfinite(a) || !isfinite(b))) atomicMin(bad_row, row);
+        if (!degenerate) {
+          if (c < dim) a = __fdiv_rn(a, nr);
+          if (c + 1 < dim) b = __fdiv_rn(b, nr);
+        }
+        if (c < ld_out) out[(uint64_t)row * ld_out + c] = a;
+        if (c + 1 < ld_out) out[(uint64_t)row * ld_out + c + 1] = b;
+      }
+      if (row < n_pad16) reinterpret_cast<__nv_bfloat162*>(out16)[(uint64_t)row * pairs16 + p] = __floats2bfloat162_rn(a, b);
+    }
+  }
+}
+
+bool prepare_queries_fused_supported(const float* x, uint32_t dim) {
+  return dim % 4 == 0 && dim >= 4 && (size_t)PQ_ROWS * (dim * 4 + 16) <= 200 * 1024 && ((uintptr_t)x & 15) == 0;
+}
+
+cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, float* out, uint32_t ld_out, void* out16,
+                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s) {
+  const uint32_t rows = n_pad16 > n ? n_pad16 : n;
+  if (rows == 0) return cudaSuccess;
+  const size_t smem = (size_t)PQ_ROWS * (dim * 4 + 16);
+  cudaError_t e = cudaFuncSetAttribute(k_prepare_queries, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  k_prepare_queries<<<(rows + PQ_ROWS - 1) / PQ_ROWS, PQ_THREADS, smem, s>>>(x, n, dim, out, ld_out, (__nv_bfloat16*)out16,
+                                                                             n_pad16, k_pad, bad_row);
   count_launch();
   return cudaGetLastError();
 }
@@ -213,34 +325,17 @@ __device__ __forceinline__ float combined_score_dev(float distance, unsigned lon
 constexpr int EX_QT = 16;   // queries per CTA; 8 or 4 for very long rows (the 16 x dim query tile must fit shared memory)
 constexpr int EX_ROWS = 256;
 
+// One block of EX_ROWS rows against the QT queries staged in `qs` ([body][QT], transposed): D[qq][row] for the live
+// (qq < nq) queries. `q` is the row-major query matrix the tile was staged from (scalar tail of rows with dim % 8 != 0).
 template <int QT>
-__global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
-                                                    const float* __restrict__ x, uint64_t n, uint32_t dim,
-                                                    uint32_t ldx, float* __restrict__ D, uint64_t ldD,
-                                                    const uint32_t* __restrict__ active_count,
-                                                    uint32_t active_base, ContextEpilogue ce) {
-  constexpr int EX_QT = QT;  // shadows the default inside the kernel
-  extern __shared__ __align__(16) float qs[];  // [body][QT]
-  if (active_count) {
-    uint32_t ac = *active_count;
-    ac = ac > active_base ? ac - active_base : 0;
-    if (blockIdx.y * EX_QT >= ac) return;
-    nq = min(nq, ac);
-  }
+__device__ __forceinline__ void exact_dist_rowblock(const float* __restrict__ qs, const float* __restrict__ q, uint32_t nq,
+                                                    uint32_t ldq, uint32_t q0, const float* __restrict__ x, uint64_t n,
+                                                    uint32_t dim, uint32_t ldx, float* __restrict__ D, uint64_t ldD,
+                                                    uint64_t rb, const ContextEpilogue& ce) {
+  constexpr int EX_QT = QT;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t j = lane & 7, rsub = lane >> 3;
   const uint32_t body = dim & ~7u;
-  const uint32_t q0 = blockIdx.y * EX_QT;
-
-  for (uint32_t idx = tid; idx < body * EX_QT; idx += 256) {
-    uint32_t e = idx / EX_QT, qi = idx % EX_QT;
-    uint32_t qq = q0 + qi;
-    qs[idx] = qq < nq ? q[(uint64_t)qq * ldq + e] : 0.0f;
-  }
-  __syncthreads();
-
-  const uint64_t n_row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
-  for (uint64_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
   const uint64_t row_base = rb * EX_ROWS;
   for (uint32_t pass = 0; pass < EX_ROWS / 32; ++pass) {
     uint64_t row = row_base + pass * 32 + warp * 4 + rsub;
@@ -294,7 +389,38 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q,
       }
     }
   }
+}
+
+// Stage queries [q0, q0 + QT) of `q` into qs[e][qi] (transposed; rows past nq are zero).
+template <int QT>
+__device__ __forceinline__ void exact_dist_stage_queries(float* qs, const float* __restrict__ q, uint32_t nq, uint32_t ldq,
+                                                         uint32_t q0, uint32_t body) {
+  for (uint32_t idx = threadIdx.x; idx < body * QT; idx += blockDim.x) {
+    uint32_t e = idx / QT, qi = idx % QT;
+    uint32_t qq = q0 + qi;
+    qs[idx] = qq < nq ? q[(uint64_t)qq * ldq + e] : 0.0f;
   }
+}
+
+template <int QT>
+__global__ void __launch_bounds__(256) k_exact_dist(const float* __restrict__ q, uint32_t nq, uint32_t ldq,
+                                                    const float* __restrict__ x, uint64_t n, uint32_t dim,
+                                                    uint32_t ldx, float* __restrict__ D, uint64_t ldD,
+                                                    const uint32_t* __restrict__ active_count,
+                                                    uint32_t active_base, ContextEpilogue ce) {
+  extern __shared__ __align__(16) float qs[];  // [body][QT]
+  if (active_count) {
+    uint32_t ac = *active_count;
+    ac = ac > active_base ? ac - active_base : 0;
+    if (blockIdx.y * QT >= ac) return;
+    nq = min(nq, ac);
+  }
+  const uint32_t q0 = blockIdx.y * QT;
+  exact_dist_stage_queries<QT>(qs, q, nq, ldq, q0, dim & ~7u);
+  __syncthreads();
+  const uint64_t n_row_blocks = (n + EX_ROWS - 1) / EX_ROWS;
+  for (uint64_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x)
+    exact_dist_rowblock<QT>(qs, q, nq, ldq, q0, x, n, dim, ldx, D, ldD, rb, ce);
 }
 
 cudaError_t launch_exact_dist(const float* q, uint32_t nq, uint32_t ldq, const float* x, uint64_t n, uint32_t dim,
@@ -471,6 +597,43 @@ __device__ __forceinline__ void select_flush(unsigned long long* keys, uint32_t 
   __syncthreads();
 }
 
+// The k smallest (distance, handle) of one row of D -> ids/dist[0..k). All SEL_THREADS threads of the CTA.
+__device__ __forceinline__ void select_row(const float* __restrict__ row, uint64_t n, const uint8_t* __restrict__ deleted,
+                                           uint32_t k, uint32_t kp, unsigned long long* keys, SelState* st,
+                                           uint32_t* __restrict__ ids, float* __restrict__ dist, int skip_inf) {
+  for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) keys[i] = kKeyMax;
+  if (threadIdx.x == 0) {
+    st->cnt = 0;
+    st->tau = kKeyMax;
+  }
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += SEL_STEP) {
+    unsigned long long tau = st->tau;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint64_t i = base + c * SEL_THREADS + threadIdx.x;
+      if (i < n) {
+        unsigned long long key = pack_key(row[i], (uint32_t)i);
+        if (key < tau && !(deleted && deleted[i]) && !(skip_inf && (uint32_t)(key >> 32) == 0xFF800000u)) {  // +inf
+          uint32_t slot = atomicAdd(&st->cnt, 1u);
+          keys[kp + slot] = key;
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t pending = st->cnt;  // read between two barriers: no thread is appending
+    __syncthreads();
+    if (pending > SEL_BUF - SEL_STEP) select_flush(keys, kp, k, st);
+  }
+  select_flush(keys, kp, k, st);
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    unsigned long long key = keys[i];
+    bool ok = key != kKeyMax;
+    ids[i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    dist[i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  }
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* __restrict__ D, uint64_t ldD, uint64_t n,
                                                                   const uint8_t* __restrict__ deleted, uint32_t k,
                                                                   uint32_t kp, uint32_t* __restrict__ ids,
@@ -482,38 +645,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_from_dist(const float* _
   __shared__ SelState st;
   if (active_count && active_base + blockIdx.x >= *active_count) return;
   const uint32_t out_row = qmap ? qmap[blockIdx.x] : blockIdx.x;
-  const float* row = D + (uint64_t)blockIdx.x * ldD;
-  for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) keys[i] = kKeyMax;
-  if (threadIdx.x == 0) {
-    st.cnt = 0;
-    st.tau = kKeyMax;
-  }
-  __syncthreads();
-  for (uint64_t base = 0; base < n; base += SEL_STEP) {
-    unsigned long long tau = st.tau;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint64_t i = base + c * SEL_THREADS + threadIdx.x;
-      if (i < n) {
-        unsigned long long key = pack_key(row[i], (uint32_t)i);
-        if (key < tau && !(deleted && deleted[i]) && !(skip_inf && (uint32_t)(key >> 32) == 0xFF800000u)) {  // +inf
-          uint32_t slot = atomicAdd(&st.cnt, 1u);
-          keys[kp + slot] = key;
-        }
-      }
-    }
-    __syncthreads();
-    uint32_t pending = st.cnt;  // read between two barriers: no thread is appending
-    __syncthreads();
-    if (pending > SEL_BUF - SEL_STEP) select_flush(keys, kp, k, &st);
-  }
-  select_flush(keys, kp, k, &st);
-  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-    unsigned long long key = keys[i];
-    bool ok = key != kKeyMax;
-    ids[(uint64_t)out_row * out_ld + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
-    dist[(uint64_t)out_row * out_ld + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
-  }
+  select_row(D + (uint64_t)blockIdx.x * ldD, n, deleted, k, kp, keys, &st, ids + (uint64_t)out_row * out_ld,
+             dist + (uint64_t)out_row * out_ld, skip_inf);
 }
 
 cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, uint64_t n, const uint8_t* deleted,
@@ -529,13 +662,111 @@ cudaError_t launch_select_from_dist(const float* D, uint64_t ldD, uint32_t nq, u
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// In-stream fp32 fallback of the tensor-core scan: ONE cooperative launch that re-runs every flagged query through
+// the bit-exact fp32 scan + select, however many there are, without a host round trip — and costs one empty launch
+// (a few microseconds) in the normal case of none. Per chunk of FB_QT flagged queries: gather their prepared rows,
+// all CTAs fill D[FB_QT][n] (row blocks grid-strided), grid barrier, one CTA per query selects its k smallest,
+// grid barrier.
+// ---------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int FB_QT = 16;
+
+struct FallbackArgs {
+  const float* qn;            // all prepared queries of the call [nq][ldq]
+  uint32_t ldq;
+  const uint32_t* flag_list;  // [*flag_count] query indices
+  const uint32_t* flag_count;
+  float* qc;                  // compact copy of one chunk's queries [FB_QT][ldq]
+  const float* x;
+  uint64_t n;
+  uint32_t dim, ldx;
+  float* D;                   // [FB_QT][ldD]
+  uint64_t ldD;
+  const uint8_t* deleted;
+  uint32_t k, kp;
+  uint32_t* ids;              // [nq][k] — rows of the flagged queries are overwritten
+  float* dist;
+};
+
+__global__ void __launch_bounds__(256) k_fallback_exact(FallbackArgs a) {
+  extern __shared__ __align__(16) unsigned char fb_smem[];  // max(query tile, select keys)
+  __shared__ SelState st;
+  const uint32_t fc = *a.flag_count;
+  if (fc == 0) return;  // uniform over the grid: nobody reaches a grid barrier
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t body = a.dim & ~7u;
+  const uint64_t n_row_blocks = (a.n + EX_ROWS - 1) / EX_ROWS;
+  const ContextEpilogue none{};
+  for (uint32_t c0 = 0; c0 < fc; c0 += FB_QT) {
+    const uint32_t nqc = min((uint32_t)FB_QT, fc - c0);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nqc * a.ldq; i += gridDim.x * blockDim.x)
+      a.qc[i] = a.qn[(uint64_t)a.flag_list[c0 + i / a.ldq] * a.ldq + i % a.ldq];
+    grid.sync();
+    float* qs = reinterpret_cast<float*>(fb_smem);
+    exact_dist_stage_queries<FB_QT>(qs, a.qc, nqc, a.ldq, 0, body);
+    __syncthreads();
+    for (uint64_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x)
+      exact_dist_rowblock<FB_QT>(qs, a.qc, nqc, a.ldq, 0, a.x, a.n, a.dim, a.ldx, a.D, a.ldD, rb, none);
+    grid.sync();
+    if (blockIdx.x < nqc) {
+      const uint32_t q = a.flag_list[c0 + blockIdx.x];
+      select_row(a.D + (uint64_t)blockIdx.x * a.ldD, a.n, a.deleted, a.k, a.kp,
+                 reinterpret_cast<unsigned long long*>(fb_smem), &st, a.ids + (uint64_t)q * a.k, a.dist + (uint64_t)q * a.k, 0);
+    }
+    grid.sync();
+  }
+}
+
+size_t fallback_exact_dist_bytes(uint64_t n) { return (size_t)FB_QT * ((n + 3) & ~3ull) * sizeof(float); }
+size_t fallback_exact_query_bytes(uint32_t ldq) { return (size_t)FB_QT * ldq * sizeof(float); }
+
+cudaError_t launch_fallback_exact(const float* qn, uint32_t ldq, const uint32_t* flag_list, const uint32_t* flag_count,
+                                  float* qc, const float* x, uint64_t n, uint32_t dim, uint32_t ldx, float* D,
+                                  const uint8_t* deleted, uint32_t k, uint32_t* ids, float* dist, int sm_count,
+                                  cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  FallbackArgs a;
+  a.qn = qn;
+  a.ldq = ldq;
+  a.flag_list = flag_list;
+  a.flag_count = flag_count;
+  a.qc = qc;
+  a.x = x;
+  a.n = n;
+  a.dim = dim;
+  a.ldx = ldx;
+  a.D = D;
+  a.ldD = (n + 3) & ~3ull;
+  a.deleted = deleted;
+  a.k = k;
+  a.kp = next_pow2(k < 32 ? 32 : k);
+  a.ids = ids;
+  a.dist = dist;
+  const size_t smem = std::max((size_t)(dim & ~7u) * FB_QT * sizeof(float),
+                               (size_t)next_pow2(a.kp + SEL_BUF) * sizeof(unsigned long long));
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;  // rows too long for a 16-query tile: the caller keeps the fp32 engine
+  cudaError_t e = cudaFuncSetAttribute(k_fallback_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fallback_exact, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)std::max(sm_count * std::min(per_sm, 2), FB_QT);  // every CTA co-resident (grid barrier)
+  if ((int)grid > sm_count * per_sm) return cudaErrorInvalidValue;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((void*)k_fallback_exact, dim3(grid), dim3(256), args, smem, s);
+  count_launch();
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K5 shard merge — ShardedRwLockHnsw::search's gather step (src/index/sharded_rwlock.rs:81-94): concat the
 // per-shard lists, sort by (distance, global handle), truncate. global = local * n_shards + shard.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_merge_topk(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
-                                                    uint32_t n_shards, uint32_t nq, uint32_t len, uint32_t out_len,
-                                                    uint32_t P, uint32_t* __restrict__ out_ids,
-                                                    float* __restrict__ out_dist) {
+                                                    const unsigned long long* __restrict__ packed, uint32_t n_shards,
+                                                    uint32_t nq, uint32_t len, uint32_t out_len, uint32_t P,
+                                                    uint32_t* __restrict__ out_ids, float* __restrict__ out_dist) {
   extern __shared__ __align__(16) unsigned long long keys[];  // P >= n_shards * len
   const uint32_t qi = blockIdx.x;
   const uint32_t total = n_shards * len;
@@ -544,8 +775,13 @@ __global__ void __launch_bounds__(256) k_merge_topk(const uint32_t* __restrict__
     if (i < total) {
       uint32_t sh = i / len, jj = i % len;
       uint64_t o = ((uint64_t)sh * nq + qi) * len + jj;
-      uint32_t local = ids[o];
-      if (local != CM_NO_ID_DEV) key = pack_key(dist[o], local * n_shards + sh);
+      if (packed) {  // (TotalF32 distance << 32 | local handle) as cm_pack_topk_dev leaves it; all-ones = padding
+        const unsigned long long pk = packed[o];
+        if (pk != kKeyMax) key = (pk & 0xFFFFFFFF00000000ull) | ((uint32_t)pk * n_shards + sh);
+      } else {
+        uint32_t local = ids[o];
+        if (local != CM_NO_ID_DEV) key = pack_key(dist[o], local * n_shards + sh);
+      }
     }
     keys[i] = key;
   }
@@ -558,8 +794,9 @@ __global__ void __launch_bounds__(256) k_merge_topk(const uint32_t* __restrict__
   }
 }
 
-cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
-                              uint32_t out_len, uint32_t* out_ids, float* out_dist, cudaStream_t s) {
+cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, const unsigned long long* packed, uint32_t n_shards,
+                              uint32_t nq, uint32_t len, uint32_t out_len, uint32_t* out_ids, float* out_dist,
+                              cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint32_t P = next_pow2(n_shards * len < 32 ? 32 : n_shards * len);
   size_t smem = (size_t)P * sizeof(unsigned long long);
@@ -568,7 +805,20 @@ cudaError_t launch_merge_topk(const uint32_t* ids, const float* dist, uint32_t n
     cudaError_t e = cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
   }
-  k_merge_topk<<<nq, 256, smem, s>>>(ids, dist, n_shards, nq, len, out_len, P, out_ids, out_dist);
+  k_merge_topk<<<nq, P >= 512 ? 256 : 64, smem, s>>>(ids, dist, packed, n_shards, nq, len, out_len, P, out_ids, out_dist);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// (distance, local handle) pairs -> one sortable u64 each, so that a sharded search exchanges ONE array per step.
+__global__ void k_pack_topk(const uint32_t* __restrict__ ids, const float* __restrict__ dist, uint64_t n,
+                            unsigned long long* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = ids[i] == CM_NO_ID_DEV ? kKeyMax : pack_key(dist[i], ids[i]);
+}
+cudaError_t launch_pack_topk(const uint32_t* ids, const float* dist, uint64_t n, unsigned long long* out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_pack_topk<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(ids, dist, n, out);
   count_launch();
   return cudaGetLastError();
 }

@@ -561,6 +561,7 @@ struct RescoreArgs {
   uint32_t approx;        // 1: emit the top-k by bf16 score (distance = 1 - score) without the exact rescore
   uint32_t rows;          // rows gathered per copy round, <= RS_ROWS
   float eps2;             // 2 * eps_for_dim(dim)
+  uint32_t region;        // bytes of the shared keys / row-buffer region (128-byte multiple)
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -572,9 +573,12 @@ struct RescoreArgs {
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   extern __shared__ __align__(128) unsigned char rs_smem[];
   const uint32_t row_stride = a.ldx * 4 + RG_ROW_PAD;
+  // The candidate keys are only needed until the rows to re-score are known, the row buffer only afterwards: they
+  // share one region (a barrier separates the last read of `keys` from the first bulk copy), which is what lets six
+  // queries instead of four be resident per SM.
   unsigned char* rowbuf = rs_smem;                                                       // [RS_ROWS][row_stride]
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rowbuf + (size_t)a.rows * row_stride);  // [rs_max] ~(score key, row)
-  unsigned long long* dkeys = keys + a.rs_max;                                           // [RS2_MAX] (distance, row)
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);             // [rs_max] ~(score key, row)
+  unsigned long long* dkeys = reinterpret_cast<unsigned long long*>(rs_smem + a.region);  // [RS2_MAX] (distance, row)
   uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);                         // [RS2_MAX] rows to re-score
   float* qs = reinterpret_cast<float*>(rows + RS2_MAX);                                  // [ldq]
   __shared__ unsigned long long mbar;
@@ -782,12 +786,13 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.approx = l.approx ? 1u : 0u;
   a.eps2 = 2.0f * eps_for_dim(ix.dim);
   const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
-  const size_t other = (size_t)a.rs_max * 8 + (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
-  // ~24 KB of row buffer (8 rows of 768 floats; a typical query re-scores ~15-30 rows = 2-4 rounds) keeps 4 CTAs per
-  // SM; the kernel is latency-bound per CTA, so queries in flight matter more than rounds.
+  const size_t other = (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
+  // ~24 KB of row buffer (8 rows of 768 floats; a typical query re-scores ~15-30 rows = 2-4 rounds): the kernel is
+  // latency-bound per CTA, so queries in flight per SM matter more than rounds.
   a.rows = std::min<uint32_t>(RS_ROWS, std::max<uint32_t>(4u, (uint32_t)((24u * 1024u + row_stride - 1) / row_stride)));
   while (a.rows > 1 && a.rows * row_stride + other > 200 * 1024) --a.rows;   // very long rows: fewer per round
-  const size_t smem = a.rows * row_stride + other;
+  a.region = (uint32_t)((std::max<size_t>(a.rows * row_stride, (size_t)a.rs_max * 8) + 127) & ~(size_t)127);
+  const size_t smem = a.region + other;
   {  // per device, so set on every launch (microseconds)
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;

@@ -97,6 +97,8 @@ ABI = {
     "cm_similar_pairs": (_i, [_vp, _f, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "cm_decay_sweep_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _f, _u64, _i, _vp]),
     "cm_merge_topk_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _i, _vp]),
+    "cm_pack_topk_dev": (_i, [_vp, _vp, _u64, _vp, _i, _vp]),
+    "cm_merge_topk_keys_dev": (_i, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _i, _vp]),
     "cm_rerank_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _f, _f, _u64, _u32, _vp, _vp, _vp, _i, _vp]),
     "cm_metric_preprocess_dev": (_i, [_vp, _u64, _u32, _vp, _i, _vp]),
     "cm_metric_distance_prepared_dev": (_i, [_vp, _vp, _u64, _u32, _vp, _i, _vp]),
@@ -475,6 +477,27 @@ def merge_topk_cuda(ids, dist, out_len: int):
     st = torch.cuda.current_stream(ids.device).cuda_stream
     _check(native().cm_merge_topk_dev(ids.data_ptr(), dist.data_ptr(), s_, nq, ln, out_len, oi.data_ptr(),
                                       od.data_ptr(), ids.device.index or 0, st))
+    return oi, od
+
+
+def pack_topk_cuda(ids, dist, out=None):
+    """(distance, local handle) lists -> sortable int64 keys of the same shape (one array to all-gather)."""
+    import torch
+    keys = out if out is not None else torch.empty(ids.shape, dtype=torch.int64, device=ids.device)
+    st = torch.cuda.current_stream(ids.device).cuda_stream
+    _check(native().cm_pack_topk_dev(ids.data_ptr(), dist.data_ptr(), ids.numel(), keys.data_ptr(), ids.device.index or 0, st))
+    return keys
+
+
+def merge_topk_keys_cuda(keys, out_len: int):
+    """Shard merge of all-gathered packed keys `[n_shards, nq, len]` -> ([nq, out_len] global handles, distances)."""
+    import torch
+    s_, nq, ln = keys.shape
+    oi = torch.empty((nq, out_len), dtype=torch.int32, device=keys.device)
+    od = torch.empty((nq, out_len), dtype=torch.float32, device=keys.device)
+    st = torch.cuda.current_stream(keys.device).cuda_stream
+    _check(native().cm_merge_topk_keys_dev(keys.data_ptr(), s_, nq, ln, out_len, oi.data_ptr(), od.data_ptr(),
+                                           keys.device.index or 0, st))
     return oi, od
 
 

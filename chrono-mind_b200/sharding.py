@@ -43,3 +43,14 @@ def allgather_lists(ids, dist, group=None):
     td.all_gather_into_tensor(ids_g, ids.contiguous(), group=group)
     td.all_gather_into_tensor(dist_g, dist.contiguous(), group=group)
     return ids_g.view((world,) + tuple(ids.shape)), dist_g.view((world,) + tuple(dist.shape))
+
+
+def allgather_keys(keys, group=None):
+    """All-gather packed (distance, local handle) keys (`engine.pack_topk_cuda`): `[nq, len]` int64 per rank ->
+    `[G, nq, len]`, shard-major. One collective per step instead of the two of `allgather_lists`."""
+    import torch
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    out = torch.empty((world * keys.shape[0],) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+    td.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    return out.view((world,) + tuple(keys.shape))

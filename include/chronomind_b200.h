@@ -253,6 +253,13 @@ cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset
 cm_status cm_merge_topk_dev(const void* ids, const void* dist, uint32_t n_shards, uint32_t nq, uint32_t len,
                             uint32_t out_len, void* out_ids, void* out_dist, int device, void* stream);
 
+/* The same merge over ONE exchanged array per step: cm_pack_topk_dev turns `count` (distance, local handle) pairs into
+ * sortable 64-bit keys ((TotalF32 distance << 32) | handle; all-ones for CM_NO_ID padding) and
+ * cm_merge_topk_keys_dev consumes the all-gathered keys [n_shards][nq][len]. One collective instead of two. */
+cm_status cm_pack_topk_dev(const void* ids, const void* dist, uint64_t count, void* out_keys, int device, void* stream);
+cm_status cm_merge_topk_keys_dev(const void* keys, uint32_t n_shards, uint32_t nq, uint32_t len, uint32_t out_len,
+                                 void* out_ids, void* out_dist, int device, void* stream);
+
 /* The rerank tail of `ChronoMind::search` (src/store.rs:327-344) on an already merged pool of GLOBAL handles
  * (multi-GPU: merge first, then rerank). Attribute arrays are device pointers indexed by global
  * handle. pool_ids/pool_dist: [nq][pool]; out: [nq][k]. */

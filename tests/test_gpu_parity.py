@@ -428,6 +428,13 @@ def test_shard_merge_equals_global_scan():
     assert np.array_equal(bits(md.cpu().numpy()), bits(gd))
     oi, od = oracle.sharded_merge(ids.cpu().numpy().view(np.uint32), ds.cpu().numpy(), k)
     assert np.array_equal(oi, gi) and np.array_equal(bits(od), bits(gd))
+    # the packed form (one exchanged array per step): same result, padding included
+    from chronomind_b200.engine import merge_topk_keys_cuda, pack_topk_cuda
+    ids[1, 3, 7:] = -1                                     # a short list: CM_NO_ID padding must survive the packing
+    ki, kd = merge_topk_keys_cuda(pack_topk_cuda(ids, ds), k)
+    mi2, md2 = merge_topk_cuda(ids, ds, k)
+    torch.cuda.synchronize()
+    assert torch.equal(ki, mi2) and np.array_equal(bits(kd.cpu().numpy()), bits(md2.cpu().numpy()))
 
 
 def test_sharded_store_search_is_merge_then_rerank():

@@ -32,6 +32,13 @@ def _worker(rank, world, port, n, nq, dim, k, out_dir):
         assert ids_g.shape == (world, nq, k)
         assert np.array_equal(ids_g[rank].numpy().view(np.uint32), li)       # rank r's list sits at index r
         mi, md = oracle.sharded_merge(ids_g.numpy().view(np.uint32), dist_g.numpy(), k)
+        # the one-collective form bench.py uses: packed (TotalF32 distance << 32 | local handle) keys
+        from bench import total_keys
+        keys = torch.from_numpy(total_keys(ld, li).view(np.int64))
+        kg = sharding.allgather_keys(keys).numpy().view(np.uint64)
+        assert kg.shape == (world, nq, k)
+        assert np.array_equal((kg & np.uint64(0xFFFFFFFF)).astype(np.uint32), ids_g.numpy().view(np.uint32))
+        assert np.array_equal(kg[rank], total_keys(ld, li))
         np.save(os.path.join(out_dir, "ids%d.npy" % rank), mi)
         np.save(os.path.join(out_dir, "dist%d.npy" % rank), md)
     finally:
