@@ -303,14 +303,19 @@ def run_reference(args, rank, world):
     truth, _, bf_secs = cpu_scan_streaming(gen, queries_all[:rs], K, threads, prepared_cache if n_rows * DIM * 4 <= 8e9 else None)
     brute_qps = rs / bf_secs
     log("[bench] brute force (ground truth) on %d queries: %.1f q/s (%.1fs)" % (rs, brute_qps, time.time() - t0))
+    # The traversal is deterministic and identical on CPU and GPU (same graph, same arithmetic), so recall at a given ef
+    # is ONE number for both arms; this arm can only afford a small truth sample, so the gate is applied with the
+    # sample's two-sigma allowance — in the reference's favour (a smaller ef is faster).
     sweep = {}
     ef_star = None
     for ef in ([args.ef] if args.ef else sorted({int(e) for e in args.efs.split(",")})):
         if ef < K:
             continue
         ids, _, _, _ = orc.search_batch(queries_all[:rs], ef, K, threads=threads)
-        sweep[str(ef)] = {"recall_at_10": recall_at_k(ids, truth)}
-        if ef_star is None and sweep[str(ef)]["recall_at_10"] >= 0.95:
+        per_q = np.array([len(set(a) & set(b)) / K for a, b in zip(ids.tolist(), truth.tolist())])
+        sigma = float(per_q.std(ddof=1) / np.sqrt(len(per_q))) if len(per_q) > 1 else 0.0
+        sweep[str(ef)] = {"recall_at_10": float(per_q.mean()), "stderr": sigma}
+        if ef_star is None and per_q.mean() + 2.0 * sigma >= 0.95:
             ef_star = ef
             break
     if ef_star is None:
@@ -332,8 +337,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(n_rows, DIM, args.data, nq, K),
-                   "engine": "CPU LockFreeHnsw::search (oracle port, AVX2+FMA), ef=%d = smallest ef with recall@10 >= 0.95, %d host threads"
-                             % (ef_star, threads),
+                   "engine": "CPU LockFreeHnsw::search (oracle port, AVX2+FMA), ef=%d = smallest ef whose recall@10 reaches 0.95 within "
+                             "two standard errors of the %d-query truth sample, %d host threads" % (ef_star, rs, threads),
                    "recall_at_10": rec, "ef": ef_star, "ef_sweep_recall": sweep,
                    "graph": how, "graph_build_s": build_s, "brute_force_qps": brute_qps,
                    "brute_force_note": "tests/recall_test.rs:70-79 linear scan, the reference's ground-truth helper (not its serving path)",
@@ -709,6 +714,82 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# =====================================================================================================================
+# --abi-group: the sharded path as ONE object behind the C ABI (cm_group_*), one process driving N devices
+# =====================================================================================================================
+def run_group(args):
+    """`python bench.py --gpus N --abi-group`: no torchrun, no torch.distributed — `cm_group_create(devices)` loads NCCL
+    inside the library, `cm_group_search_*` takes HOST buffers and returns merged global handles. Every number here is
+    end to end (H2D of the batch, sharded search, NCCL all-gather + merge, D2H inside the timed region)."""
+    import torch
+    from chronomind_b200 import datasets
+    from chronomind_b200.engine import ShardedChronoMindB200, default_config
+    G = args.gpus
+    if torch.cuda.device_count() < G:
+        raise SystemExit("--abi-group --gpus %d needs %d visible CUDA devices" % (G, G))
+    n_rows, nq = args.rows, args.queries
+    threads_all = os.cpu_count() or 1
+    shard, queries_all, gen = make_data(n_rows, nq * QUERY_BATCHES, args.data, 0, 1)
+    ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, NOW[0])
+    cfg = default_config(dimensions=DIM, ef_construction=args.efc)
+    t0 = time.time()
+    grp = ShardedChronoMindB200.from_matrix(list(range(G)), shard, cfg, ts_s, ts_n, decay)
+    want_hnsw = not args.no_hnsw and DIM == 768
+    build_s = None
+    if want_hnsw:
+        t1 = time.time()
+        grp.build_graphs(SEED, threads_all, gpu=args.build == "gpu")
+        build_s = time.time() - t1
+    grp.upload()
+    log("[bench] cm_group over %d device(s): %d rows resident in %.1fs (graphs %.1fs)" % (G, n_rows, time.time() - t0, build_s or 0.0))
+    q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory().numpy() for i in range(QUERY_BATCHES)]
+
+    def timed(fn, warmup, steps):
+        for i in range(warmup):
+            fn(i)
+        t1 = time.perf_counter()
+        out = None
+        for i in range(steps):
+            out = fn(warmup + i)
+        return time.perf_counter() - t1, out
+
+    secs, out = timed(lambda i: grp.search_exact(q_host[i % QUERY_BATCHES], K), args.warmup, args.steps)
+    last = (args.warmup + args.steps - 1) % QUERY_BATCHES
+    exact_qps = nq * args.steps / secs
+    parity = None
+    if not args.no_cpu_baseline:
+        sample = min(args.cpu_sample or 64, nq)
+        wi, wd, _ = cpu_scan_streaming(gen, queries_all[last * nq:last * nq + sample], K, threads_all)
+        parity = bool(np.array_equal(out[0][:sample], wi) and np.array_equal(out[1][:sample].view(np.uint32), wd.view(np.uint32)))
+    hn = None
+    if want_hnsw:
+        truth = out[0]
+        per_ef = {}
+        for ef in sorted({int(e) for e in args.efs.split(",")}):
+            if ef < K:
+                continue
+            s1, o1 = timed(lambda i, ef=ef: grp.search_index(q_host[last], ef, K), 1, 3)
+            s2, _ = timed(lambda i, ef=ef: grp.search(q_host[last], K, now=NOW, ef_search=ef, temporal_weight=TEMPORAL_W,
+                                                      base_decay_rate=BASE_DECAY), 1, 3)
+            per_ef[str(ef)] = {"ef": ef, "e2e_index_qps": nq * 3 / s1, "e2e_temporal_qps": nq * 3 / s2,
+                               "recall_at_10": recall_at_k(o1[0], truth)}
+            log("[bench] group hnsw ef=%d: %s" % (ef, json.dumps(per_ef[str(ef)])))
+        ef_star = frontier_ef(per_ef) or max(int(e) for e in per_ef)
+        hn = {"frontier": dict(per_ef[str(ef_star)], rule="smallest measured ef with recall@10 >= 0.95 against the exact scan"),
+              "per_ef": per_ef, "graph_build_s": build_s, "graph_build": args.build}
+    line = {"metric": METRIC, "value": exact_qps, "unit": "queries/s", "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_string(n_rows, DIM, args.data, nq, K),
+                       "engine": "cm_group_search_exact: tcgen05 bf16 scan + fp32 rescore per shard, NCCL all-gather + device merge inside the library",
+                       "parallelism": "cm_group: ONE process, %d device(s), one host thread + stream per device, ncclCommInitAll inside libchronomind_b200.so" % G,
+                       "parity_on_sample": parity, "timing": "host wall clock around the blocking C-ABI call (it synchronises before returning)"},
+            "e2e": {"value": exact_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
+            "gpu_launches": None, "hnsw": hn}
+    print(json.dumps(line), flush=True)
+    grp.close()
+
+
 def main():
     global DIM, K
     ap = argparse.ArgumentParser()
@@ -725,6 +806,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW block (graph build + ef sweep)")
     ap.add_argument("--no-graph-cache", action="store_true", help="neither read nor write the /tmp graph sidecar")
+    ap.add_argument("--abi-group", action="store_true",
+                    help="drive the N GPUs from ONE process through cm_group_* (NCCL inside the library) instead of torchrun ranks")
     ap.add_argument("--workload", default="exact", choices=["exact", "hnsw"],
                     help="which leg is the line's headline: exact (BASELINE configs[1], the metric's workload) or hnsw (configs[2])")
     ap.add_argument("--ef", type=int, default=0, help="hnsw: quote the headline at this ef instead of the recall frontier")
@@ -746,6 +829,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.abi_group:
+        run_group(args)
         return
     run_ours(args, rank, world, local_rank)
 

@@ -94,6 +94,19 @@ ABI = {
     "cm_search_hnsw_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_temporal_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp, _vp]),
     "cm_index_dev_status": (_i, [_vp, C.POINTER(_u64), _i]),
+    "cm_group_create": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "cm_group_free": (None, [_vp]),
+    "cm_group_from_matrix": (_i, [_vp, _vp, _u64, _u32, C.POINTER(Config)]),
+    "cm_group_set_attrs": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cm_group_build_graphs": (_i, [_vp, _u64, _i, _i]),
+    "cm_group_upload": (_i, [_vp]),
+    "cm_group_size": (_u32, [_vp]),
+    "cm_group_slots": (_u64, [_vp]),
+    "cm_group_len": (_u64, [_vp]),
+    "cm_group_shard": (_vp, [_vp, _u32]),
+    "cm_group_search_exact": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "cm_group_search_hnsw": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "cm_group_search_temporal": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp]),
     "cm_similar_pairs": (_i, [_vp, _f, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "cm_decay_sweep_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _f, _u64, _i, _vp]),
     "cm_merge_topk_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _i, _vp]),
@@ -465,6 +478,92 @@ class ChronoMindB200:
         _check(native().cm_search_temporal_dev(self._h, q.data_ptr(), nq, k, efs, w, base, now[0], now[1],
                                                1 if exact else 0, ids.data_ptr(), score.data_ptr(), dist.data_ptr(), s))
         return ids, score, dist
+
+
+class ShardedChronoMindB200:
+    """One store sharded by vector id over several GPUs of THIS process (`cm_group`): the read side of
+    `ShardedRwLockHnsw` (src/index/sharded_rwlock.rs:43-94) — one object, one call per batch, global handles."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(native().cm_group_create(C.cast(devs, C.c_void_p), len(devices), C.byref(h)))
+        self._h, self.devices, self.dim = h, list(devices), None
+
+    @classmethod
+    def from_matrix(cls, devices, x, config: Config | None = None, ts_secs=None, ts_nanos=None, decay_rate=None, deleted=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self = cls(devices)
+        cfg = config if config is not None else default_config(dimensions=x.shape[1])
+        _check(native().cm_group_from_matrix(self._h, _ptr(x), x.shape[0], x.shape[1], C.byref(cfg)))
+        self.dim, self._cfg = x.shape[1], cfg
+        if any(a is not None for a in (ts_secs, ts_nanos, decay_rate, deleted)):
+            arrs = [None if a is None else np.ascontiguousarray(a, dtype=dt)
+                    for a, dt in ((ts_secs, np.uint64), (ts_nanos, np.uint32), (decay_rate, np.float32), (deleted, np.uint8))]
+            _check(native().cm_group_set_attrs(self._h, *[_ptr(a) for a in arrs]))
+        return self
+
+    def build_graphs(self, layer_seed: int = 0x5EED, threads: int = 0, gpu: bool = True):
+        _check(native().cm_group_build_graphs(self._h, layer_seed & (2 ** 64 - 1), threads, 1 if gpu else 0))
+        return self
+
+    def upload(self):
+        _check(native().cm_group_upload(self._h))
+        return self
+
+    def shard(self, i: int) -> "ChronoMindB200":
+        """Borrowed view of shard i (owned by the group: never closed through this object)."""
+        view = ChronoMindB200(C.c_void_p(native().cm_group_shard(self._h, i)), self.devices[i])
+        view.close = lambda: None
+        return view
+
+    def __len__(self):
+        return int(native().cm_group_len(self._h))
+
+    @property
+    def slots(self) -> int:
+        return int(native().cm_group_slots(self._h))
+
+    def close(self):
+        if self._h:
+            native().cm_group_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search_exact(self, q, k: int):
+        q = ChronoMindB200._queries(q)
+        ids = np.empty((q.shape[0], k), dtype=np.uint32)
+        dist = np.empty((q.shape[0], k), dtype=np.float32)
+        _check(native().cm_group_search_exact(self._h, _ptr(q), q.shape[0], q.shape[1], k, _ptr(ids), _ptr(dist)))
+        return ids, dist
+
+    def search_index(self, q, ef: int, k: int | None = None):
+        q = ChronoMindB200._queries(q)
+        k = ef if k is None else k
+        ids = np.empty((q.shape[0], k), dtype=np.uint32)
+        dist = np.empty((q.shape[0], k), dtype=np.float32)
+        _check(native().cm_group_search_hnsw(self._h, _ptr(q), q.shape[0], q.shape[1], ef, k, _ptr(ids), _ptr(dist)))
+        return ids, dist
+
+    def search(self, q, k: int, now=None, exact: bool = False, ef_search=None, temporal_weight=None, base_decay_rate=None,
+               want_dist=False):
+        q = ChronoMindB200._queries(q)
+        cfg = self._cfg
+        efs = cfg.index.ef_search if ef_search is None else ef_search
+        w = cfg.temporal_weight if temporal_weight is None else temporal_weight
+        base = cfg.base_decay_rate if base_decay_rate is None else base_decay_rate
+        secs, nanos = _now() if now is None else now
+        ids = np.empty((q.shape[0], k), dtype=np.uint32)
+        score = np.empty((q.shape[0], k), dtype=np.float32)
+        dist = np.empty((q.shape[0], k), dtype=np.float32) if want_dist else None
+        _check(native().cm_group_search_temporal(self._h, _ptr(q), q.shape[0], q.shape[1], k, efs, w, base, secs, nanos,
+                                                 1 if exact else 0, _ptr(ids), _ptr(score), _ptr(dist)))
+        return (ids, score, dist) if want_dist else (ids, score)
 
 
 def merge_topk_cuda(ids, dist, out_len: int):

@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 typedef struct cm_index cm_index; /* opaque */
+typedef struct cm_group cm_group; /* opaque: one index sharded over several GPUs of this process */
 
 #define CM_NO_ID 0xFFFFFFFFu
 
@@ -267,6 +268,38 @@ cm_status cm_rerank_dev(const void* pool_ids, const void* pool_dist, uint32_t nq
                         const void* ts_secs, const void* ts_nanos, const void* decay_rate, float temporal_weight,
                         float base_decay_rate, uint64_t now_secs, uint32_t now_nanos, void* out_ids,
                         void* out_score, void* out_dist, int device, void* stream);
+
+/* ---- sharded search: ONE object over G GPUs of this process ------------------------------------------------------
+ * Replaces `ShardedRwLockHnsw` (src/index/sharded_rwlock.rs:43-94): rows are dealt out round-robin (shard = id mod G,
+ * local = id div G, :54-74), every shard is an independent index (its own HNSW sub-graph) resident on its own GPU,
+ * and a search is ONE call: each device copies 1/G of the batch over its own PCIe link and the slices are
+ * all-gathered over NVLink, every shard searches the whole batch, the per-shard lists are all-gathered (NCCL) and
+ * merged on the device by (distance, global handle) (:81-94); the store-level search reranks the MERGED pool
+ * (src/store.rs:323-344). Results carry GLOBAL handles. NCCL is loaded at cm_group_create (n_devices > 1); a missing or
+ * failing NCCL is CM_ERR_NCCL. One batch at a time per group (calls on one group serialise). */
+cm_status cm_group_create(const int* devices, int n_devices, cm_group** out);
+void cm_group_free(cm_group* g);
+/* `insert` loop of the sharded index: row i becomes global handle i (shard i mod G). Replaces any previous contents. */
+cm_status cm_group_from_matrix(cm_group* g, const float* x, uint64_t n, uint32_t dim, const cm_config* cfg);
+/* Attribute arrays indexed by GLOBAL handle (any pointer may be NULL); before cm_group_upload. */
+cm_status cm_group_set_attrs(cm_group* g, const uint64_t* ts_secs, const uint32_t* ts_nanos, const float* decay_rate,
+                             const uint8_t* deleted);
+/* One HNSW sub-graph per shard (seed + shard), all shards concurrently; gpu_assisted != 0 uses each shard's own GPU
+ * (cm_index_build_graph_gpu), else the host replay of `LockFreeHnsw::insert` with threads / G threads per shard. */
+cm_status cm_group_build_graphs(cm_group* g, uint64_t layer_seed, int threads, int gpu_assisted);
+cm_status cm_group_upload(cm_group* g);
+uint32_t cm_group_size(const cm_group* g);
+uint64_t cm_group_slots(const cm_group* g);
+uint64_t cm_group_len(const cm_group* g);
+cm_index* cm_group_shard(const cm_group* g, uint32_t shard); /* borrowed: introspection, sidecars */
+/* Same contracts as cm_search_exact / cm_search_hnsw / cm_search_temporal, host buffers, GLOBAL handles. */
+cm_status cm_group_search_exact(const cm_group* g, const float* q, uint32_t nq, uint32_t qdim, uint32_t k, uint32_t* ids,
+                                float* dist);
+cm_status cm_group_search_hnsw(const cm_group* g, const float* q, uint32_t nq, uint32_t qdim, uint32_t ef, uint32_t k,
+                               uint32_t* ids, float* dist);
+cm_status cm_group_search_temporal(const cm_group* g, const float* q, uint32_t nq, uint32_t qdim, uint32_t k,
+                                   uint32_t ef_search, float temporal_weight, float base_decay_rate, uint64_t now_secs,
+                                   uint32_t now_nanos, int exact, uint32_t* ids, float* score, float* dist);
 
 /* ---- maintenance passes over the same device-resident arrays ------------------------------- */
 /* The all-pairs test of `ChronoMind::consolidate` (src/store.rs:516-568: `metric.similarity(a.data, b.data) >

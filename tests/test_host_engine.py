@@ -339,3 +339,14 @@ def test_candidates_outside_their_layer_are_ignored():
             assert set(st.neighbors(int(h), layer).tolist()) <= inside
     with pytest.raises(CmError):
         st.build_graph_from_candidates(77, [np.full((len(m), 3), 600, np.uint32) for m in members])   # out of range
+
+
+def test_group_needs_cuda_devices():
+    """`cm_group_create` on a box without a CUDA device: a typed error, not a crash (and nothing falls back to the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from chronomind_b200.engine import ShardedChronoMindB200
+    with pytest.raises(CmError) as e:
+        ShardedChronoMindB200([0])
+    assert e.value.kind == "Cuda"
