@@ -725,6 +725,7 @@ def run_group(args):
     from chronomind_b200 import datasets
     from chronomind_b200.engine import ShardedChronoMindB200, default_config
     G = args.gpus
+    quiet_nccl_stdout()                       # the library loads NCCL: keep its banner off the JSON line
     if torch.cuda.device_count() < G:
         raise SystemExit("--abi-group --gpus %d needs %d visible CUDA devices" % (G, G))
     n_rows, nq = args.rows, args.queries

@@ -102,6 +102,7 @@ struct DevBuf {
 struct Workspace {
   DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable, qnorm, qctx;
   DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
+  DevBuf bias;                          // search_in_context: per-row temporal bias of the call
   cudaStream_t stream = nullptr;  // host-buffer variants
   cudaEvent_t done = nullptr;     // completion of the last call that used this workspace
   cudaStream_t last_stream = nullptr;
@@ -109,7 +110,7 @@ struct Workspace {
   unsigned hnsw_grid = 0;
   void release() {
     for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qnorm, &qctx, &qbf16,
-                      &tc_state, &cand, &qflag})
+                      &tc_state, &cand, &qflag, &bias})
       b->release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -536,6 +537,86 @@ static cm_status search_temporal_dev_impl(const cm_index* idx, Workspace* ws, co
   return CM_OK;
 }
 
+// ChronoMind::search_in_context on the tensor cores (scan_tc.cu): biased threshold scan of the bf16 rows restricted to
+// each query's context, then the reference's exact arithmetic on the stored rows of the few dozen candidates. Flagged
+// queries (candidate overflow) are counted; the host-buffer caller redoes the call on the fp32 scan.
+static cm_status search_in_context_tc(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq, const uint32_t* want,
+                                      uint32_t k, float w, float base, uint64_t now_secs, uint32_t now_nanos,
+                                      uint32_t* bad_row, uint32_t* ids, float* score, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  tl_used_tc = true;
+  tl_scan_bounded = true;  // no in-stream fallback here: any flagged query means "redo"
+  tl_counters.exact_engine = 2;
+  const uint32_t nq_pad_all = scan_tc_pad_queries(nq);
+  CM_CUDA(ws->qn.ensure((size_t)nq * d.dim_pad * sizeof(float)));
+  CM_CUDA(ws->qbf16.ensure((size_t)nq_pad_all * d.k_pad * 2));
+  if (prepare_queries_fused_supported(q, d.dim)) {
+    CM_CUDA(launch_prepare_queries(q, nq, d.dim, ws->qn.as<float>(), d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, bad_row, s));
+  } else {
+    CM_CUDA(launch_preprocess_rows(q, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
+    CM_CUDA(launch_to_bf16(ws->qn.as<float>(), nq, d.dim, d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, nullptr, false, s));
+  }
+  CM_CUDA(ws->qnorm.ensure((size_t)nq * 4));
+  CM_CUDA(launch_pair_dot(q, q, nq, d.dim, d.dim, ws->qnorm.as<float>(), s));
+  CM_CUDA(ws->bias.ensure(d.n_pad * sizeof(float)));
+  CM_CUDA(launch_context_bias(d, w, base, now_secs, now_nanos, ws->bias.as<float>(), s));
+  const uint32_t cap = scan_tc_cand_cap(k);
+  CM_CUDA(ws->small.ensure(kSmallBytes));
+  uint8_t* small = ws->small.as<uint8_t>();
+  CM_CUDA(cudaMemsetAsync(small + 80, 0, 16, s));  // call totals
+  for (uint32_t q0 = 0; q0 < nq; q0 += kTcQueryChunk) {
+    const uint32_t nb = std::min(kTcQueryChunk, nq - q0);
+    const uint32_t nq_pad = scan_tc_pad_queries(nb);
+    CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
+    CM_CUDA(ws->cand.ensure((size_t)nq_pad * cap * 8));
+    CM_CUDA(ws->qflag.ensure((size_t)nq_pad * 4));
+    uint32_t* tau_key = ws->tc_state.as<uint32_t>();
+    uint32_t* cand_cnt = tau_key + nq_pad;
+    CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
+    CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));
+    ScanTcLaunch sl;
+    sl.q_bf16 = static_cast<const uint8_t*>(ws->qbf16.p) + (size_t)q0 * d.k_pad * 2;
+    sl.nq = nb;
+    sl.k = k;
+    sl.tau_key = tau_key;
+    sl.cand_cnt = cand_cnt;
+    sl.cand = ws->cand.as<unsigned long long>();
+    sl.cap = cap;
+    sl.bias = ws->bias.as<float>();
+    sl.row_ctx = d.ctx;
+    sl.q_ctx = want + q0;
+    {
+      ProfileScope prof(s);
+      CM_CUDA(launch_scan_tc(d, sl, s));
+    }
+    ContextRescoreLaunch rl;
+    rl.q_raw = q + (size_t)q0 * d.dim;
+    rl.ldq = d.dim;
+    rl.nq = nb;
+    rl.k = k;
+    rl.qnorm2 = ws->qnorm.as<float>() + q0;
+    rl.w = w;
+    rl.base = base;
+    rl.now_secs = now_secs;
+    rl.now_nanos = now_nanos;
+    rl.tau_key = tau_key;
+    rl.cand_cnt = cand_cnt;
+    rl.cand = sl.cand;
+    rl.cap = cap;
+    rl.ids = ids + (size_t)q0 * k;
+    rl.score = score + (size_t)q0 * k;
+    rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
+    rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
+    rl.flag_list = ws->qflag.as<uint32_t>();
+    rl.flag_cap = nq_pad;
+    CM_CUDA(launch_rescore_context(d, rl, s));
+    // every flagged query is unresolved here; the host-buffer caller (bad_row != nullptr) reads the count and redoes
+    // the call, the asynchronous one reports through the status word
+    CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, 0, bad_row ? nullptr : d.status + 1, s));
+  }
+  return CM_OK;
+}
+
 // ChronoMind::search_in_context (src/store.rs:353-377): fp32 scan of the RAW rows with the context epilogue, then
 // the k smallest (score, handle). q: raw queries [nq][dim] (device), want: [nq] context ids (device).
 static cm_status search_in_context_dev_impl(const cm_index* idx, Workspace* ws, const float* q, uint32_t nq,
@@ -550,13 +631,17 @@ static cm_status search_in_context_dev_impl(const cm_index* idx, Workspace* ws, 
     CM_CUDA(launch_fill(score, (uint64_t)nq * k, INFINITY, s));
     return CM_OK;
   }
+  tl_counters.dist_evals += (uint64_t)nq * d.n;
+  // The tensor-core path needs 0 <= w < 1 (the bias scales with 1 / (1 - w)) and an index the scan accepts.
+  if (w >= 0.0f && w <= 0.999f && exact_uses_tc(idx, false, k))
+    return search_in_context_tc(idx, ws, q, nq, want, k, w, base, now_secs, now_nanos, bad_row, ids, score, s);
+  tl_counters.exact_engine = 1;
   if (bad_row) {  // validate_query's finiteness check (the normalised copy is scratch)
     CM_CUDA(ws->qn.ensure((size_t)nq * d.dim_pad * sizeof(float)));
     CM_CUDA(launch_preprocess_rows(q, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
   }
   CM_CUDA(ws->qnorm.ensure((size_t)nq * 4));
   CM_CUDA(launch_pair_dot(q, q, nq, d.dim, d.dim, ws->qnorm.as<float>(), s));
-  tl_counters.dist_evals += (uint64_t)nq * d.n;
   uint64_t ldD = (d.n + 3) & ~3ull;
   uint64_t qb = std::max<uint64_t>(16, (kDistWorkspaceBytes / (ldD * 4)) & ~15ull);
   qb = std::min<uint64_t>(qb, ((uint64_t)nq + 15) & ~15ull);
@@ -910,7 +995,9 @@ cm_status cm_index_upload(cm_index* idx, int device) {
                          cudaMemcpyHostToDevice));
     CM_CUDA(cudaMalloc(&d.norm2_raw, rows * 4));
     CM_CUDA(launch_pair_dot(d.xraw, d.xraw, n, d.dim, d.dim_pad, d.norm2_raw, nullptr));
-    CM_CUDA(cudaMalloc(&d.ctx, rows * 4));
+    // padded to the scan's tile height (the biased scan stages whole tiles of context ids); padding = CM_NO_ID
+    CM_CUDA(cudaMalloc(&d.ctx, scan_tc_pad_rows(rows) * 4));
+    CM_CUDA(cudaMemset(d.ctx, 0xFF, scan_tc_pad_rows(rows) * 4));
     CM_CUDA(cudaMemcpy(d.ctx, idx->ctx.data(), n * 4, cudaMemcpyHostToDevice));
   }
   // bf16 copy for the tensor-core scan, padded to whole tiles; tombstoned and padding rows are NaN-masked.
@@ -1556,6 +1643,7 @@ cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq,
   if (nq) CM_CUDA(cudaMemcpyAsync(lease.ws->qctx.p, context_ids, (size_t)nq * 4, cudaMemcpyHostToDevice, hc.s));
   uint32_t* bad_row = lease.ws->small.as<uint32_t>() + 48;  // offset 192
   CM_CUDA(cudaMemsetAsync(bad_row, 0xFF, 4, hc.s));
+  tl_used_tc = false;
   st = search_in_context_dev_impl(idx, lease.ws, hc.q_dev, nq, lease.ws->qctx.as<uint32_t>(), k, w, base, now_secs,
                                   now_nanos, bad_row, hc.ids_dev, hc.a_dev, hc.s);
   if (st != CM_OK) return st;
@@ -1570,6 +1658,25 @@ cm_status cm_search_in_context(const cm_index* idx, const float* q, uint32_t nq,
   if (bad != 0xFFFFFFFFu)
     return fail(CM_ERR_INVALID_VECTOR,
                 "invalid vector data: query contains NaN or infinite components (row " + std::to_string(bad) + ")");
+  if (tl_used_tc) {
+    fetch_scan_counters(lease.ws);
+    if (tl_counters.fallback_queries > 0) {
+      // Some query's candidate buffer overflowed on the tensor-core path: redo the call on the fp32 context scan.
+      const uint64_t flagged = tl_counters.fallback_queries;
+      tl_counters = cm_counters();
+      tl_counters.fallback_queries = flagged;
+      tl_force_fp32 = true;
+      st = search_in_context_dev_impl(idx, lease.ws, hc.q_dev, nq, lease.ws->qctx.as<uint32_t>(), k, w, base, now_secs,
+                                      now_nanos, nullptr, hc.ids_dev, hc.a_dev, hc.s);
+      tl_force_fp32 = false;
+      if (st != CM_OK) return st;
+      if (ob) {
+        CM_CUDA(cudaMemcpyAsync(ids, hc.ids_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+        CM_CUDA(cudaMemcpyAsync(score, hc.a_dev, ob, cudaMemcpyDeviceToHost, hc.s));
+      }
+      CM_CUDA(cudaStreamSynchronize(hc.s));
+    }
+  }
   return CM_OK;
 }
 

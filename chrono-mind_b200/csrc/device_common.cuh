@@ -41,6 +41,42 @@ __device__ __forceinline__ float octet_hsum(float v) {
   return v;
 }
 
+// Temporal half of combined_score (src/store.rs:395-415): w * (1 - exp(-rate * age_hours)), every operation rounded
+// like the reference's f32 code.
+__device__ __forceinline__ float temporal_term_dev(unsigned long long ts_secs, uint32_t ts_nanos, float decay_rate,
+                                                   unsigned long long now_secs, uint32_t now_nanos, float w,
+                                                   float base_decay_rate) {
+  // now.duration_since(ts).unwrap_or_default()
+  unsigned long long dsecs = 0;
+  uint32_t dnanos = 0;
+  bool later = (now_secs > ts_secs) || (now_secs == ts_secs && now_nanos >= ts_nanos);
+  if (later) {
+    dsecs = now_secs - ts_secs;
+    if (now_nanos >= ts_nanos) {
+      dnanos = now_nanos - ts_nanos;
+    } else {
+      dsecs -= 1;
+      dnanos = now_nanos + 1000000000u - ts_nanos;
+    }
+  }
+  // Duration::as_secs_f32 = secs as f32 + nanos as f32 / 1e9
+  float age_secs = __fadd_rn(__ull2float_rn(dsecs), __fdiv_rn(__uint2float_rn(dnanos), 1.0e9f));
+  float age_hours = __fdiv_rn(age_secs, 3600.0f);
+  float rate = decay_rate > 0.0f ? decay_rate : base_decay_rate;
+  // f32::exp: evaluated in double and rounded once (correctly rounded fp32 result).
+  float temporal_relevance = (float)exp((double)__fmul_rn(-rate, age_hours));
+  return __fmul_rn(w, __fsub_rn(1.0f, temporal_relevance));
+}
+
+// combined_score (src/store.rs:395-415), shared by the rerank (K4) and the context scans.
+__device__ __forceinline__ float combined_score_dev(float distance, unsigned long long ts_secs, uint32_t ts_nanos,
+                                                    float decay_rate, unsigned long long now_secs,
+                                                    uint32_t now_nanos, float w, float base_decay_rate) {
+  float geo = __fmul_rn(__fsub_rn(1.0f, w), __fdiv_rn(distance, 2.0f));
+  float tmp = temporal_term_dev(ts_secs, ts_nanos, decay_rate, now_secs, now_nanos, w, base_decay_rate);
+  return __fadd_rn(geo, tmp);
+}
+
 // Ascending bitonic sort of n (power of two) u64 keys in shared memory by all threads of the block.
 __device__ __forceinline__ void block_bitonic_sort(unsigned long long* s, uint32_t n) {
   for (uint32_t size = 2; size <= n; size <<= 1) {

@@ -18,6 +18,7 @@
 #include <nccl.h>  // types and enums only: every entry point is resolved at run time
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
@@ -215,6 +216,8 @@ struct SearchCall {
   uint32_t* ids;
   float* a;  // dist (Exact/Hnsw) or score (Temporal)
   float* b;  // Temporal: dist (optional)
+  bool validate = false;                       // store-level call: reject NaN/Inf queries
+  std::atomic<uint32_t>* bad_row = nullptr;   // smallest offending row over all slices (UINT32_MAX: none)
 };
 
 cm_status search_rank(cm_group* g, const SearchCall& c, int r, std::string* err) {
@@ -229,6 +232,19 @@ cm_status search_rank(cm_group* g, const SearchCall& c, int r, std::string* err)
   const size_t slice_bytes = (size_t)per * dim * 4;
   G_CUDA(d.q_slice.grow(slice_bytes));
   G_CUDA(d.q_all.grow(slice_bytes * G));
+  if (c.validate) {  // validate_query's finiteness check (src/store.rs:386-390) on this device's slice, all slices at once
+    for (uint32_t row = lo; row < hi; ++row) {
+      const float* v = c.q + (size_t)row * dim;
+      float acc = 0.0f;
+      for (uint32_t e = 0; e < dim; ++e) acc += v[e] * 0.0f;  // NaN/Inf poison the sum; vectorises
+      if (!(acc == 0.0f)) {
+        uint32_t seen = c.bad_row->load(std::memory_order_relaxed);
+        while (row < seen && !c.bad_row->compare_exchange_weak(seen, row, std::memory_order_relaxed)) {
+        }
+        break;
+      }
+    }
+  }
   if (hi > lo) G_CUDA(cudaMemcpyAsync(d.q_slice.p, c.q + (size_t)lo * dim, (size_t)(hi - lo) * dim * 4, cudaMemcpyHostToDevice, s));
   if (G > 1) G_NCCL(g_nccl.AllGather(d.q_slice.p, d.q_all.p, (size_t)per * dim, ncclFloat32, d.comm, s));
   const void* q_dev = G > 1 ? d.q_all.p : d.q_slice.p;
@@ -498,17 +514,17 @@ cm_status cm_group_search_temporal(const cm_group* g, const float* q, uint32_t n
   // validate_query (src/store.rs:379-392): dimensions first, then finiteness — the first bad row decides
   if (qdim != g->dim) return gfail(CM_ERR_INVALID_DIMENSIONS, "invalid dimensions: got " + std::to_string(qdim) + ", expected " + std::to_string(g->dim));
   if (nq && !q) return gfail(CM_ERR_INVALID_ARGUMENT, "null buffer");
-  for (uint32_t r = 0; r < nq; ++r) {
-    const float* v = q + (size_t)r * qdim;
-    float acc = 0.0f;
-    for (uint32_t e = 0; e < qdim; ++e) acc += v[e] * 0.0f;  // NaN/Inf poison the sum; vectorises
-    if (!(acc == 0.0f))
-      return gfail(CM_ERR_INVALID_VECTOR, "invalid vector data: query contains NaN or infinite components (row " + std::to_string(r) + ")");
-  }
   const uint64_t pool = std::max<uint64_t>(ef_search, (uint64_t)k * 3);  // OVERSAMPLE (src/store.rs:40,323)
   if (pool > CM_MAX_K) return gfail(CM_ERR_INVALID_ARGUMENT, "max(ef_search, 3k) exceeds CM_MAX_K");
   SearchCall c{Kind::Temporal, q, nq, k, (uint32_t)pool, (uint32_t)pool, exact, w, base, now_secs, now_nanos, ids, score, dist};
-  return group_search(g, c);
+  std::atomic<uint32_t> bad_row{0xFFFFFFFFu};
+  c.validate = true;
+  c.bad_row = &bad_row;
+  cm_status st = group_search(g, c);
+  if (bad_row.load() != 0xFFFFFFFFu)  // the whole call fails with the first bad row, as `search` would for that query
+    return gfail(CM_ERR_INVALID_VECTOR, "invalid vector data: query contains NaN or infinite components (row " +
+                                            std::to_string(bad_row.load()) + ")");
+  return st;
 }
 
 }  // extern "C"

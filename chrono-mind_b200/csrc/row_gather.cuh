@@ -62,8 +62,16 @@ __device__ __forceinline__ void rg_stage_rows(const float* x, uint32_t ldx, unsi
 // consecutive lanes); thread c of the quad carries the reference's SIMD lanes 2c, 2c+1, i.e. two FMA chains over
 // elements 8t+2c, 8t+2c+1. All four threads return the same bits. Must be called by whole quads (inactive quads
 // pass active = false and still take part in the shuffles).
+__device__ __forceinline__ float rg_quad_dot(const float* qs, const unsigned char* row, uint32_t dim, uint32_t c, bool active);
 __device__ __forceinline__ float rg_quad_distance(const float* qs, const unsigned char* row, uint32_t dim, uint32_t c,
                                                   bool active) {
+  return clamp02(__fsub_rn(1.0f, rg_quad_dot(qs, row, dim, c, active)));
+}
+
+// dot_avx2(row, q) (src/metric.rs:129-147) by one thread quad — also the `dot` accumulator of dot_and_norms_avx2
+// (:78-116: same FMA chain, same horizontal sum, same scalar tail). All four threads return the same bits.
+__device__ __forceinline__ float rg_quad_dot(const float* qs, const unsigned char* row, uint32_t dim, uint32_t c,
+                                             bool active) {
   const uint32_t body = dim & ~7u;
   const float* xr = reinterpret_cast<const float*>(row);
   float a0 = 0.0f, a1 = 0.0f;
@@ -88,7 +96,7 @@ __device__ __forceinline__ float rg_quad_distance(const float* qs, const unsigne
   float sum = __fadd_rn(t0, t1);
   if (active)
     for (uint32_t e = body; e < dim; ++e) sum = __fadd_rn(sum, __fmul_rn(xr[e], qs[e]));
-  return clamp02(__fsub_rn(1.0f, sum));
+  return sum;
 }
 
 }  // namespace cm

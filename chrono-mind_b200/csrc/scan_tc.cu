@@ -216,6 +216,11 @@ struct ScanArgs {
   unsigned long long* pairs;     // [pair_cap] (query << 32 | row)
   uint32_t* pair_count;          // pairs found (may exceed pair_cap: the caller retries with a larger buffer)
   uint32_t pair_cap;
+  // biased mode (kBiased instantiation, `search_in_context`): the ranking key of query q against row r is
+  // score + bias[r], and only rows with row_ctx[r] == q_ctx[q] take part
+  const float* bias;             // [n_pad]
+  const uint32_t* row_ctx;       // [n_pad]
+  const uint32_t* q_ctx;         // [nq]
 };
 
 // Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists [k][128] | barriers | tmem ptr.
@@ -257,6 +262,7 @@ struct LocalTopK {
   }
 };
 
+template <bool kBiased>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -265,6 +271,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   float* lists = reinterpret_cast<float*>(tiles + a.stages * kStageBytes);  // [k][128]
   ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(tiles + a.stages * kStageBytes + (size_t)a.k * 128 * 4);
+  // biased mode: the current tile's 256 row biases and context ids, one slot per accumulator stage
+  float* tile_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + ((sizeof(ScanSmemTail) + 15) & ~(size_t)15));
+  uint32_t* tile_ctx = reinterpret_cast<uint32_t*>(tile_bias + kAccStages * BN);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
@@ -382,6 +391,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (a.join) t0 = max(t0, m);  // self-join keeps row > query: tiles below the diagonal are skipped
       const uint32_t q = m * PAIR_M + rank * BM + row_in_cta;
       const bool q_valid = q < a.nq;
+      uint32_t my_ctx = CM_NO_ID_DEV;  // biased mode: CM_NO_ID matches no row
+      if (kBiased && q_valid) my_ctx = a.q_ctx[q];
       unsigned long long* my_cand = a.cand + (uint64_t)q * a.cap;
       // Per-unit state: the k best scores of this unit's rows, and a chunk of reserved candidate slots.
       top.filled = 0;
@@ -399,10 +410,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const float g = tk ? key_to_float(tk) : -INFINITY;
           tau = fmaxf(g, top.filled == top.k ? top.kth - a.eps2 : -INFINITY);
         }
+        const uint64_t row0 = (uint64_t)t * BN;
+        const float* tb = tile_bias + acc * BN;
+        const uint32_t* tcx = tile_ctx + acc * BN;
+        if (kBiased) {
+          // Stage this tile's per-row terms. The 4 epilogue warps meet at a named barrier per tile, so a slot is
+          // rewritten (two tiles later) only after every warp has finished reading it.
+          float* wb = tile_bias + acc * BN;
+          uint32_t* wc = tile_ctx + acc * BN;
+          wb[row_in_cta] = a.bias[row0 + row_in_cta];
+          wb[row_in_cta + 128] = a.bias[row0 + row_in_cta + 128];
+          wc[row_in_cta] = a.row_ctx[row0 + row_in_cta];
+          wc[row_in_cta + 128] = a.row_ctx[row0 + row_in_cta + 128];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(smem_u32(&tail->tmem_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * BN;
-        const uint64_t row0 = (uint64_t)t * BN;
         bool improved = false;
         // Cold start (no threshold yet): first build the running top-k from this tile WITHOUT emitting, so the
         // main pass below emits ~k rows instead of all 256. Tombstoned and padding rows score NaN (see
@@ -419,7 +443,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (cold) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float s = __uint_as_float(r[i]);
+                float s = __uint_as_float(r[i]);
+                if (kBiased) s = tcx[c + i] == my_ctx ? s + tb[c + i] : __int_as_float(0x7FC00000);
                 if (s == s) top.insert(s);
               }
             }
@@ -433,7 +458,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         }
         // Main pass, software pipelined: the next 32 columns are in flight while this chunk is filtered.
-        auto filter_chunk = [&](const uint32_t (&r)[32], uint32_t c) {
+        auto filter_chunk = [&](uint32_t (&r)[32], uint32_t c) {
+          if (kBiased) {  // ranking key = score + bias[row] (broadcast reads: every lane looks at the same rows)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + tb[c + i]);
+          }
           float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
           for (int i = 2; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));  // fmaxf drops NaN
@@ -444,6 +473,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             while (mask) {
               const uint32_t i = __ffs(mask) - 1;
               mask &= mask - 1;
+              if (kBiased && tcx[c + i] != my_ctx) continue;  // a row of another context
               const float s = pick32(r, i);
               if (s >= tau && a.join) {
                 const uint32_t row = (uint32_t)(row0 + c + i);
@@ -666,6 +696,145 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// `ChronoMind::search_in_context` (src/store.rs:353-377) on the tensor cores.
+//
+// The reference scores every live member r of the query's context with
+//   score = (1 - w) * distance(r, q) / 2 + w * (1 - exp(-rate_r * age_r))          (combined_score, :395-415)
+// and keeps the k smallest. With cos = 1 - distance:  score = (1 - w)/2 * (1 - (cos - c_r)),
+//   c_r = 2 w (1 - exp(-rate_r * age_r)) / (1 - w) >= 0,
+// so the k smallest scores are the k LARGEST cos - c_r: the exact scan's threshold select with a per-row additive
+// bias -c_r (k_context_bias, one pass over the attributes per call) and a membership test on the hits
+// (scan_tc_kernel<true>). The candidates are then decided by the reference's own arithmetic on the rows AS STORED
+// (rescore_context_kernel): dot_and_norms' dot chain, sqrt(na * nb), true division, clamp, combined_score — bit for
+// bit what the fp32 context scan computes, for a few dozen rows per query instead of all of them.
+// Fewer than k candidates is NOT an error here: a threshold only ever rises once k members of the context have been
+// seen, so a list shorter than k simply is the whole (live) context.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_context_bias(const unsigned long long* __restrict__ ts_secs, const uint32_t* __restrict__ ts_nanos,
+                               const float* __restrict__ decay, uint64_t n, uint64_t n_pad, float w, float base,
+                               unsigned long long now_secs, uint32_t now_nanos, float* __restrict__ bias) {
+  const float scale = __fdiv_rn(2.0f, __fsub_rn(1.0f, w));
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (uint64_t)gridDim.x * blockDim.x)
+    bias[i] = i < n ? -__fmul_rn(scale, temporal_term_dev(ts_secs[i], ts_nanos[i], decay[i], now_secs, now_nanos, w, base)) : 0.0f;
+}
+
+struct ContextRescoreArgs {
+  const float* q_raw;   // queries as given [nq][ldq]
+  uint32_t ldq, nq, k, dim, ldx;
+  const float* qnorm2;  // [nq] squared norms of the raw queries (dot chain)
+  const float* xraw;    // rows as stored [n][ldx]
+  const float* norm2_raw;
+  const unsigned long long* ts_secs;
+  const uint32_t* ts_nanos;
+  const float* decay;
+  float w, base;
+  unsigned long long now_secs;
+  uint32_t now_nanos;
+  const uint32_t* tau_key;
+  const uint32_t* cand_cnt;
+  const unsigned long long* cand;
+  uint32_t cap, rs_max, rows, region;
+  float eps2;
+  uint32_t* ids;
+  float* score;
+  uint32_t* flag_count;
+  uint32_t* flag_list;
+  uint32_t flag_cap;
+  unsigned long long* rescored_total;
+};
+
+__global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextRescoreArgs a) {
+  extern __shared__ __align__(128) unsigned char rs_smem[];
+  const uint32_t row_stride = a.ldx * 4 + RG_ROW_PAD;
+  unsigned char* rowbuf = rs_smem;                                                        // shares its region with keys
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);              // [rs_max] ~(biased score key, row)
+  unsigned long long* dkeys = reinterpret_cast<unsigned long long*>(rs_smem + a.region);  // [RS2_MAX] (score, row)
+  uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);
+  float* qs = reinterpret_cast<float*>(rows + RS2_MAX);
+  __shared__ unsigned long long mbar;
+  __shared__ uint32_t n_surv, n_keep;
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t cnt_raw = a.cand_cnt[q];
+  const uint32_t cnt = min(cnt_raw, a.cap);
+  const uint32_t tk = a.tau_key[q];
+  if (tid == 0) {
+    n_surv = 0, n_keep = 0;
+    rg_mbar_init(&mbar);
+  }
+  for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.q_raw[(uint64_t)q * a.ldq + e];
+  __syncthreads();
+  for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
+    const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
+    if (c != 0ull && (uint32_t)(c >> 32) >= tk) {
+      uint32_t slot = atomicAdd(&n_surv, 1u);
+      if (slot < a.rs_max) keys[slot] = ~c;
+    }
+  }
+  __syncthreads();
+  const uint32_t ns = n_surv;
+  bool bad = cnt_raw > a.cap || ns > a.rs_max;
+  uint32_t keep = 0;
+  if (!bad) {
+    const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
+    for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
+    block_bitonic_sort(keys, P);
+    uint32_t thr = 0;  // fewer than k candidates: the whole context, keep everything
+    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - a.eps2);
+    for (uint32_t i = tid; i < ns; i += RS_THREADS)
+      if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);
+    __syncthreads();
+    keep = n_keep;
+    bad = keep > RS2_MAX;
+  }
+  if (bad) {
+    if (tid == 0) {
+      uint32_t slot = atomicAdd(a.flag_count, 1u);
+      if (slot < a.flag_cap) a.flag_list[slot] = q;
+    }
+    for (uint32_t i = tid; i < a.k; i += RS_THREADS) {  // visibly invalid until the caller's fp32 redo replaces it
+      a.ids[(uint64_t)q * a.k + i] = CM_NO_ID_DEV;
+      a.score[(uint64_t)q * a.k + i] = __int_as_float(0x7FC00000);
+    }
+    return;
+  }
+  const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
+  for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
+  for (uint32_t i = tid; i < keep; i += RS_THREADS) rows[i] = (uint32_t)(~keys[i]);
+  __syncthreads();
+  const uint32_t r_slot = tid >> 2, c4 = tid & 3;
+  const float nb = a.qnorm2[q];
+  uint32_t phase = 0;
+  for (uint32_t r0 = 0; r0 < keep; r0 += a.rows) {
+    const uint32_t cntr = min(a.rows, keep - r0);
+    rg_stage_rows(a.xraw, a.ldx, &mbar, rowbuf, row_stride, rows + r0, cntr, phase);
+    const bool active = r_slot < cntr;
+    const float dot = rg_quad_dot(qs, rowbuf + (size_t)r_slot * row_stride, a.dim, c4, active);
+    if (active && c4 == 0) {
+      const uint32_t row = rows[r0 + r_slot];
+      // CosineDistance::distance on the stored rows (src/metric.rs:163-195)
+      const float denom = __fsqrt_rn(__fmul_rn(a.norm2_raw[row], nb));
+      float dist = 2.0f;  // zero vector: similarity undefined
+      if (!(denom <= 1.1920929e-7f)) {
+        float c = __fdiv_rn(dot, denom);
+        c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);  // f32::clamp: NaN passes through
+        dist = __fsub_rn(1.0f, c);
+      }
+      const float sc = combined_score_dev(dist, a.ts_secs[row], a.ts_nanos[row], a.decay[row], a.now_secs, a.now_nanos, a.w, a.base);
+      dkeys[r0 + r_slot] = pack_key(sc, row);
+    }
+    __syncthreads();
+  }
+  block_bitonic_sort(dkeys, P2);
+  for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
+    unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
+    bool ok = key != kKeyMax;
+    a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    a.score[(uint64_t)q * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  }
+  if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)keep);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -748,15 +917,20 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.pair_count = l.pair_count;
   a.pair_cap = l.pair_cap;
   if (l.join) a.splits = 1;  // units = query-tile pairs, each from its diagonal tile to the end
-  const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 16;
+  const bool biased = l.bias != nullptr;
+  a.bias = l.bias;
+  a.row_ctx = l.row_ctx;
+  a.q_ctx = l.q_ctx;
+  const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
   a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
   if (a.stages < 2) return cudaErrorInvalidValue;
   const size_t smem = fixed + (size_t)a.stages * kStageBytes;
-  cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+  auto kernel = biased ? scan_tc_kernel<true> : scan_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
   if (e != cudaSuccess) return e;
   const uint32_t units = a.m_pairs * a.splits;
   const unsigned grid = 2u * std::min(clusters, units);  // whole CTA pairs (__cluster_dims__(2,1,1))
-  scan_tc_kernel<<<grid, kThreads, smem, s>>>(map_q, map_x, a);
+  kernel<<<grid, kThreads, smem, s>>>(map_q, map_x, a);
   count_launch();
   return cudaGetLastError();
 }
@@ -799,6 +973,61 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   }
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   rescore_kernel<<<l.nq, RS_THREADS, smem, s>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_context_bias(const DeviceIndex& ix, float w, float base, uint64_t now_secs, uint32_t now_nanos, float* bias,
+                                cudaStream_t s) {
+  if (ix.n_pad == 0) return cudaSuccess;
+  k_context_bias<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(ix.ts_secs), ix.ts_nanos, ix.decay, ix.n,
+                                          ix.n_pad, w, base, now_secs, now_nanos, bias);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rescore_context(const DeviceIndex& ix, const ContextRescoreLaunch& l, cudaStream_t s) {
+  if (l.nq == 0) return cudaSuccess;
+  ContextRescoreArgs a;
+  a.q_raw = l.q_raw;
+  a.ldq = l.ldq;
+  a.nq = l.nq;
+  a.k = l.k;
+  a.dim = ix.dim;
+  a.ldx = ix.dim_pad;
+  a.qnorm2 = l.qnorm2;
+  a.xraw = ix.xraw;
+  a.norm2_raw = ix.norm2_raw;
+  a.ts_secs = reinterpret_cast<const unsigned long long*>(ix.ts_secs);
+  a.ts_nanos = ix.ts_nanos;
+  a.decay = ix.decay;
+  a.w = l.w;
+  a.base = l.base;
+  a.now_secs = l.now_secs;
+  a.now_nanos = l.now_nanos;
+  a.tau_key = l.tau_key;
+  a.cand_cnt = l.cand_cnt;
+  a.cand = l.cand;
+  a.cap = l.cap;
+  a.ids = l.ids;
+  a.score = l.score;
+  a.flag_count = l.flag_count;
+  a.flag_list = l.flag_list;
+  a.flag_cap = l.flag_cap;
+  a.rescored_total = l.rescored_total;
+  a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
+  // the stored rows are not unit length and the reference divides by fp32 norms: a little slack on top of the scan's bound
+  a.eps2 = 2.0f * (eps_for_dim(ix.dim) + 2e-5f);
+  const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
+  const size_t other = (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
+  a.rows = std::min<uint32_t>(RS_ROWS, std::max<uint32_t>(4u, (uint32_t)((24u * 1024u + row_stride - 1) / row_stride)));
+  while (a.rows > 1 && a.rows * row_stride + other > 200 * 1024) --a.rows;
+  a.region = (uint32_t)((std::max<size_t>(a.rows * row_stride, (size_t)a.rs_max * 8) + 127) & ~(size_t)127);
+  const size_t smem = a.region + other;
+  cudaError_t e = cudaFuncSetAttribute(rescore_context_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  rescore_context_kernel<<<l.nq, RS_THREADS, smem, s>>>(a);
   count_launch();
   return cudaGetLastError();
 }

@@ -27,6 +27,10 @@ struct ScanTcLaunch {
   unsigned long long* pairs = nullptr;
   uint32_t* pair_count = nullptr;  // zeroed by the caller
   uint32_t pair_cap = 0;
+  // biased mode (`search_in_context`): ranking key = score + bias[row], restricted to rows with row_ctx[row] == q_ctx[q]
+  const float* bias = nullptr;        // [pad_rows(n)]
+  const uint32_t* row_ctx = nullptr;  // [pad_rows(n)]
+  const uint32_t* q_ctx = nullptr;    // [nq]
 };
 cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s);
 
@@ -46,5 +50,29 @@ struct RescoreLaunch {
   bool approx = false;       // top-k by bf16 score, no exact rescore (graph-construction candidates)
 };
 cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaStream_t s);
+
+// `search_in_context` on the tensor cores (see scan_tc.cu): the per-row bias of one call, and the exact decision on the
+// stored rows.
+cudaError_t launch_context_bias(const DeviceIndex& ix, float w, float base, uint64_t now_secs, uint32_t now_nanos, float* bias,
+                                cudaStream_t s);
+struct ContextRescoreLaunch {
+  const float* q_raw;        // queries as given [nq][ldq]
+  uint32_t ldq, nq, k;
+  const float* qnorm2;       // [nq]
+  float w, base;
+  uint64_t now_secs;
+  uint32_t now_nanos;
+  const uint32_t* tau_key;
+  const uint32_t* cand_cnt;
+  const unsigned long long* cand;
+  uint32_t cap;
+  uint32_t* ids;             // [nq][k]
+  float* score;              // [nq][k]
+  uint32_t* flag_count;
+  uint32_t* flag_list;
+  uint32_t flag_cap;
+  unsigned long long* rescored_total;
+};
+cudaError_t launch_rescore_context(const DeviceIndex& ix, const ContextRescoreLaunch& l, cudaStream_t s);
 
 }  // namespace cm

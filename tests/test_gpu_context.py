@@ -56,6 +56,34 @@ def test_search_in_context_matches_oracle(n, nq, dim, k, w):
     assert np.all(np.diff(score, axis=1)[live[:, 1:]] >= 0)
 
 
+@pytest.mark.parametrize("n,nq,dim,k,w,n_ctx", [(20000, 300, 768, 10, 0.3, 4), (30000, 257, 128, 50, 0.7, 200), (12000, 64, 64, 10, 0.0, 3),
+                                                (50000, 600, 96, 20, 0.5, 1000), (9000, 70, 768, 100, 0.3, 2)])
+def test_search_in_context_tensor_core_engine_equals_fp32_engine_and_oracle(n, nq, dim, k, w, n_ctx):
+    """The tensor-core context path (biased threshold scan + exact decision on the stored rows) must return what the
+    fp32 context scan returns BIT FOR BIT — both end in the same arithmetic on the same rows, ordered by (score, handle)
+    — and that equals the oracle up to last-ulp expf ties."""
+    st, raw, ctx, dele, (ts_s, ts_n, dec) = _store(n, dim, n + k, n_ctx=n_ctx)
+    rng = np.random.default_rng(7)
+    q = (rng.normal(size=(nq, dim)) * 2.0).astype(np.float32)
+    q[5] = raw[11] * 3.0                                         # a stored direction: near-zero distances
+    want = rng.integers(0, n_ctx + 1, size=nq).astype(np.uint32)   # id n_ctx has no members
+    from chronomind_b200.engine import last_counters
+    ia, sa = st.set_exact_engine(2).search_in_context(want, q, k, now=NOW, temporal_weight=w, base_decay_rate=0.1)
+    ca = last_counters()
+    ib, sb = st.set_exact_engine(1).search_in_context(want, q, k, now=NOW, temporal_weight=w, base_decay_rate=0.1)
+    cb = last_counters()
+    assert ca["exact_engine"] == 2 and cb["exact_engine"] == 1 and ca["fallback_queries"] == 0
+    assert np.array_equal(ia, ib) and np.array_equal(bits(sa), bits(sb))
+    rc, wi, ws = oracle.search_in_context(raw, ctx, q, want, k, w, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1], deleted=dele, threads=8)
+    assert rc == 0
+    if w == 0.0:
+        assert np.array_equal(ia, wi) and np.array_equal(bits(sa), bits(ws))
+    else:
+        assert assert_order_matches_up_to_ties(ia, wi, sa, ws) <= 0.001 * ia.size
+    live = ia != NO_ID
+    assert np.all(ctx[ia[live]] == np.broadcast_to(want[:, None], ia.shape)[live]) and not dele[ia[live]].any()
+
+
 def test_search_in_context_errors_and_states():
     st, raw, ctx, dele, _ = _store(500, 8, 1)
     with pytest.raises(CmError) as e:
