@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <unordered_map>
 
@@ -103,6 +104,7 @@ struct Workspace {
   DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable, qnorm, qctx;
   DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
   DevBuf bias;                          // search_in_context: per-row temporal bias of the call
+  DevBuf vmap, vmap_epoch;              // HNSW at large ef: visited byte maps in HBM (one slab per CTA) and their epochs
   cudaStream_t stream = nullptr;  // host-buffer variants
   cudaEvent_t done = nullptr;     // completion of the last call that used this workspace
   cudaStream_t last_stream = nullptr;
@@ -110,7 +112,7 @@ struct Workspace {
   unsigned hnsw_grid = 0;
   void release() {
     for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qnorm, &qctx, &qbf16,
-                      &tc_state, &cand, &qflag, &bias})
+                      &tc_state, &cand, &qflag, &bias, &vmap, &vmap_epoch})
       b->release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -440,13 +442,28 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
     CM_CUDA(launch_fill(ws->pool_dist.as<float>(), (uint64_t)nq * ef, INFINITY, s));
     return CM_OK;
   }
-  uint32_t hb = visited_entries_for(ef);
+  // visited set: shared-memory hash table for small ef, one byte per node per CTA in HBM from ef = 96 up, where the
+  // table (30 * ef entries) would be what limits the queries in flight per SM. CM_HNSW_VMAP=0/1 forces either.
+  bool use_vmap = ef >= 96;
+  if (const char* env = getenv("CM_HNSW_VMAP")) use_vmap = atoi(env) != 0;
+  uint32_t hb = use_vmap ? 0 : visited_entries_for(ef);
   unsigned grid = 0;
   uint32_t rows = 0;
   cudaError_t ge = hnsw_grid_size(d, ef, hb, &grid, &rows);
   if (ge != cudaSuccess) return fail(CM_ERR_INVALID_ARGUMENT, "ef / dim too large for the HNSW kernel's shared memory");
   CM_CUDA(ws->small.ensure(kSmallBytes));
-  CM_CUDA(ws->gtable.ensure(((size_t)grid << kGHashBits) * 4));
+  const uint64_t vstride = (d.n + 15) & ~15ull;
+  if (use_vmap) {
+    const size_t need = (size_t)grid * vstride;
+    if (need > ws->vmap.cap || (size_t)grid * 4 > ws->vmap_epoch.cap) {  // fresh slabs start at epoch 0, all zero
+      CM_CUDA(ws->vmap.ensure(need));
+      CM_CUDA(ws->vmap_epoch.ensure((size_t)grid * 4));
+      CM_CUDA(cudaMemsetAsync(ws->vmap.p, 0, ws->vmap.cap, s));
+      CM_CUDA(cudaMemsetAsync(ws->vmap_epoch.p, 0, ws->vmap_epoch.cap, s));
+    }
+  } else {
+    CM_CUDA(ws->gtable.ensure(((size_t)grid << kGHashBits) * 4));
+  }
   CM_CUDA(cudaMemsetAsync(ws->small.p, 0, 160, s));  // counters + work counter (bad_row at 192 is the caller's)
   HnswLaunch l;
   l.q = pq.qn;
@@ -464,6 +481,11 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
   l.grid = grid;
   l.rows = rows;
   l.status = d.status;
+  if (use_vmap) {
+    l.vmap = ws->vmap.as<unsigned char>();
+    l.vmap_stride = vstride;
+    l.vmap_epoch = ws->vmap_epoch.as<uint32_t>();
+  }
   {
     ProfileScope prof(s);
     CM_CUDA(launch_hnsw_search(d, l, s));

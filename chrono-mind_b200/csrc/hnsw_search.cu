@@ -21,6 +21,10 @@
 //   * `visited` (HashSet<u32>) is an open-addressing table in shared memory, tagged with an 8-bit epoch so it
 //     never has to be cleared between layers or queries. Membership is exact. When a query would crowd the
 //     table past 3/4 the CTA restarts that query on a larger per-CTA table in global memory.
+//     At large ef that table is the biggest shared-memory consumer (30 * ef entries) and caps the queries in flight
+//     per SM, so from ef = 96 up `visited` moves to HBM instead: one BYTE per node per resident CTA, holding the epoch
+//     of the search that last visited the node (a plain load + store per neighbor — the lanes of warp 0 look at
+//     distinct nodes; 32 scattered sectors per expansion, ~2 % of the row bytes, and no capacity limit at all).
 //   * the fresh neighbors' rows are GATHERED BY THE COPY ENGINE: one `cp.async.bulk` (UBLKCP) per row, issued by
 //     one thread each, lands the whole dim*4-byte row in shared memory and signals an mbarrier — all rows of a
 //     round (up to HN_ROWS x 3 KB) are in flight at once and cost no registers. (A register-staged gather keeps
@@ -69,6 +73,9 @@ struct HnswKernelArgs {
   uint32_t ghash_bits;
   uint32_t rows;           // rows staged per round, <= HN_ROWS
   uint32_t* status;        // optional: bumped once per query that could not be answered like the reference
+  unsigned char* vmap;     // visited byte maps in HBM, one slab of vmap_stride bytes per CTA (nullptr: shared-memory table)
+  uint64_t vmap_stride;
+  uint32_t* vmap_epoch;    // [gridDim.x] epoch each CTA's slab was last written with (persists across launches)
 };
 
 struct HnShared {
@@ -95,6 +102,7 @@ struct HnShared {
 struct VisitedTable {
   uint32_t* slots;
   uint32_t size;  // entries (not necessarily a power of two: shared memory is what limits the CTAs per SM)
+  unsigned char* bytes;  // byte-map mode (HBM): bytes[id] == epoch <=> visited in this search_layer call
 };
 
 __device__ __forceinline__ uint32_t key_handle(unsigned long long key) { return ((uint32_t)key) >> 1; }
@@ -105,6 +113,12 @@ __device__ __forceinline__ unsigned long long make_key(float d, uint32_t id) {
 // HashSet::insert — true when `id` was not present. Called by the lanes of warp 0 concurrently. The caller
 // keeps the load below 3/4, so the probe always ends.
 __device__ __forceinline__ bool visited_insert(const VisitedTable& t, uint32_t tag, uint32_t id) {
+  if (t.bytes) {  // concurrent lanes hold distinct ids (a neighbor list has no duplicates): plain load + store
+    const unsigned char e = (unsigned char)(tag >> 24);
+    if (t.bytes[id] == e) return false;
+    t.bytes[id] = e;
+    return true;
+  }
   uint32_t want = tag | id;
   uint32_t h = __umulhi(id * 2654435761u, t.size);  // multiply-shift range reduction: [0, size)
   for (;;) {
@@ -127,11 +141,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const float* qs, unsigned long long* lists,
                                 uint32_t ef_cap, const VisitedTable& vt, uint32_t ef, uint32_t layer, uint32_t ep,
                                 unsigned char* rowbuf, uint32_t row_stride, uint32_t& phase) {
+  const uint64_t vt_bytes_len = a.vmap_stride;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
   const uint32_t cap = layer == 0 ? a.cap0 : a.capU;
   const uint32_t table_size = vt.size;
-  const uint32_t limit = (table_size >> 1) + (table_size >> 2);
+  const uint32_t limit = vt.bytes ? 0xFFFFFFFFu - 64u : (table_size >> 1) + (table_size >> 2);  // the byte map never fills
   int buf = 0;
 
   // A fresh visited set per call (:148): bump the epoch; clear the table when the 8-bit tag wraps.
@@ -142,7 +157,12 @@ __device__ int search_layer_dev(const HnswKernelArgs& a, HnShared* sh, const flo
   }
   __syncthreads();
   if (sh->epoch == 256) {
-    for (uint32_t i = tid; i < table_size; i += blockDim.x) vt.slots[i] = 0;
+    if (vt.bytes) {
+      uint4* w = reinterpret_cast<uint4*>(vt.bytes);
+      for (uint64_t i = tid; i < vt_bytes_len / 16; i += blockDim.x) w[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (uint32_t i = tid; i < table_size; i += blockDim.x) vt.slots[i] = 0;
+    }
     __syncthreads();
     if (tid == 0) sh->epoch = 1;
     __syncthreads();
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   const uint32_t tid = threadIdx.x;
   for (uint32_t i = tid; i < a.table_entries; i += blockDim.x) stable[i] = 0;
   if (tid == 0) {
-    sh->epoch = 0;
+    sh->epoch = a.vmap ? a.vmap_epoch[blockIdx.x] : 0;  // the byte map outlives the launch: so does its epoch
     sh->ctr_evals = sh->ctr_exp = sh->ctr_entries = sh->ctr_replays = 0;
     sh->limbo_count = sh->limbo_lost = 0;
     rg_mbar_init(&sh->mbar);
@@ -389,7 +409,12 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
     int b = 0;
     for (;;) {
       VisitedTable vt;
-      if (use_global) {
+      vt.bytes = nullptr;
+      if (a.vmap) {
+        vt.bytes = a.vmap + (size_t)blockIdx.x * a.vmap_stride;
+        vt.slots = nullptr;
+        vt.size = 0;
+      } else if (use_global) {
         vt.slots = a.gtable + ((size_t)blockIdx.x << a.ghash_bits);
         vt.size = 1u << a.ghash_bits;
         for (uint32_t i = tid; i < vt.size; i += blockDim.x) vt.slots[i] = 0;
@@ -449,6 +474,7 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
     }
     __syncthreads();
   }
+  if (tid == 0 && a.vmap) a.vmap_epoch[blockIdx.x] = sh->epoch;
   if (tid == 0 && a.counters) {
     atomicAdd(&a.counters[0], sh->ctr_evals);
     atomicAdd(&a.counters[1], sh->ctr_exp);
@@ -464,7 +490,13 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
 // Threads per CTA: the row distances need only 4 lanes per staged row, the rest of the CTA speeds up the list merge,
 // the table clears and the pop scan, which grow with ef. Measured (1M x 768, ms per 10k batch, 64/128/256 threads):
 // ef=64 7.58/7.11/7.18, ef=128 16.34/15.74/15.18, ef=200 26.32/23.99/23.62.
-static int hnsw_threads_for(uint32_t ef) { return ef <= 96 ? 128 : HN_THREADS; }
+static int hnsw_threads_for(uint32_t ef) {
+  if (const char* env = getenv("CM_HNSW_THREADS")) {  // experiments only
+    const int t = atoi(env);
+    if (t == 64 || t == 128 || t == 256) return t;
+  }
+  return ef <= 96 ? 128 : HN_THREADS;
+}
 
 static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t table_entries, uint32_t rows) {
   const size_t dim_pad = (dim + 7) & ~7u;
@@ -535,6 +567,9 @@ cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& l, cudaS
   a.ghash_bits = l.ghash_bits;
   a.rows = l.rows;
   a.status = l.status;
+  a.vmap = l.vmap;
+  a.vmap_stride = l.vmap_stride;
+  a.vmap_epoch = l.vmap_epoch;
   cudaError_t e = cudaMemsetAsync(l.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned grid = l.grid < l.nq ? l.grid : l.nq;

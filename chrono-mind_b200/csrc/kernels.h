@@ -108,6 +108,11 @@ struct HnswLaunch {
   unsigned grid;             // from hnsw_grid_size()
   uint32_t rows;             // rows staged per copy round, from hnsw_grid_size()
   uint32_t* status = nullptr;  // optional device word bumped once per query that could not be answered exactly
+  // visited set in HBM (large ef): one slab of vmap_stride bytes (>= rows, multiple of 16) per CTA of `grid`, zeroed when
+  // allocated, plus the per-CTA epoch words (zeroed with it). table_entries must be 0 then.
+  unsigned char* vmap = nullptr;
+  uint64_t vmap_stride = 0;
+  uint32_t* vmap_epoch = nullptr;
 };
 cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows);
 cudaError_t launch_hnsw_search(const DeviceIndex& ix, const HnswLaunch& a, cudaStream_t s);
