@@ -951,9 +951,30 @@ cm_status cm_index_remove(cm_index* idx, uint32_t handle, int* removed) {
   if (handle < idx->n && !idx->deleted[handle]) {
     idx->deleted[handle] = 1;
     idx->live--;
+    if (idx->uploaded) idx->pending_removed.push_back(handle);  // reaches the device at cm_index_sync_deleted / upload
     r = 1;
   }
   if (removed) *removed = r;
+  return CM_OK;
+}
+
+cm_status cm_index_sync_deleted(cm_index* idx) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
+  if (!idx->uploaded) return fail(CM_ERR_CUDA, "index is not resident on a CUDA device (call cm_index_upload); there is no CPU path");
+  if (idx->pending_removed.empty()) return CM_OK;
+  cm_status st = set_device(idx);
+  if (st != CM_OK) return st;
+  DeviceIndex& d = idx->dev;
+  const size_t m = idx->pending_removed.size();
+  uint32_t* handles = nullptr;
+  CM_CUDA(cudaMalloc(&handles, m * 4));
+  cudaError_t e = cudaMemcpy(handles, idx->pending_removed.data(), m * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_apply_tombstones(handles, (uint32_t)m, d.deleted, d.xbf16, d.k_pad, nullptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(handles);
+  if (e != cudaSuccess) return cuda_fail(e, "cm_index_sync_deleted");
+  d.live = idx->live;
+  idx->pending_removed.clear();
   return CM_OK;
 }
 
@@ -980,6 +1001,7 @@ cm_status cm_index_upload(cm_index* idx, int device) {
   if (device < 0 || device >= count) return fail(CM_ERR_INVALID_ARGUMENT, "device ordinal out of range");
   free_device(idx->dev);
   idx->uploaded = false;
+  idx->pending_removed.clear();  // the upload below carries every tombstone
   CM_CUDA(cudaSetDevice(device));
   DeviceIndex& d = idx->dev;
   d.device = device;

@@ -161,6 +161,7 @@ struct cm_index {
   uint32_t dim = 0;
   std::vector<float> x;             // [n][dim] preprocessed rows (host copy: graph build + upload source)
   std::vector<uint8_t> deleted;     // [n]
+  std::vector<uint32_t> pending_removed;  // tombstoned since the last upload / cm_index_sync_deleted
   std::vector<uint64_t> ts_secs;    // [n]
   std::vector<uint32_t> ts_nanos;   // [n]
   std::vector<float> decay;         // [n]

@@ -27,6 +27,10 @@ cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, flo
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
                            uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s);
 
+// Tombstone `m` handles on the device replica (deleted byte + NaN mask of the bf16 row).
+cudaError_t launch_apply_tombstones(const uint32_t* handles, uint32_t m, uint8_t* deleted, void* xbf16, uint32_t k_pad,
+                                    cudaStream_t s);
+
 // distance_prepared for n row pairs (src/metric.rs:219-224).
 cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,
                                  cudaStream_t s);

@@ -228,6 +228,25 @@ cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld
   return cudaGetLastError();
 }
 
+// `VectorIndex::remove` on the device replica (src/index/lockfree_hnsw.rs:451-467 flips `Node.deleted`): set the
+// tombstone byte the HNSW final-list filter and the fp32 scans read, and NaN-mask column 0 of the bf16 row so the
+// tensor-core scans never emit it again. The node keeps routing traffic, as in the reference.
+__global__ void k_apply_tombstones(const uint32_t* __restrict__ handles, uint32_t m, uint8_t* __restrict__ deleted,
+                                   __nv_bfloat16* __restrict__ xbf16, uint32_t k_pad) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t h = handles[i];
+    deleted[h] = 1;
+    xbf16[(uint64_t)h * k_pad] = __float2bfloat16(__int_as_float(0x7FC00000));
+  }
+}
+cudaError_t launch_apply_tombstones(const uint32_t* handles, uint32_t m, uint8_t* deleted, void* xbf16, uint32_t k_pad,
+                                    cudaStream_t s) {
+  if (m == 0) return cudaSuccess;
+  k_apply_tombstones<<<(m + 255) / 256, 256, 0, s>>>(handles, m, deleted, (__nv_bfloat16*)xbf16, k_pad);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // distance_prepared on row pairs (src/metric.rs:219-224): one lane-octet per pair; lane j carries the
 // reference's SIMD lane j (elements j, j+8, ...), then the reference's reduction order and scalar tail.

@@ -63,6 +63,7 @@ ABI = {
     "cm_index_set_contexts": (_i, [_vp, _vp, _vp]),
     "cm_index_context_id": (_u32, [_vp, C.c_char_p]),
     "cm_index_remove": (_i, [_vp, _u32, C.POINTER(_i)]),
+    "cm_index_sync_deleted": (_i, [_vp]),
     "cm_index_build_graph": (_i, [_vp, _u64, _i]),
     "cm_index_build_graph_gpu": (_i, [_vp, _u64, _i, _i, _u32]),
     "cm_index_build_graph_from_candidates": (_i, [_vp, _u64, _i, _u32, _vp, _vp]),
@@ -261,6 +262,11 @@ class ChronoMindB200:
         r = C.c_int(0)
         _check(native().cm_index_remove(self._h, handle, C.byref(r)))
         return bool(r.value)
+
+    def sync_deleted(self):
+        """Push the tombstones recorded by `remove` since the last upload to the device replica (bytes, not a re-upload)."""
+        _check(native().cm_index_sync_deleted(self._h))
+        return self
 
     def build_graph(self, layer_seed: int = 0x5EED, threads: int = 1):
         _check(native().cm_index_build_graph(self._h, layer_seed & (2 ** 64 - 1), threads))

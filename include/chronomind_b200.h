@@ -120,8 +120,13 @@ cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_
 uint32_t cm_index_context_id(const cm_index* idx, const char* label);
 
 /* `VectorIndex::remove` (src/index/lockfree_hnsw.rs:451-467): tombstone one handle. *removed = 1 when this
- * call flipped it. Takes effect on the device at the next cm_index_upload. */
+ * call flipped it. O(1) on the host; the device replica learns of it at cm_index_sync_deleted (or the next upload). */
 cm_status cm_index_remove(cm_index* idx, uint32_t handle, int* removed);
+/* Push the tombstones recorded since the last upload / sync to the device: a few bytes per removed handle (the
+ * `deleted` flag the HNSW final-list filter reads, src/index/lockfree_hnsw.rs:488-492, and a NaN mask on the row's
+ * bf16 copy so the tensor-core scans stop emitting it) instead of re-uploading the index. Tombstoned nodes keep
+ * routing, as in the reference. Call between batches: searches already enqueued may or may not see the removal. */
+cm_status cm_index_sync_deleted(cm_index* idx);
 
 /* Host HNSW construction following `LockFreeHnsw::insert` (src/index/lockfree_hnsw.rs:375-449) with
  * `with_seed(layer_seed)`. threads == 1 reproduces the reference's single-threaded (deterministic) graph;

@@ -586,3 +586,42 @@ def test_hnsw_1m_graph_identical_to_oracle(tmp_path):
         assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1]) and c["list_entries"] == int(octr[2])
         assert c["failures"] == 0
     assert st.dev_status() == 0
+
+
+def test_remove_then_sync_deleted_reaches_every_engine():
+    """`VectorIndex::remove` is O(1) in the reference (src/index/lockfree_hnsw.rs:451-467). Here: remove on the host,
+    `cm_index_sync_deleted` pushes a few bytes per handle, and the fp32 scan, the tensor-core scan, the HNSW search
+    and the store search all drop the handles — identical to the oracle with the same tombstones, and to a full
+    re-upload."""
+    data, q = datasets.embedding_dataset(12000, 120, 0xDE1)
+    ts_s, ts_n, dec = datasets.temporal_attrs(12000, 9, NOW[0])
+    cfg = default_config(dimensions=768, ef_construction=100, ef_search=64)
+    st = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec).build_graph(0xDE1, 1).upload(0)
+    orc = _oracle_for(data, 16, 100, 0xDE1)
+    first, _ = st.search_exact(q, 10)
+    victims = np.unique(first[:, :3].ravel())                 # the best hits of every query
+    dele = np.zeros(12000, np.uint8)
+    dele[victims] = 1
+    for h in victims:
+        assert st.remove(int(h)) and not st.remove(int(h))    # the second call finds it gone (:455-466)
+        orc.remove(int(h))
+    assert len(st) == 12000 - len(victims)
+    before, _ = st.search_exact(q, 10)
+    assert np.array_equal(before, first)                      # the replica has not been told yet
+    st.sync_deleted()
+    prepared = oracle.preprocess_rows(data)
+    wi, wd = oracle.brute_force(prepared, q, 10, mode="prepared", deleted=dele, threads=8)
+    for engine_id in (1, 2):
+        gi, gd = st.set_exact_engine(engine_id).search_exact(q, 10)
+        assert np.array_equal(gi, wi) and np.array_equal(bits(gd), bits(wd)), engine_id
+    st.set_exact_engine(0)
+    hi, hd = st.search_index(q, 64, 10)
+    oi, od, _, _ = orc.search_batch(q, 64, 10)
+    assert np.array_equal(hi, oi) and np.array_equal(bits(hd), bits(od))
+    assert not np.isin(hi, victims).any()
+    ti, tsc = st.search(q, 5, now=NOW)
+    rc, ri, rs, _ = orc.store_search_batch(q, 5, 768, 64, cfg.temporal_weight, cfg.base_decay_rate, ts_s, ts_n, dec, NOW[0], NOW[1])
+    assert rc == 0 and assert_order_matches_up_to_ties(ti, ri, tsc, rs) <= 0.001 * ti.size
+    again = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec, dele).build_graph(0xDE1, 1).upload(0)
+    ai, ad = again.search_exact(q, 10)
+    assert np.array_equal(ai, wi) and np.array_equal(bits(ad), bits(wd))
