@@ -442,9 +442,10 @@ static cm_status hnsw_pool(const cm_index* idx, Workspace* ws, const PreparedQue
     CM_CUDA(launch_fill(ws->pool_dist.as<float>(), (uint64_t)nq * ef, INFINITY, s));
     return CM_OK;
   }
-  // visited set: shared-memory hash table for small ef, one byte per node per CTA in HBM from ef = 96 up, where the
-  // table (30 * ef entries) would be what limits the queries in flight per SM. CM_HNSW_VMAP=0/1 forces either.
-  bool use_vmap = ef >= 96;
+  // visited set: shared-memory hash table for small ef, one byte per node per CTA in HBM from ef = 48 up, where the
+  // table (30 * ef entries) would be what limits the queries in flight per SM (measured cross-over between ef = 32
+  // and 64, hnsw_search.cu). CM_HNSW_VMAP=0/1 forces either.
+  bool use_vmap = ef >= 48;
   if (const char* env = getenv("CM_HNSW_VMAP")) use_vmap = atoi(env) != 0;
   uint32_t hb = use_vmap ? 0 : visited_entries_for(ef);
   unsigned grid = 0;

@@ -22,7 +22,7 @@
 //     never has to be cleared between layers or queries. Membership is exact. When a query would crowd the
 //     table past 3/4 the CTA restarts that query on a larger per-CTA table in global memory.
 //     At large ef that table is the biggest shared-memory consumer (30 * ef entries) and caps the queries in flight
-//     per SM, so from ef = 96 up `visited` moves to HBM instead: one BYTE per node per resident CTA, holding the epoch
+//     per SM, so from ef = 48 up `visited` moves to HBM instead: one BYTE per node per resident CTA, holding the epoch
 //     of the search that last visited the node (a plain load + store per neighbor — the lanes of warp 0 look at
 //     distinct nodes; 32 scattered sectors per expansion, ~2 % of the row bytes, and no capacity limit at all).
 //   * the fresh neighbors' rows are GATHERED BY THE COPY ENGINE: one `cp.async.bulk` (UBLKCP) per row, issued by
@@ -487,15 +487,17 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswKernelArgs a) {
   }
 }
 
-// Threads per CTA: the row distances need only 4 lanes per staged row, the rest of the CTA speeds up the list merge,
-// the table clears and the pop scan, which grow with ef. Measured (1M x 768, ms per 10k batch, 64/128/256 threads):
-// ef=64 7.58/7.11/7.18, ef=128 16.34/15.74/15.18, ef=200 26.32/23.99/23.62.
+// Threads per CTA: the row distances need only 4 lanes per staged row; the rest of the CTA shortens the list merge, the
+// table clears and the pop scan, which grow with ef — but every extra warp also lowers the queries resident per SM.
+// Round-2 sweep on 1M x 768 (tools/diag_hnsw_rows.py, profiles/r02_diag_hnsw_sweep.txt; ms per 10k batch at 64/128/256
+// threads, best rows, visited set where it is fastest): ef=32 3.92/3.84/4.12, ef=64 6.69/6.44/7.0, ef=128
+// 12.06/11.62/13.4, ef=200 19.17/17.86/20.8 => 128 threads throughout the measured range.
 static int hnsw_threads_for(uint32_t ef) {
   if (const char* env = getenv("CM_HNSW_THREADS")) {  // experiments only
     const int t = atoi(env);
     if (t == 64 || t == 128 || t == 256) return t;
   }
-  return ef <= 96 ? 128 : HN_THREADS;
+  return ef <= 256 ? 128 : HN_THREADS;
 }
 
 static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t table_entries, uint32_t rows) {
@@ -505,34 +507,26 @@ static size_t hnsw_smem_bytes(uint32_t dim, uint32_t ef, uint32_t table_entries,
 }
 
 // Rows per round vs CTAs per SM: fewer rows per round leave shared memory for more queries in flight but add a
-// dependent copy round per expansion (an expansion evaluates ~17 of its 32 neighbors on average). Measured on
-// 1M x 768 (tools/diag_hnsw_rows.py, ms per 10k-query batch at rows = 16/14/12/10/8/6):
-//   ef=64: 11.3/9.4/9.9/9.1/8.5/8.9   ef=128: 21.2/22.1/23.2/19.0/20.2/19.5   ef=200: 46.6/48.0/50.1/37.3/40.6/45.7
-// => a ~32 KB row buffer (10 rows of 768 floats) is the sweet spot; small rows take the full 16.
+// dependent copy round per expansion (an expansion evaluates ~17 of its 32 neighbors on average). Round-2 sweep
+// (same tool; ms per 10k batch at rows = 12/10/8/6, 128 threads): ef=32 (table) -/4.22/3.84/3.92, ef=64 (byte map)
+// -/-/6.60/6.44, ef=128 (byte map) -/13.39/12.09/11.62, ef=200 (byte map) 21.11/-/17.86/18.79 => 8 rows (~25 KB of
+// row buffer at 768 floats) for small and very large ef, 6 in between; short rows take the full 16.
 cudaError_t hnsw_grid_size(const DeviceIndex& ix, uint32_t ef, uint32_t table_entries, unsigned* grid, uint32_t* rows_out) {
   cudaError_t e = cudaFuncSetAttribute(k_hnsw_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) return e;
   const uint32_t row_stride = ix.dim_pad * 4 + HN_ROW_PAD;
-  uint32_t rows = std::min(HN_ROWS, std::max(4u, (32u * 1024u) / row_stride));
-  bool forced = false;
+  const uint32_t budget = (ef < 48 || ef >= 160) ? 25u * 1024u : 19u * 1024u;  // 8 or 6 rows of 768 floats
+  uint32_t rows = std::min(HN_ROWS, std::max(4u, budget / row_stride));
   if (const char* env = getenv("CM_HNSW_ROWS")) {  // experiments only
     uint32_t f = (uint32_t)atoi(env);
-    if (f) rows = std::min(std::max(f, 1u), HN_ROWS), forced = true;
+    if (f) rows = std::min(std::max(f, 1u), HN_ROWS);
   }
   while (rows > 1 && hnsw_smem_bytes(ix.dim, ef, table_entries, rows) > 220 * 1024) --rows;
-  auto ctas = [&](uint32_t r, int* out) -> cudaError_t {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_hnsw_search, hnsw_threads_for(ef), hnsw_smem_bytes(ix.dim, ef, table_entries, r));
-  };
   if (hnsw_smem_bytes(ix.dim, ef, table_entries, rows) > 220 * 1024) return cudaErrorInvalidValue;
   int per_sm = 0;
-  e = ctas(rows, &per_sm);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hnsw_search, hnsw_threads_for(ef),
+                                                    hnsw_smem_bytes(ix.dim, ef, table_entries, rows));
   if (e != cudaSuccess) return e;
-  if (!forced && rows > 8) {  // large ef (big visited table): two rows fewer per round if that admits one more CTA per SM
-    int per_sm8 = 0;
-    e = ctas(rows - 2, &per_sm8);
-    if (e != cudaSuccess) return e;
-    if (per_sm8 > per_sm && per_sm < 4) rows -= 2, per_sm = per_sm8;
-  }
   if (per_sm < 1) return cudaErrorInvalidValue;
   *grid = (unsigned)ix.sm_count * per_sm;
   *rows_out = rows;

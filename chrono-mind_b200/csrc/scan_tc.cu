@@ -459,9 +459,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         // Main pass, software pipelined: the next 32 columns are in flight while this chunk is filtered.
         auto filter_chunk = [&](uint32_t (&r)[32], uint32_t c) {
-          if (kBiased) {  // ranking key = score + bias[row] (broadcast reads: every lane looks at the same rows)
+          if (kBiased) {
+            // ranking key = score + bias[row] for the rows of this query's context, NaN for every other row (broadcast
+            // reads: all lanes look at the same rows). Folding the membership test into the value keeps chunks
+            // without a member on the fast path — with many small contexts that is nearly every chunk.
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + tb[c + i]);
+            for (int i = 0; i < 32; ++i)
+              r[i] = tcx[c + i] == my_ctx ? __float_as_uint(__uint_as_float(r[i]) + tb[c + i]) : 0x7FC00000u;
           }
           float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
@@ -473,7 +477,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             while (mask) {
               const uint32_t i = __ffs(mask) - 1;
               mask &= mask - 1;
-              if (kBiased && tcx[c + i] != my_ctx) continue;  // a row of another context
               const float s = pick32(r, i);
               if (s >= tau && a.join) {
                 const uint32_t row = (uint32_t)(row0 + c + i);
