@@ -431,7 +431,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // Cold start (no threshold yet): first build the running top-k from this tile WITHOUT emitting, so the
         // main pass below emits ~k rows instead of all 256. Tombstoned and padding rows score NaN (see
         // launch_to_bf16) and never enter a list or pass a threshold.
-        const bool cold = q_valid && tau == -INFINITY;
+        // (biased mode: a sparse context may never fill its running top-k — after two tiles the few members are simply
+        // emitted instead of paying the extra pass over the accumulator on every tile)
+        const bool cold = q_valid && tau == -INFINITY && (!kBiased || t < t0 + 2);
         bool listed = a.join != 0;  // this tile's rows are already in the running top-k (join: there is none)
         if (__any_sync(0xFFFFFFFFu, cold)) {
 #pragma unroll 1
