@@ -1393,9 +1393,67 @@ cm_status cm_search_exact(const cm_index* idx, const float* q, uint32_t nq, uint
   return search_exact_host(idx, q, nq, qdim, k, ids, dist, false);
 }
 
-// GPU-assisted graph construction (host half in hnsw_build.cpp): per layer, the candidate
-// neighbors of every member come from one all-pairs kNN of the layer's members on the device (tensor-core scan,
-// bf16-ranked, in batches of queries), then the host selects and links like `LockFreeHnsw::insert`.
+// One batch of the predecessor kNN behind the GPU-assisted construction: rows [q0, q0 + nb) of the resident index
+// against the rows BEFORE each of them (tensor-core scan in predecessor mode, bf16-ranked top-k, no exact rescore:
+// the host re-measures every candidate). ids_dev/dist_dev: [nb][k] device scratch; flagged (overflowed) queries come
+// back as CM_NO_ID rows and are redone by the caller.
+static cm_status pred_knn_batch(const cm_index* idx, Workspace* ws, uint32_t q0, uint32_t nb, uint32_t k, uint32_t* ids_dev,
+                                float* dist_dev, cudaStream_t s) {
+  const DeviceIndex& d = idx->dev;
+  const uint32_t nq_pad = scan_tc_pad_queries(nb);
+  const uint32_t cap = scan_tc_cand_cap(k);
+  CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
+  CM_CUDA(ws->cand.ensure((size_t)nq_pad * cap * 8));
+  CM_CUDA(ws->small.ensure(kSmallBytes));
+  CM_CUDA(ws->qflag.ensure((size_t)nq_pad * 4));
+  uint32_t* tau_key = ws->tc_state.as<uint32_t>();
+  uint32_t* cand_cnt = tau_key + nq_pad;
+  uint8_t* small = ws->small.as<uint8_t>();
+  CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
+  CM_CUDA(cudaMemsetAsync(small + 64, 0, 32, s));
+  ScanTcLaunch sl;
+  sl.q_bf16 = static_cast<const uint8_t*>(d.xbf16) + (size_t)q0 * d.k_pad * 2;  // the corpus rows ARE the queries
+  sl.nq = nb;
+  sl.k = k;
+  sl.tau_key = tau_key;
+  sl.cand_cnt = cand_cnt;
+  sl.cand = ws->cand.as<unsigned long long>();
+  sl.cap = cap;
+  sl.pred = true;
+  sl.q_base = q0;
+  {
+    ProfileScope prof(s);
+    CM_CUDA(launch_scan_tc(d, sl, s));
+  }
+  RescoreLaunch rl;
+  rl.qn = nullptr;  // approx mode never reads the fp32 queries
+  rl.ldq = d.dim_pad;
+  rl.nq = nb;
+  rl.k = k;
+  rl.tau_key = tau_key;
+  rl.cand_cnt = cand_cnt;
+  rl.cand = sl.cand;
+  rl.cap = cap;
+  rl.ids = ids_dev;
+  rl.dist = dist_dev;
+  rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
+  rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
+  rl.flag_list = ws->qflag.as<uint32_t>();
+  rl.flag_cap = nq_pad;
+  rl.approx = true;
+  rl.pred = true;
+  rl.pred_base = q0;
+  CM_CUDA(launch_rescore(d, rl, s));
+  return CM_OK;
+}
+
+// GPU-assisted graph construction (host half in hnsw_build.cpp). `LockFreeHnsw::insert` links node
+// i to a diverse pick of its nearest ALREADY INSERTED nodes (src/index/lockfree_hnsw.rs:419-432) — that is what makes
+// the graph navigable: early nodes link far and wide because nothing nearer exists yet. Per layer, the candidates of
+// every member therefore come from a PREDECESSOR kNN on the device: member j against members 0..j-1 only (tensor-core
+// scan of the layer's members against themselves, lower triangle, bf16-ranked, in batches of queries) — half the
+// work of an all-pairs join, and on clustered data the difference between a searchable graph and islands. The host
+// then selects and links like the reference (hnsw_build.cpp).
 cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates) {
   if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
   if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -1420,7 +1478,7 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
     lc.members.swap(members[layer]);
     const uint64_t nm = lc.members.size();
     if (nm <= 1) continue;
-    const uint32_t k = (uint32_t)std::min<uint64_t>(C + 1, nm);  // + the member itself (its own nearest neighbor)
+    const uint32_t k = (uint32_t)std::min<uint64_t>(C, nm - 1);
     lc.width = k;
     lc.ids.assign(nm * k, CM_NO_ID);
     cm_index* tmp = new_index(idx->config, nm, dim);
@@ -1434,13 +1492,42 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
     }
     cm_status st = cm_index_upload(tmp, device);
     if (layer == 0) lap("layer 0 upload");
-    const uint32_t batch = 16384;
-    std::vector<float> dist_scratch((size_t)std::min<uint64_t>(batch, nm) * k);
-    for (uint64_t q0 = 0; st == CM_OK && q0 < nm; q0 += batch) {
-      const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nm - q0);
-      st = search_exact_host(tmp, tmp->x.data() + q0 * dim, nb, dim, k, &lc.ids[q0 * k], dist_scratch.data(), /*approx=*/true);
+    std::vector<uint32_t> redo;  // members whose candidate buffer overflowed on the device
+    if (st == CM_OK && !(tmp->all_finite && scan_tc_supported(tmp->dev, k)))
+      st = fail(CM_ERR_STATE, "the GPU-assisted build needs the tensor-core scan (finite rows, at most 127 candidates)");
+    if (st == CM_OK) {
+      WorkspaceLease lease(tmp, nullptr, true);
+      if (lease.err != cudaSuccess) st = cuda_fail(lease.err, "workspace lease");
+      const uint32_t batch = 16384;  // a multiple of the tile height: batches start on tile boundaries
+      Workspace* ws = lease.ws;
+      cudaError_t ce = cudaSuccess;
+      if (st == CM_OK && ((ce = ws->out_ids.ensure((size_t)batch * k * 4)) != cudaSuccess || (ce = ws->out_a.ensure((size_t)batch * k * 4)) != cudaSuccess))
+        st = cuda_fail(ce, "scratch");
+      for (uint64_t q0 = 0; st == CM_OK && q0 < nm; q0 += batch) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nm - q0);
+        st = pred_knn_batch(tmp, ws, (uint32_t)q0, nb, k, ws->out_ids.as<uint32_t>(), ws->out_a.as<float>(), lease.s);
+        if (st != CM_OK) break;
+        ce = cudaMemcpyAsync(&lc.ids[q0 * k], ws->out_ids.p, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, lease.s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(lease.s);
+        if (ce != cudaSuccess) st = cuda_fail(ce, "predecessor kNN batch");
+      }
     }
-    if (layer == 0) lap("layer 0 self-join");
+    if (st == CM_OK)
+      for (uint64_t i = 1; i < nm; ++i)  // member 0 has no predecessor; anything else without candidates was flagged
+        if (lc.ids[i * k] == CM_NO_ID) redo.push_back((uint32_t)i);
+    if (layer == 0) lap("layer 0 predecessor kNN");
+    if (st == CM_OK && !redo.empty()) {  // rare: exact predecessor scan on the host for the flagged members
+      const float* X = tmp->x.data();
+      parallel_rows(redo.size(), [&](uint64_t r) {
+        const uint32_t i = redo[r];
+        std::vector<std::pair<float, uint32_t>> best;
+        best.reserve(i);
+        for (uint32_t p = 0; p < i; ++p) best.emplace_back(dist_prepared_host(X + (uint64_t)p * dim, X + (uint64_t)i * dim, dim), p);
+        const size_t kk = std::min<size_t>(k, best.size());
+        std::partial_sort(best.begin(), best.begin() + (long)kk, best.end());
+        for (size_t c = 0; c < kk; ++c) lc.ids[(uint64_t)i * k + c] = best[c].second;
+      });
+    }
     if (layer == 0) tmp->x.swap(idx->x);
     cm_index_free(tmp);
     if (st != CM_OK) return st;

@@ -86,6 +86,7 @@ void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const
 
 // Host metric kernels (same arithmetic as src/metric.rs; see metric_host.h).
 void preprocess_row(const float* v, uint32_t n, float* out);
+float dist_prepared_host(const float* a, const float* b, uint32_t n);  // distance_prepared, AVX2+FMA lane order
 
 // ---------------------------------------------------------------------------------------------------------
 // Snapshot records (src/types.rs) as parsed by snapshot.cpp.

@@ -644,6 +644,8 @@ int check_graph_invariants(const Graph& g) {
   return 0;
 }
 
+float dist_prepared_host(const float* a, const float* b, uint32_t n) { return dist_prepared(a, b, n); }
+
 void preprocess_row(const float* v, uint32_t n, float* out) {  // src/metric.rs:208-214
   float s = 0.0f;
   for (uint32_t i = 0; i < n; ++i) s += v[i] * v[i];

@@ -216,6 +216,10 @@ struct ScanArgs {
   unsigned long long* pairs;     // [pair_cap] (query << 32 | row)
   uint32_t* pair_count;          // pairs found (may exceed pair_cap: the caller retries with a larger buffer)
   uint32_t pair_cap;
+  // predecessor mode (graph construction): query i of this launch is corpus row q_base + i (q_base a multiple of
+  // 256) and only rows BEFORE it count — what `LockFreeHnsw::insert` can see when it links node q_base + i
+  uint32_t pred;
+  uint32_t q_base;
   // biased mode (kBiased instantiation, `search_in_context`): the ranking key of query q against row r is
   // score + bias[r], and only rows with row_ctx[r] == q_ctx[q] take part
   const float* bias;             // [n_pad]
@@ -262,7 +266,7 @@ struct LocalTopK {
   }
 };
 
-template <bool kBiased>
+template <bool kBiased, bool kPred>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -315,8 +319,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
         uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-        const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        const uint32_t t1_all = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
+        const uint32_t t1 = kPred ? min(t1_all, a.q_base / BN + m + 1) : t1_all;  // predecessors: up to the diagonal tile
         const int32_t q_row = (int32_t)(m * PAIR_M + rank * BM);
         for (uint32_t t = t0; t < t1; ++t) {
           const int32_t x_row = (int32_t)(t * BN + rank * BN_HALF);
@@ -344,8 +349,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t sp = u / a.m_pairs;
         uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-        const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
+        if (kPred) t1 = min(t1, a.q_base / BN + u % a.m_pairs + 1);  // predecessors: up to the diagonal tile
         for (uint32_t t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&tail->tmem_empty[acc]), acc_phase ^ 1);  // both epilogues drained this accumulator
           tc_fence_after();
@@ -387,9 +393,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (uint32_t u = cluster_id; u < units; u += n_clusters) {
       const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
       uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-      const uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+      uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
       if (a.join) t0 = max(t0, m);  // self-join keeps row > query: tiles below the diagonal are skipped
+      if (kPred) t1 = min(t1, a.q_base / BN + m + 1);  // predecessors: up to the diagonal tile
       const uint32_t q = m * PAIR_M + rank * BM + row_in_cta;
+      const uint64_t q_row_id = (uint64_t)a.q_base + q;  // predecessor mode: this query IS corpus row q_base + q
       const bool q_valid = q < a.nq;
       uint32_t my_ctx = CM_NO_ID_DEV;  // biased mode: CM_NO_ID matches no row
       if (kBiased && q_valid) my_ctx = a.q_ctx[q];
@@ -411,6 +419,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tau = fmaxf(g, top.filled == top.k ? top.kth - a.eps2 : -INFINITY);
         }
         const uint64_t row0 = (uint64_t)t * BN;
+        const bool diag = kPred && t == a.q_base / BN + m;  // the only tile that holds rows at or after the query
         const float* tb = tile_bias + acc * BN;
         const uint32_t* tcx = tile_ctx + acc * BN;
         if (kBiased) {
@@ -447,7 +456,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               for (int i = 0; i < 32; ++i) {
                 float s = __uint_as_float(r[i]);
                 if (kBiased) s = tcx[c + i] == my_ctx ? s + tb[c + i] : __int_as_float(0x7FC00000);
-                if (s == s) top.insert(s);
+                if (s == s && (!diag || row0 + c + i < q_row_id)) top.insert(s);
               }
             }
           }
@@ -480,6 +489,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               const uint32_t i = __ffs(mask) - 1;
               mask &= mask - 1;
               const float s = pick32(r, i);
+              if (diag && row0 + c + i >= q_row_id) continue;  // not a predecessor
               if (s >= tau && a.join) {
                 const uint32_t row = (uint32_t)(row0 + c + i);
                 if (row > q) {
@@ -597,6 +607,8 @@ struct RescoreArgs {
   uint32_t rows;          // rows gathered per copy round, <= RS_ROWS
   float eps2;             // 2 * eps_for_dim(dim)
   uint32_t region;        // bytes of the shared keys / row-buffer region (128-byte multiple)
+  uint32_t pred;          // predecessor mode: query q has only pred_base + q rows to choose from
+  uint32_t pred_base;
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -626,7 +638,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     n_surv = 0, n_keep = 0;
     rg_mbar_init(&mbar);
   }
-  for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.qn[(uint64_t)q * a.ldq + e];
+  if (!a.approx)  // the bf16 ranking of `approx` never looks at the fp32 query
+    for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.qn[(uint64_t)q * a.ldq + e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
     const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
@@ -637,7 +650,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   }
   __syncthreads();
   const uint32_t ns = n_surv;
-  const uint32_t need = (uint32_t)(a.n_live < a.k ? a.n_live : a.k);
+  uint32_t need = (uint32_t)(a.n_live < a.k ? a.n_live : a.k);
+  if (a.pred) need = min(a.k, a.pred_base + q);
   bool bad = cnt_raw > a.cap || ns > a.rs_max || ns < need;
   uint32_t keep = 0;
   if (!bad) {
@@ -908,6 +922,12 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.nq = l.nq;
   a.m_pairs = nq_pad / PAIR_M;
   a.n_tiles = (uint32_t)(ix.n_pad / BN);
+  a.pred = l.pred ? 1u : 0u;
+  a.q_base = l.q_base;
+  if (l.pred) {
+    if (l.q_base % BN != 0) return cudaErrorInvalidValue;
+    a.n_tiles = std::min<uint32_t>(a.n_tiles, (l.q_base + nq_pad) / BN);  // no query of this launch sees rows beyond that
+  }
   a.k_blocks = ix.k_pad / BK;
   a.k = l.k;
   a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters, l.k, l.cap);
@@ -930,7 +950,8 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
   if (a.stages < 2) return cudaErrorInvalidValue;
   const size_t smem = fixed + (size_t)a.stages * kStageBytes;
-  auto kernel = biased ? scan_tc_kernel<true> : scan_tc_kernel<false>;
+  auto kernel = biased ? scan_tc_kernel<true, false> : (l.pred ? scan_tc_kernel<false, true> : scan_tc_kernel<false, false>);
+  if (biased && l.pred) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
   if (e != cudaSuccess) return e;
   const uint32_t units = a.m_pairs * a.splits;
@@ -963,6 +984,8 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.rescored_total = l.rescored_total;
   a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
   a.approx = l.approx ? 1u : 0u;
+  a.pred = l.pred ? 1u : 0u;
+  a.pred_base = l.pred_base;
   a.eps2 = 2.0f * eps_for_dim(ix.dim);
   const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
   const size_t other = (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;

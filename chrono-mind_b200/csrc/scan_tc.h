@@ -27,6 +27,10 @@ struct ScanTcLaunch {
   unsigned long long* pairs = nullptr;
   uint32_t* pair_count = nullptr;  // zeroed by the caller
   uint32_t pair_cap = 0;
+  // predecessor mode (graph construction): q_bf16 = rows [q_base, q_base + nq) of the corpus copy itself (q_base a
+  // multiple of 256); row r competes for query i only when r < q_base + i
+  bool pred = false;
+  uint32_t q_base = 0;
   // biased mode (`search_in_context`): ranking key = score + bias[row], restricted to rows with row_ctx[row] == q_ctx[q]
   const float* bias = nullptr;        // [pad_rows(n)]
   const uint32_t* row_ctx = nullptr;  // [pad_rows(n)]
@@ -48,6 +52,8 @@ struct RescoreLaunch {
   uint32_t flag_cap;
   unsigned long long* rescored_total;
   bool approx = false;       // top-k by bf16 score, no exact rescore (graph-construction candidates)
+  bool pred = false;         // predecessor mode: query i has pred_base + i rows to choose from
+  uint32_t pred_base = 0;
 };
 cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaStream_t s);
 

@@ -134,14 +134,14 @@ cm_status cm_index_sync_deleted(cm_index* idx);
  * to run. Needed before cm_search_hnsw / cm_search_temporal(exact = 0). */
 cm_status cm_index_build_graph(cm_index* idx, uint64_t layer_seed, int threads);
 
-/* GPU-assisted construction: the candidate neighbors of every node (`search_layer(ef_construction)`
- * in `LockFreeHnsw::insert`, src/index/lockfree_hnsw.rs:419-432) come from an all-pairs kNN of each layer's members
- * on CUDA device `device` (tensor-core scan, `n_candidates` nearest per node, 0 = min(ef_construction, 64), at most
- * 127); the host then applies the reference's `select_diverse` (:205-240) and `add_backlink` (:246-280) with `threads`
- * threads. Same layer draw and entry point as cm_index_build_graph; the linkage differs (as it does between any two
- * concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. Nearest-neighbor candidates
- * alone do not guarantee a connected layer 0 (clustered data): components the entry point cannot reach are bridged
- * afterwards (see cm_index_unreachable). */
+/* GPU-assisted construction. `LockFreeHnsw::insert` links node i to a diverse pick of its nearest
+ * ALREADY INSERTED nodes (`search_layer(ef_construction)` over the graph so far, src/index/lockfree_hnsw.rs:419-432).
+ * Here those candidates come from an exact PREDECESSOR kNN of each layer's members on CUDA device `device`: member j
+ * against members 0..j-1 (tensor-core scan, lower triangle, `n_candidates` nearest per node, 0 = min(ef_construction,
+ * 64), at most 127); the host then applies the reference's `select_diverse` (:205-240) and `add_backlink` (:246-280)
+ * with `threads` threads. Same layer draw and entry point as cm_index_build_graph; the linkage differs (as it does
+ * between any two concurrent builds of the reference, :21-26) and satisfies cm_index_check_invariants. Components the
+ * entry point cannot reach are bridged afterwards (see cm_index_unreachable). */
 cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates);
 
 /* The host half of the GPU-assisted construction on caller-supplied candidates (any kNN source): `cand_ids[l]` holds

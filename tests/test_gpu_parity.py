@@ -625,3 +625,28 @@ def test_remove_then_sync_deleted_reaches_every_engine():
     again = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec, dele).build_graph(0xDE1, 1).upload(0)
     ai, ad = again.search_exact(q, 10)
     assert np.array_equal(ai, wi) and np.array_equal(bits(ad), bits(wd))
+
+
+def test_gpu_assisted_build_on_clustered_data_is_navigable():
+    """Tight, well separated clusters are where a nearest-neighbor graph falls apart into islands (every candidate of a
+    row lies in its own cluster). The GPU-assisted build takes PREDECESSOR neighbors like `LockFreeHnsw::insert` does, so
+    early rows link across clusters: every node must be reachable and queries at the cluster centres must find their
+    cluster — recall no worse than the host replay of the reference's insertion minus 0.02."""
+    rng = np.random.default_rng(0xC1)
+    centres = rng.normal(size=(200, 48)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    data = (np.repeat(centres, 50, axis=0) + 0.02 * rng.normal(size=(10000, 48))).astype(np.float32)
+    data = data[rng.permutation(len(data))]
+    q = (centres + 0.01 * rng.normal(size=centres.shape)).astype(np.float32)
+    cfg = default_config(dimensions=48, ef_construction=64)
+    host = ChronoMindB200.from_matrix(data, cfg).build_graph(9, 1).upload(0)
+    gpu = ChronoMindB200.from_matrix(data, cfg).build_graph_gpu(9, 0, 8, 24).upload(0)   # 24 candidates < a cluster's 50 rows
+    assert gpu.check_invariants() == 0 and gpu.unreachable() == 0
+    truth, _ = host.search_exact(q, 10)
+
+    def recall(st, ef):
+        ids, _ = st.search_index(q, ef, 10)
+        return float(np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ids.tolist(), truth.tolist())]))
+    for ef in (32, 64):
+        r_host, r_gpu = recall(host, ef), recall(gpu, ef)
+        assert r_gpu >= 0.95 and r_gpu >= r_host - 0.02, (ef, r_host, r_gpu)
