@@ -288,14 +288,29 @@ def _clustered(n_clusters, per, dim, seed, spread=0.02):
     return x[perm].astype(np.float32), centres
 
 
-@pytest.mark.parametrize("clusters,per,width,bridging_needed", [(24, 120, 33, False), (160, 18, 65, False), (160, 18, 13, True)])
-def test_knn_graph_on_clustered_data_is_bridged_and_searchable(tmp_path, clusters, per, width, bridging_needed):
+def _predecessor_knn(prepared, members, k):
+    """Candidates as `LockFreeHnsw::insert` sees them: for member j, its k nearest among members 0..j-1."""
+    x = prepared[members]
+    sim = x @ x.T
+    out = np.full((len(members), k), 0xFFFFFFFF, np.uint32)
+    for j in range(1, len(members)):
+        kk = min(k, j)
+        idx = np.argsort(-sim[j, :j], kind="stable")[:kk]
+        out[j, :kk] = members[idx]
+    return out
+
+
+@pytest.mark.parametrize("clusters,per,width,bridging_needed,predecessors",
+                         [(24, 120, 33, False, False), (160, 18, 65, False, False), (160, 18, 13, True, False),
+                          (160, 18, 13, False, True)])
+def test_knn_graph_on_clustered_data_is_bridged_and_searchable(tmp_path, clusters, per, width, bridging_needed, predecessors):
     """Nearest-neighbor candidates alone can leave whole clusters without a way in (the reference's incremental insert
     cannot: every new node is linked into what the entry already reaches). The candidate-based builder must bridge
     them: no layer-0 node unreachable from the entry (the way a search moves), invariants intact, and the oracle
     searching THAT graph meets the recall gate on queries at the cluster centres. The last case feeds fewer candidates
     than a cluster has rows — every cluster without an upper-layer member starts out isolated — and only requires what
-    the repair guarantees: reachability."""
+    the repair guarantees: reachability. With PREDECESSOR candidates (what the GPU-assisted build feeds) the same starved
+    configuration is navigable again: early rows have no near predecessor and link across clusters, as in the reference."""
     data, centres = _clustered(clusters, per, 32, 0xC1)
     cfg = default_config(dimensions=32, ef_construction=64)
     seed = 5
@@ -304,6 +319,9 @@ def test_knn_graph_on_clustered_data_is_bridged_and_searchable(tmp_path, cluster
     cands = []
     for m in st.layer_members(seed):
         k = min(width, len(m))
+        if predecessors:
+            cands.append(_predecessor_knn(prepared, m, k))
+            continue
         ids, _ = oracle.brute_force(prepared[m], prepared[m], k, mode="prepared", threads=4)
         cands.append(np.where(ids == 0xFFFFFFFF, 0xFFFFFFFF, m[np.minimum(ids, len(m) - 1)]).astype(np.uint32))
     st.build_graph_from_candidates(seed, cands, threads=4)
