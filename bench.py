@@ -511,6 +511,7 @@ def run_ours(args, rank, world, local_rank):
         dev_ids = res[0].cpu().numpy().view(np.uint32).copy()      # what the timed device path returned last
         dev_dist = res[1].cpu().numpy().copy()
         unresolved_status = st.dev_status()                        # queries the async path could not resolve (0 normally)
+        dev_ctr = st.dev_counters()                                # of every device-resident step so far (warm-up included)
         e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps)
         counters = engine.last_counters() if world == 1 else {}    # of the last host-buffer call (the e2e leg)
         truth = [None] * QUERY_BATCHES
@@ -525,7 +526,7 @@ def run_ours(args, rank, world, local_rank):
         exact = {
             "ms": ms, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
             "dev_ids": dev_ids, "dev_dist": dev_dist, "last_batch": last_batch, "tc": tc, "unresolved": unresolved + unresolved_status,
-            "counters": counters,
+            "counters": counters, "dev_counters": dev_ctr, "dev_steps": args.warmup + args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                          "frac": (achieved / burst) if achieved else None,
                          "frac_burst": (achieved / burst) if achieved else None,
@@ -689,6 +690,8 @@ def run_ours(args, rank, world, local_rank):
                                 "recall_at_10": (cpu or {}).get("recall_at_10_on_sample", "exact by construction (unchecked: --no-cpu-baseline)"),
                                 "unresolved_queries": exact["unresolved"], "fallback_queries_e2e": exact["counters"].get("fallback_queries"),
                                 "rescored_per_query_e2e": (exact["counters"].get("rescored", 0) / nq) if exact["counters"] else None,
+                                "fallback_queries_device_steps": exact["dev_counters"]["fallback_queries"],
+                                "rescored_per_query_per_shard_device_steps": exact["dev_counters"]["rescored"] / (nq * exact["dev_steps"]),
                                 "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
                                 "l2": "inputs larger than L2: %.2f GB bf16 corpus per GPU streamed per step; %d query batches rotated"
                                       % (shard.shape[0] * DIM * 2 / 1e9, QUERY_BATCHES)},

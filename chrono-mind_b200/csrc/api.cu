@@ -1317,6 +1317,19 @@ cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset
   return CM_OK;
 }
 
+cm_status cm_index_dev_counters(const cm_index* idx, uint64_t* rescored, uint64_t* fallback_queries, int reset) {
+  if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!idx->uploaded) return fail(CM_ERR_CUDA, "index is not resident on a CUDA device (call cm_index_upload); there is no CPU path");
+  cm_status st = set_device(idx);
+  if (st != CM_OK) return st;
+  uint32_t w[8];
+  CM_CUDA(cudaMemcpy(w, idx->dev.status, sizeof w, cudaMemcpyDeviceToHost));  // waits for the work enqueued so far
+  if (rescored) *rescored = ((uint64_t)w[3] << 32) | w[2];
+  if (fallback_queries) *fallback_queries = w[4];
+  if (reset) CM_CUDA(cudaMemset(idx->dev.status + 2, 0, 3 * sizeof(uint32_t)));
+  return CM_OK;
+}
+
 cm_status cm_set_exact_engine(cm_index* idx, int engine) {
   if (!idx || engine < 0 || engine > 2) return fail(CM_ERR_INVALID_ARGUMENT, "engine must be 0, 1 or 2");
   idx->exact_engine = engine;

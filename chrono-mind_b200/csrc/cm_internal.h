@@ -149,7 +149,9 @@ struct DeviceIndex {
   int sm_count = 0;
   // Device status words for the asynchronous (_dev) entry points, which cannot report through a return value:
   // [0] HNSW queries that could not be answered like the reference (visited-table exhaustion, oversized tie group),
-  // [1] exact-scan queries left unresolved (more flagged queries than the in-stream fp32 fallback absorbs).
+  // [1] exact-scan queries left unresolved (more flagged queries than the in-stream fp32 fallback absorbs),
+  // [2..3] rows re-scored by K2 (u64) and [4] queries routed to the fp32 fallback since the last reset — the work
+  // counters a host-buffer call reports through cm_last_counters, for callers that never synchronise.
   uint32_t* status = nullptr;
 };
 

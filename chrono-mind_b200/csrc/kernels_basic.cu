@@ -464,7 +464,11 @@ __global__ void k_fold_scan_counters(const unsigned char* chunk, unsigned char* 
   *reinterpret_cast<uint32_t*>(total + 8) += f;
   uint32_t* worst = reinterpret_cast<uint32_t*>(total + 12);
   if (f > *worst) *worst = f;
-  if (status && f > flag_cap) atomicAdd(status, f - flag_cap);
+  if (status) {  // status points at word [1] of the index's status block: [1] unresolved, [2..3] rescored (u64), [4] flagged
+    if (f > flag_cap) atomicAdd(status, f - flag_cap);
+    atomicAdd(reinterpret_cast<unsigned long long*>(status + 1), r);
+    atomicAdd(status + 3, f);
+  }
 }
 cudaError_t launch_fold_scan_counters(const void* chunk, void* total, uint32_t flag_cap, uint32_t* status, cudaStream_t s) {
   k_fold_scan_counters<<<1, 1, 0, s>>>((const unsigned char*)chunk, (unsigned char*)total, flag_cap, status);

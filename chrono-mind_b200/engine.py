@@ -95,6 +95,7 @@ ABI = {
     "cm_search_hnsw_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "cm_search_temporal_dev": (_i, [_vp, _vp, _u32, _u32, _u32, _f, _f, _u64, _u32, _i, _vp, _vp, _vp, _vp]),
     "cm_index_dev_status": (_i, [_vp, C.POINTER(_u64), _i]),
+    "cm_index_dev_counters": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), _i]),
     "cm_group_create": (_i, [_vp, _i, C.POINTER(_vp)]),
     "cm_group_free": (None, [_vp]),
     "cm_group_from_matrix": (_i, [_vp, _vp, _u64, _u32, C.POINTER(Config)]),
@@ -321,6 +322,12 @@ class ChronoMindB200:
         f = C.c_uint64(0)
         _check(native().cm_index_dev_status(self._h, C.byref(f), 1 if reset else 0))
         return int(f.value)
+
+    def dev_counters(self, reset: bool = True) -> dict:
+        """Work counters of the asynchronous exact searches enqueued so far (waits for them)."""
+        r, f = C.c_uint64(0), C.c_uint64(0)
+        _check(native().cm_index_dev_counters(self._h, C.byref(r), C.byref(f), 1 if reset else 0))
+        return {"rescored": int(r.value), "fallback_queries": int(f.value)}
 
     def set_exact_engine(self, engine: int):
         _check(native().cm_set_exact_engine(self._h, engine))

@@ -251,6 +251,9 @@ cm_status cm_search_in_context_dev(const cm_index* idx, const void* q, uint32_t 
  * enqueued so far on that device, returns the count in *failures and optionally clears it. The host-buffer variants
  * need no such call: they redo the batch or return CM_ERR_CAPACITY_EXCEEDED. */
 cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset);
+/* Work counters of the asynchronous exact searches since the last reset (what cm_last_counters reports for a
+ * host-buffer call): rows re-scored by the fp32 rescore and queries routed to the fp32 fallback. Waits like the above. */
+cm_status cm_index_dev_counters(const cm_index* idx, uint64_t* rescored, uint64_t* fallback_queries, int reset);
 
 /* Merge step of `ShardedRwLockHnsw::search` (src/index/sharded_rwlock.rs:81-94): concatenate per-shard lists,
  * sort by (distance, global handle), truncate. ids/dist: device [n_shards][nq][len] LOCAL handles as produced

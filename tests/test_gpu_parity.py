@@ -650,3 +650,39 @@ def test_gpu_assisted_build_on_clustered_data_is_navigable():
     for ef in (32, 64):
         r_host, r_gpu = recall(host, ef), recall(gpu, ef)
         assert r_gpu >= 0.95 and r_gpu >= r_host - 0.02, (ef, r_host, r_gpu)
+
+
+def test_async_calls_on_different_streams_do_not_share_scratch():
+    """The `_dev` entry points return while their kernels still run; the workspace they used carries a completion event,
+    so a call on ANOTHER stream (or thread) either gets a different workspace or waits for that event on the device.
+    Interleave exact, HNSW and temporal searches over three streams without synchronising in between: every result must
+    equal the one computed alone, and the status word must stay clean."""
+    import torch
+    data, q = datasets.embedding_dataset(16000, 3000, 0x57E)
+    ts_s, ts_n, dec = datasets.temporal_attrs(16000, 2, NOW[0])
+    cfg = default_config(dimensions=768, ef_construction=100)
+    st = ChronoMindB200.from_matrix(data, cfg, ts_s, ts_n, dec).build_graph(3, 8).upload(0)
+    tq = [torch.from_numpy(q[i * 1000:(i + 1) * 1000]).cuda() for i in range(3)]
+    want = []
+    for t in tq:
+        e = st.search_exact_cuda(t, 10)
+        h = st.search_index_cuda(t, 64, 10)
+        s = st.search_cuda(t, 5, NOW, ef_search=64)
+        torch.cuda.synchronize()
+        want.append([x.clone() for x in (*e, *h, *s)])
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(4):
+        got = []
+        for i, (t, sm) in enumerate(zip(tq, streams)):          # enqueue everything before waiting for anything
+            with torch.cuda.stream(sm):
+                e = st.search_exact_cuda(t, 10)
+                h = st.search_index_cuda(t, 64, 10)
+                s = st.search_cuda(t, 5, NOW, ef_search=64)
+            got.append((*e, *h, *s))
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            for a, b in zip(g, w):
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32)), rep
+    assert st.dev_status() == 0
+    c = st.dev_counters()
+    assert c["fallback_queries"] == 0 and c["rescored"] >= 10 * 1000 * 3
