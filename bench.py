@@ -397,8 +397,11 @@ def run_ours(args, rank, world, local_rank):
 
     q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(QUERY_BATCHES)]
     q_dev = [q.to(dev) for q in q_host]
-    ids_l = torch.empty((nq, K), dtype=torch.int32, device=dev)
-    dist_l = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    n_streams = max(1, args.streams)
+    streams = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
+    ids_s = [torch.empty((nq, K), dtype=torch.int32, device=dev) for _ in range(n_streams)]      # one result buffer per
+    dist_s = [torch.empty((nq, K), dtype=torch.float32, device=dev) for _ in range(n_streams)]   # batch in flight
+    ids_l, dist_l = ids_s[0], dist_s[0]
     out_ids_host = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     out_dist_host = torch.empty((nq, K), dtype=torch.float32).pin_memory()
     # N > 1: every rank needs the whole batch on its GPU. Each rank copies 1/N of it from pinned host memory over
@@ -442,12 +445,23 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.start()
 
-    def timed_device(step_fn, warmup, steps):
+    def timed_device(step_fn, warmup, steps, pipelined=False):
         """W untimed + K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream, max over
-        ranks. Returns (ms, result of the last step, kernels launched, (dominant-kernel ms, launches))."""
+        ranks. `pipelined`: consecutive batches go to alternating CUDA streams (a serving loop with two batches in
+        flight: the rescore / exchange / merge of batch i runs under the scan of batch i + 1); the events still bracket
+        ALL the work — the side streams fork from the timing stream after ev0 and join it before ev1.
+        Returns (ms, result of the last step, kernels launched, (dominant-kernel ms, launches))."""
         res = None
+        cur = torch.cuda.current_stream(dev)
+        use = streams if pipelined else []
+
+        def run(i):
+            if use:
+                with torch.cuda.stream(use[i % len(use)]):
+                    return step_fn(i)
+            return step_fn(i)
         for i in range(warmup):
-            step_fn(i)
+            run(i)
         barrier()
         engine.profile_enable(True)
         engine.profile_read()
@@ -457,8 +471,12 @@ def run_ours(args, rank, world, local_rank):
         if sampler:
             sampler.region(True)
         ev0.record()
+        for sm in use:
+            sm.wait_stream(cur)
         for i in range(steps):
-            res = step_fn(warmup + i)
+            res = run(warmup + i)
+        for sm in use:
+            cur.wait_stream(sm)
         ev1.record()
         barrier()
         if sampler:
@@ -469,21 +487,39 @@ def run_ours(args, rank, world, local_rank):
         engine.profile_enable(False)
         return ms, res, launches, prof
 
-    def timed_host(step_fn, warmup, steps):
+    def timed_host(step_fn, warmup, steps, callers=1):
+        """K timed calls of a blocking host-buffer entry point. `callers` > 1: that many caller threads share the index
+        (`&self` + Send + Sync; the reference's own benches time search from T threads, benches/comparison.rs:125-139) —
+        one thread's H2D / D2H then overlaps another's kernels. Every call still moves its own batch in and its own
+        result out inside the timed region. Returns (seconds, result of the last call)."""
         for i in range(min(warmup, 2)):
             step_fn(i)
         barrier()
         if sampler:
             sampler.region(True)
+        out = [None]
         t0 = time.perf_counter()
-        out = None
-        for i in range(steps):
-            out = step_fn(warmup + i)
+        if callers <= 1:
+            for i in range(steps):
+                out[0] = step_fn(warmup + i)
+        else:
+            def worker(t):
+                for i in range(t, steps, callers):
+                    r = step_fn(warmup + i)
+                    if i == steps - 1:
+                        out[0] = r
+            ts = [threading.Thread(target=worker, args=(t,)) for t in range(callers)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
         if sampler:
             sampler.region(False)
-        return max_over_ranks(secs), out
+        return max_over_ranks(secs), out[0]
+
+    e2e_callers = max(1, args.callers) if world == 1 else 1      # N > 1: the e2e leg drives torch collectives from one thread
 
     # ---- exact scan (configs[1]; ground truth of everything else) ---------------------------------------------------
     exact = None
@@ -491,8 +527,9 @@ def run_ours(args, rank, world, local_rank):
     if want_exact:
         def step_device(i):
             """Inputs resident in HBM; result stays on the device."""
-            st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_l, dist_l)
-            return merged(ids_l, dist_l, K)
+            b = i % n_streams
+            st.search_exact_cuda(q_dev[i % QUERY_BATCHES], K, ids_s[b], dist_s[b])
+            return merged(ids_s[b], dist_s[b], K)
 
         def step_e2e(i):
             """Public API with HOST buffers: H2D of the query batch and D2H of the result inside the step."""
@@ -506,13 +543,15 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             return out_ids_host, out_dist_host
 
-        ms, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, args.warmup, args.steps)
+        ms, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, args.warmup, args.steps, pipelined=n_streams > 1)
         last_batch = (args.warmup + args.steps - 1) % QUERY_BATCHES
         dev_ids = res[0].cpu().numpy().view(np.uint32).copy()      # what the timed device path returned last
         dev_dist = res[1].cpu().numpy().copy()
         unresolved_status = st.dev_status()                        # queries the async path could not resolve (0 normally)
         dev_ctr = st.dev_counters()                                # of every device-resident step so far (warm-up included)
-        e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps)
+        e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps, callers=e2e_callers)
+        if world == 1:
+            step_e2e(0)                                            # once more on THIS thread: its counters are thread-local
         counters = engine.last_counters() if world == 1 else {}    # of the last host-buffer call (the e2e leg)
         truth = [None] * QUERY_BATCHES
         truth[last_batch] = dev_ids
@@ -590,11 +629,13 @@ def run_ours(args, rank, world, local_rank):
             ms, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, h_warm, h_steps)
             last = (h_warm + h_steps - 1) % nb
             got = res[0].cpu().numpy().view(np.uint32)
-            e2e_t, _ = timed_host(step_e2e_temporal, 1, 3)
+            e2e_steps = 4
+            e2e_t, _ = timed_host(step_e2e_temporal, 1, e2e_steps, callers=e2e_callers)
             e2e_i = None
             if world == 1:
-                e2e_i, _ = timed_host(step_e2e_index, 1, 3)
-                c = engine.last_counters()                               # of the last host-buffer index search == one batch
+                e2e_i, _ = timed_host(step_e2e_index, 1, e2e_steps, callers=e2e_callers)
+                step_e2e_index(last)
+                c = engine.last_counters()                               # of a host-buffer index search on this thread == one batch
             else:
                 st.search_index(q_host[last].numpy(), ef, K)
                 c = engine.last_counters()
@@ -606,7 +647,7 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes_per_query": bytes_per_batch / nq, "kernel_ms_avg": kern_avg,
                 "achieved_gbs": bytes_per_batch / (kern_avg * 1e-3) / 1e9 if kern_avg > 0 else None,
                 "hbm_frac": bytes_per_batch / (kern_avg * 1e-3) / 1e9 / hbm_peak if kern_avg > 0 else None,
-                "e2e_index_qps": (nq * 3 / e2e_i) if e2e_i else None, "e2e_temporal_qps": nq * 3 / e2e_t,
+                "e2e_index_qps": (nq * e2e_steps / e2e_i) if e2e_i else None, "e2e_temporal_qps": nq * e2e_steps / e2e_t,
                 "gpu_launches_per_step": launches / h_steps, "visited_table_restarts": c["fallback_queries"],
                 "tie_replays": c.get("tie_replays", 0), "failures": c.get("failures", 0)}
             if rank == 0:
@@ -693,6 +734,10 @@ def run_ours(args, rank, world, local_rank):
                                 "fallback_queries_device_steps": exact["dev_counters"]["fallback_queries"],
                                 "rescored_per_query_per_shard_device_steps": exact["dev_counters"]["rescored"] / (nq * exact["dev_steps"]),
                                 "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
+                                "batches_in_flight": {"device": n_streams, "e2e_caller_threads": e2e_callers,
+                                                      "note": "consecutive 10k-query batches alternate over CUDA streams (device) / caller threads "
+                                                              "(e2e): the rescore, exchange and copies of one batch overlap the scan of the next; "
+                                                              "--streams 1 --callers 1 measures one batch at a time"},
                                 "l2": "inputs larger than L2: %.2f GB bf16 corpus per GPU streamed per step; %d query batches rotated"
                                       % (shard.shape[0] * DIM * 2 / 1e9, QUERY_BATCHES)},
                         e2e={"value": exact["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8},
@@ -812,6 +857,8 @@ def main():
     ap.add_argument("--no-graph-cache", action="store_true", help="neither read nor write the /tmp graph sidecar")
     ap.add_argument("--abi-group", action="store_true",
                     help="drive the N GPUs from ONE process through cm_group_* (NCCL inside the library) instead of torchrun ranks")
+    ap.add_argument("--streams", type=int, default=2, help="device-resident leg: CUDA streams the batches alternate over (1: one batch at a time)")
+    ap.add_argument("--callers", type=int, default=2, help="e2e leg (N = 1): caller threads sharing the index (1: one blocking call at a time)")
     ap.add_argument("--workload", default="exact", choices=["exact", "hnsw"],
                     help="which leg is the line's headline: exact (BASELINE configs[1], the metric's workload) or hnsw (configs[2])")
     ap.add_argument("--ef", type=int, default=0, help="hnsw: quote the headline at this ef instead of the recall frontier")

@@ -1313,7 +1313,7 @@ cm_status cm_index_dev_status(const cm_index* idx, uint64_t* failures, int reset
   uint32_t w[8];
   CM_CUDA(cudaMemcpy(w, idx->dev.status, sizeof w, cudaMemcpyDeviceToHost));  // waits for the work enqueued so far
   *failures = (uint64_t)w[0] + w[1];
-  if (reset) CM_CUDA(cudaMemset(idx->dev.status, 0, sizeof w));
+  if (reset) CM_CUDA(cudaMemset(idx->dev.status, 0, 2 * sizeof(uint32_t)));  // the work counters have their own reset
   return CM_OK;
 }
 

@@ -51,6 +51,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -948,6 +949,15 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.q_ctx = l.q_ctx;
   const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
   a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
+  // Leave room on the SM for one rescore CTA (K2, ~34 KB): a caller that pipelines batches over two streams then gets
+  // the rescore / exchange / merge of batch i for free under the scan of batch i + 1 — the scan is tensor-bound and
+  // touches 3 % of the DRAM bandwidth, the rescore is the opposite. Five stages (3 us of prefetch at full rate against
+  // ~1 us of L2 latency) measured the same as six. CM_SCAN_STAGES overrides (experiments).
+  if (l.k <= 16 && a.stages > 5) a.stages = 5;
+  if (const char* env = getenv("CM_SCAN_STAGES")) {
+    const uint32_t f = (uint32_t)atoi(env);
+    if (f >= 2 && f <= kMaxStages && fixed + (size_t)f * kStageBytes <= kMaxSmem) a.stages = f;
+  }
   if (a.stages < 2) return cudaErrorInvalidValue;
   const size_t smem = fixed + (size_t)a.stages * kStageBytes;
   auto kernel = biased ? scan_tc_kernel<true, false> : (l.pred ? scan_tc_kernel<false, true> : scan_tc_kernel<false, false>);
