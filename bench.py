@@ -398,7 +398,9 @@ def run_ours(args, rank, world, local_rank):
     q_host = [torch.from_numpy(queries_all[i * nq:(i + 1) * nq]).pin_memory() for i in range(QUERY_BATCHES)]
     q_dev = [q.to(dev) for q in q_host]
     n_streams = max(1, args.streams)
-    streams = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
+    # one notch above the default (= lowest) priority: the library runs each batch's tail (rescore, fallback) on a
+    # default-priority side stream, so the next batch's scan gets the SMs first and the tail fills in underneath
+    streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(n_streams)] if n_streams > 1 else []
     ids_s = [torch.empty((nq, K), dtype=torch.int32, device=dev) for _ in range(n_streams)]      # one result buffer per
     dist_s = [torch.empty((nq, K), dtype=torch.float32, device=dev) for _ in range(n_streams)]   # batch in flight
     ids_l, dist_l = ids_s[0], dist_s[0]

@@ -106,6 +106,14 @@ struct Workspace {
   DevBuf bias;                          // search_in_context: per-row temporal bias of the call
   DevBuf vmap, vmap_epoch;              // HNSW at large ef: visited byte maps in HBM (one slab per CTA) and their epochs
   cudaStream_t stream = nullptr;  // host-buffer variants
+  // Exact scan: everything after K1 (rescore, fallback, counters) runs on a LOW-priority side stream, forked from and
+  // joined back into the call's stream with events. For one caller stream nothing changes; a caller that keeps two
+  // batches in flight on two streams gets the tail of batch i scheduled UNDER the scan of batch i + 1 (the scan's blocks
+  // win the SMs first, a rescore CTA fits in the shared memory the scan leaves free). The default stream priority is
+  // already the lowest one, so it is the CALLER's streams that must sit a notch higher (bench.py creates them so; the
+  // host-buffer variants' own streams are created so).
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_scan = nullptr, ev_tail = nullptr;
   cudaEvent_t done = nullptr;     // completion of the last call that used this workspace
   cudaStream_t last_stream = nullptr;
   bool pending = false;           // `done` was recorded and may not have completed yet
@@ -115,9 +123,13 @@ struct Workspace {
                       &tc_state, &cand, &qflag, &bias, &vmap, &vmap_epoch})
       b->release();
     if (stream) cudaStreamDestroy(stream);
-    if (done) cudaEventDestroy(done);
+    if (tail_stream) cudaStreamDestroy(tail_stream);
+    for (cudaEvent_t* e : {&done, &ev_scan, &ev_tail}) {
+      if (*e) cudaEventDestroy(*e);
+      *e = nullptr;
+    }
     stream = nullptr;
-    done = nullptr;
+    tail_stream = nullptr;
   }
 };
 
@@ -175,7 +187,11 @@ struct WorkspaceLease {
   WorkspaceLease(const cm_index* idx, cudaStream_t stream, bool host_call)
       : pool((WorkspacePool*)idx->workspace_pool), ws(pool->acquire(stream, !host_call)), host(host_call) {
     if (host) {
-      if (!ws->stream) err = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+      if (!ws->stream) {  // one notch above the default priority: the low-priority tail streams (default priority is the
+        int lo = 0, hi = 0;  // lowest there is) then yield to the scans of other in-flight calls
+        err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&ws->stream, cudaStreamNonBlocking, hi < lo ? lo - 1 : lo);
+      }
       s = ws->stream;
     } else {
       s = stream;
@@ -355,6 +371,18 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
     ProfileScope prof(s);
     CM_CUDA(launch_scan_tc(d, sl, s));
   }
+  // fork: the tail of this batch goes to the workspace's low-priority stream
+  cudaStream_t caller = s;
+  if (!ws->tail_stream) {
+    int lo = 0, hi = 0;
+    CM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = lowest priority (numerically greatest)
+    CM_CUDA(cudaStreamCreateWithPriority(&ws->tail_stream, cudaStreamNonBlocking, lo));
+    CM_CUDA(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
+    CM_CUDA(cudaEventCreateWithFlags(&ws->ev_tail, cudaEventDisableTiming));
+  }
+  CM_CUDA(cudaEventRecord(ws->ev_scan, caller));
+  s = ws->tail_stream;
+  CM_CUDA(cudaStreamWaitEvent(s, ws->ev_scan, 0));
   RescoreLaunch rl;
   rl.qn = pq.qn;
   rl.ldq = pq.ld;
@@ -384,6 +412,9 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   }
   // chunk counters -> call totals; queries beyond what the fallback absorbed are counted in the status word
   CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, one_launch ? 0xFFFFFFFFu : kFlagCap, d.status + 1, s));
+  // join: whatever the caller enqueues next on its stream sees this batch's results
+  CM_CUDA(cudaEventRecord(ws->ev_tail, s));
+  CM_CUDA(cudaStreamWaitEvent(caller, ws->ev_tail, 0));
   return CM_OK;
 }
 
