@@ -1498,6 +1498,130 @@ static cm_status pred_knn_batch(const cm_index* idx, Workspace* ws, uint32_t q0,
 // scan of the layer's members against themselves, lower triangle, bf16-ranked, in batches of queries) — half the
 // work of an all-pairs join, and on clustered data the difference between a searchable graph and islands. The host
 // then selects and links like the reference (hnsw_build.cpp).
+// RAII for the build's temporaries on the device.
+struct DevTmp {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  ~DevTmp() {
+    if (p) cudaFree(p);
+  }
+  uint32_t* u32() const { return reinterpret_cast<uint32_t*>(p); }
+};
+
+// One layer of the GPU-assisted construction, entirely on the device once the members' rows are resident in `tmp`:
+// predecessor kNN -> each member's own list (select_diverse, phase A) -> reverse-edge lists by target (phase B). Only
+// the reverse-edge CSR is put together on the host in between (a counting sort over nm * M ids).
+static cm_status build_layer_on_device(cm_index* tmp, uint32_t k, uint32_t M, uint32_t cap, LayerLists* ll,
+                                       std::vector<uint32_t>* redo_rows, bool timing) {
+  const uint64_t nm = tmp->n;
+  const DeviceIndex& d = tmp->dev;
+  const uint32_t dim = tmp->dim;
+  auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now_s();
+  auto lap = [&](const char* what) {
+    if (timing && nm > 100000) std::fprintf(stderr, "[build_graph_gpu]   %-26s %.3f s\n", what, now_s() - t0);
+    t0 = now_s();
+  };
+  WorkspaceLease lease(tmp, nullptr, true);
+  if (lease.err != cudaSuccess) return cuda_fail(lease.err, "workspace lease");
+  Workspace* ws = lease.ws;
+  cudaStream_t s = lease.s;
+  DevTmp cand, own, own_deg, lists, deg, in_start_d, incoming_d, misc;
+  CM_CUDA(cand.alloc(nm * k * 4));
+  CM_CUDA(misc.alloc((2 + 4096) * 4));  // [0] work counter, [1..] too_big (count + ids)
+  const uint32_t batch = 16384;          // a multiple of the tile height: batches start on tile boundaries
+  CM_CUDA(ws->out_a.ensure((size_t)batch * k * 4));
+  for (uint64_t q0 = 0; q0 < nm; q0 += batch) {
+    const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nm - q0);
+    cm_status st = pred_knn_batch(tmp, ws, (uint32_t)q0, nb, k, cand.u32() + q0 * k, ws->out_a.as<float>(), s);
+    if (st != CM_OK) return st;
+  }
+  // members whose candidate buffer overflowed came back empty: exact predecessor scan on the host for those (rare)
+  std::vector<uint32_t> first(nm);
+  CM_CUDA(cudaMemcpy2DAsync(first.data(), 4, cand.p, (size_t)k * 4, 4, nm, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaStreamSynchronize(s));
+  lap("predecessor kNN");
+  redo_rows->clear();
+  for (uint64_t i = 1; i < nm; ++i)
+    if (first[i] == CM_NO_ID) redo_rows->push_back((uint32_t)i);
+  if (!redo_rows->empty()) {
+    const float* X = tmp->x.data();
+    std::vector<uint32_t> fixed(redo_rows->size() * (size_t)k, CM_NO_ID);
+    parallel_rows(redo_rows->size(), [&](uint64_t r) {
+      const uint32_t i = (*redo_rows)[r];
+      std::vector<std::pair<float, uint32_t>> best;
+      best.reserve(i);
+      for (uint32_t p = 0; p < i; ++p) best.emplace_back(dist_prepared_host(X + (uint64_t)p * dim, X + (uint64_t)i * dim, dim), p);
+      const size_t kk = std::min<size_t>(k, best.size());
+      std::partial_sort(best.begin(), best.begin() + (long)kk, best.end());
+      for (size_t c = 0; c < kk; ++c) fixed[r * k + c] = best[c].second;
+    });
+    for (size_t r = 0; r < redo_rows->size(); ++r)
+      CM_CUDA(cudaMemcpyAsync(cand.u32() + (uint64_t)(*redo_rows)[r] * k, &fixed[r * k], (size_t)k * 4, cudaMemcpyHostToDevice, s));
+    CM_CUDA(cudaStreamSynchronize(s));
+  }
+  // phase A: every member's own list
+  CM_CUDA(own.alloc(nm * M * 4));
+  CM_CUDA(own_deg.alloc(nm * 4));
+  CM_CUDA(cudaMemsetAsync(misc.p, 0, (2 + 4096) * 4, s));
+  SelectDiverseLaunch a;
+  a.n_items = (uint32_t)nm;
+  a.m = M;
+  a.cand = cand.u32();
+  a.width = k;
+  a.out = own.u32();
+  a.out_deg = own_deg.u32();
+  a.work_counter = misc.u32();
+  a.too_big = misc.u32() + 1;
+  a.too_big_cap = 4095;
+  CM_CUDA(launch_select_diverse(d, a, s));
+  ll->own_width = M;
+  ll->own.resize(nm * M);
+  ll->own_deg.resize(nm);
+  CM_CUDA(cudaMemcpyAsync(ll->own.data(), own.p, nm * M * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaMemcpyAsync(ll->own_deg.data(), own_deg.p, nm * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaStreamSynchronize(s));
+  lap("own lists (device select)");
+  build_incoming_csr(ll->own.data(), ll->own_deg.data(), nm, M, &ll->in_start, &ll->incoming);
+  lap("reverse-edge CSR (host)");
+  // phase B: the reverse edges, selected once per target
+  CM_CUDA(in_start_d.alloc((nm + 1) * 4));
+  CM_CUDA(incoming_d.alloc(ll->incoming.size() * 4));
+  CM_CUDA(lists.alloc(nm * cap * 4));
+  CM_CUDA(deg.alloc(nm * 4));
+  CM_CUDA(cudaMemcpyAsync(in_start_d.p, ll->in_start.data(), (nm + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (!ll->incoming.empty())
+    CM_CUDA(cudaMemcpyAsync(incoming_d.p, ll->incoming.data(), ll->incoming.size() * 4, cudaMemcpyHostToDevice, s));
+  CM_CUDA(cudaMemsetAsync(misc.p, 0, (2 + 4096) * 4, s));
+  SelectDiverseLaunch b;
+  b.n_items = (uint32_t)nm;
+  b.m = cap;
+  b.own = own.u32();
+  b.own_deg = own_deg.u32();
+  b.own_width = M;
+  b.in_start = in_start_d.u32();
+  b.incoming = incoming_d.u32();
+  b.out = lists.u32();
+  b.out_deg = deg.u32();
+  b.work_counter = misc.u32();
+  b.too_big = misc.u32() + 1;
+  b.too_big_cap = 4095;
+  CM_CUDA(launch_select_diverse(d, b, s));
+  ll->cap = cap;
+  ll->lists.resize(nm * cap);
+  ll->deg.resize(nm);
+  std::vector<uint32_t> big(1 + 4095);
+  CM_CUDA(cudaMemcpyAsync(ll->lists.data(), lists.p, nm * cap * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaMemcpyAsync(ll->deg.data(), deg.p, nm * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaMemcpyAsync(big.data(), misc.u32() + 1, big.size() * 4, cudaMemcpyDeviceToHost, s));
+  CM_CUDA(cudaStreamSynchronize(s));
+  if (big[0] > 4095) return fail(CM_ERR_CAPACITY_EXCEEDED, "more oversized reverse-edge lists than the build tracks");
+  ll->too_big.assign(big.begin() + 1, big.begin() + 1 + big[0]);
+  std::sort(ll->too_big.begin(), ll->too_big.end());
+  lap("reverse edges (device select)");
+  return CM_OK;
+}
+
 cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int device, int threads, uint32_t n_candidates) {
   if (!idx) return fail(CM_ERR_INVALID_ARGUMENT, "null index");
   if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -1507,6 +1631,9 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
   uint32_t C = n_candidates ? n_candidates : (uint32_t)std::min<uint64_t>(idx->config.index.ef_construction, 64);
   C = std::min(std::max(C, M + 1), 127u);
   const bool timing = getenv("CM_BUILD_TIMING") != nullptr;  // stage times on stderr (diagnostics)
+  const char* sel_env = getenv("CM_BUILD_SELECT");          // "host": select and link on the host (equivalence tests)
+  const uint32_t dim_pad = (dim + 7) & ~7u;
+  const bool device_select = !(sel_env && std::string(sel_env) == "host") && select_diverse_supported(dim_pad, 2 * M) && M >= 2;
   auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_stage = now_s();
   auto lap = [&](const char* what) {
@@ -1517,14 +1644,15 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
   layer_members(n, idx->config.index, layer_seed, &members);
   lap("layer draw");
   std::vector<LayerCandidates> layers(members.size());
+  std::vector<LayerLists> lists(members.size());
   for (size_t layer = 0; layer < members.size(); ++layer) {
     LayerCandidates& lc = layers[layer];
     lc.members.swap(members[layer]);
+    lists[layer].members = lc.members;
     const uint64_t nm = lc.members.size();
     if (nm <= 1) continue;
     const uint32_t k = (uint32_t)std::min<uint64_t>(C, nm - 1);
     lc.width = k;
-    lc.ids.assign(nm * k, CM_NO_ID);
     cm_index* tmp = new_index(idx->config, nm, dim);
     tmp->all_finite = idx->all_finite;
     if (layer == 0) {
@@ -1539,10 +1667,14 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
     std::vector<uint32_t> redo;  // members whose candidate buffer overflowed on the device
     if (st == CM_OK && !(tmp->all_finite && scan_tc_supported(tmp->dev, k)))
       st = fail(CM_ERR_STATE, "the GPU-assisted build needs the tensor-core scan (finite rows, at most 127 candidates)");
-    if (st == CM_OK) {
+    if (st == CM_OK && device_select) {
+      st = build_layer_on_device(tmp, k, M, layer == 0 ? 2 * M : M, &lists[layer], &redo, timing);
+      if (layer == 0) lap("layer 0 kNN + select + link");
+    } else if (st == CM_OK) {
+      lc.ids.assign(nm * k, CM_NO_ID);
       WorkspaceLease lease(tmp, nullptr, true);
       if (lease.err != cudaSuccess) st = cuda_fail(lease.err, "workspace lease");
-      const uint32_t batch = 16384;  // a multiple of the tile height: batches start on tile boundaries
+      const uint32_t batch = 16384;
       Workspace* ws = lease.ws;
       cudaError_t ce = cudaSuccess;
       if (st == CM_OK && ((ce = ws->out_ids.ensure((size_t)batch * k * 4)) != cudaSuccess || (ce = ws->out_a.ensure((size_t)batch * k * 4)) != cudaSuccess))
@@ -1555,33 +1687,36 @@ cm_status cm_index_build_graph_gpu(cm_index* idx, uint64_t layer_seed, int devic
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(lease.s);
         if (ce != cudaSuccess) st = cuda_fail(ce, "predecessor kNN batch");
       }
-    }
-    if (st == CM_OK)
-      for (uint64_t i = 1; i < nm; ++i)  // member 0 has no predecessor; anything else without candidates was flagged
-        if (lc.ids[i * k] == CM_NO_ID) redo.push_back((uint32_t)i);
-    if (layer == 0) lap("layer 0 predecessor kNN");
-    if (st == CM_OK && !redo.empty()) {  // rare: exact predecessor scan on the host for the flagged members
-      const float* X = tmp->x.data();
-      parallel_rows(redo.size(), [&](uint64_t r) {
-        const uint32_t i = redo[r];
-        std::vector<std::pair<float, uint32_t>> best;
-        best.reserve(i);
-        for (uint32_t p = 0; p < i; ++p) best.emplace_back(dist_prepared_host(X + (uint64_t)p * dim, X + (uint64_t)i * dim, dim), p);
-        const size_t kk = std::min<size_t>(k, best.size());
-        std::partial_sort(best.begin(), best.begin() + (long)kk, best.end());
-        for (size_t c = 0; c < kk; ++c) lc.ids[(uint64_t)i * k + c] = best[c].second;
-      });
+      if (st == CM_OK)
+        for (uint64_t i = 1; i < nm; ++i)  // member 0 has no predecessor; anything else without candidates was flagged
+          if (lc.ids[i * k] == CM_NO_ID) redo.push_back((uint32_t)i);
+      if (layer == 0) lap("layer 0 predecessor kNN");
+      if (st == CM_OK && !redo.empty()) {  // rare: exact predecessor scan on the host for the flagged members
+        const float* X = tmp->x.data();
+        parallel_rows(redo.size(), [&](uint64_t r) {
+          const uint32_t i = redo[r];
+          std::vector<std::pair<float, uint32_t>> best;
+          best.reserve(i);
+          for (uint32_t p = 0; p < i; ++p) best.emplace_back(dist_prepared_host(X + (uint64_t)p * dim, X + (uint64_t)i * dim, dim), p);
+          const size_t kk = std::min<size_t>(k, best.size());
+          std::partial_sort(best.begin(), best.begin() + (long)kk, best.end());
+          for (size_t c = 0; c < kk; ++c) lc.ids[(uint64_t)i * k + c] = best[c].second;
+        });
+      }
     }
     if (layer == 0) tmp->x.swap(idx->x);
     cm_index_free(tmp);
     if (st != CM_OK) return st;
-    if (layer > 0)  // subset-local -> global handles
+    if (!device_select && layer > 0)  // subset-local -> global handles
       for (uint32_t& v : lc.ids)
         if (v != CM_NO_ID) v = lc.members[v];
   }
   lap("upper layers (all)");
-  build_graph_from_candidates(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
-  lap("host select + link");
+  if (device_select)
+    build_graph_from_layer_lists(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, lists, &idx->graph);
+  else
+    build_graph_from_candidates(idx->x.data(), n, dim, idx->config.index, layer_seed, threads, layers, &idx->graph);
+  lap(device_select ? "write lists + reachability" : "host select + link");
   return CM_OK;
 }
 

@@ -84,6 +84,20 @@ void layer_members(uint64_t n, const cm_index_params& p, uint64_t seed, std::vec
 void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
                                  int threads, const std::vector<LayerCandidates>& layers, Graph* g);
 
+// Per-layer neighbor lists selected on the device (member-local indices), see build_select.cu / hnsw_build.cpp.
+struct LayerLists {
+  std::vector<uint32_t> members;
+  uint32_t cap = 0, own_width = 0;
+  std::vector<uint32_t> lists, deg;    // [members][cap], [members] — final lists (empty: the layer has no edges)
+  std::vector<uint32_t> own, own_deg;  // [members][own_width], [members] — each member's own pick (phase A)
+  std::vector<uint32_t> in_start, incoming;
+  std::vector<uint32_t> too_big;       // items the kernel left to the host
+};
+void build_incoming_csr(const uint32_t* own, const uint32_t* own_deg, uint64_t nm, uint32_t width,
+                        std::vector<uint32_t>* in_start, std::vector<uint32_t>* incoming);
+void build_graph_from_layer_lists(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
+                                  int threads, const std::vector<LayerLists>& layers, Graph* g);
+
 // Host metric kernels (same arithmetic as src/metric.rs; see metric_host.h).
 void preprocess_row(const float* v, uint32_t n, float* out);
 float dist_prepared_host(const float* a, const float* b, uint32_t n);  // distance_prepared, AVX2+FMA lane order

@@ -600,6 +600,75 @@ void build_graph_from_candidates(const float* x, uint64_t n, uint32_t dim, const
   g->built = true;
 }
 
+// Reverse-edge lists by target (member-local indices): for every member, the members that chose it, in ascending
+// source order — what `add_backlink` sees when nodes are inserted in handle order.
+void build_incoming_csr(const uint32_t* own, const uint32_t* own_deg, uint64_t nm, uint32_t width,
+                        std::vector<uint32_t>* in_start, std::vector<uint32_t>* incoming) {
+  in_start->assign(nm + 1, 0);
+  for (uint64_t i = 0; i < nm; ++i)
+    for (uint32_t j = 0; j < own_deg[i]; ++j) ++(*in_start)[own[i * width + j] + 1];
+  for (uint64_t i = 0; i < nm; ++i) (*in_start)[i + 1] += (*in_start)[i];
+  incoming->resize((*in_start)[nm]);
+  std::vector<uint32_t> fill(in_start->begin(), in_start->end() - 1);
+  for (uint64_t i = 0; i < nm; ++i)
+    for (uint32_t j = 0; j < own_deg[i]; ++j) (*incoming)[fill[own[i * width + j]]++] = (uint32_t)i;
+}
+
+// The graph from per-layer neighbor lists selected on the device (build_select.cu): write them into the flat layout,
+// select the few items the kernel left to the host (hubs with more incoming edges than it sorts) with the same code the
+// host path uses, then entry point and reachability as in build_graph_from_candidates.
+void build_graph_from_layer_lists(const float* x, uint64_t n, uint32_t dim, const cm_index_params& p, uint64_t seed,
+                                  int threads, const std::vector<LayerLists>& layers, Graph* g) {
+  init_layout(n, p, seed, g);
+  Builder b;
+  b.x = x;
+  b.n = n;
+  b.dim = dim;
+  b.M = (uint32_t)p.max_connections;
+  b.efC = (uint32_t)p.ef_construction;
+  b.cap0 = g->cap0;
+  b.capU = g->capU;
+  b.g = g;
+  b.mt = false;
+  for (uint32_t layer = 0; layer < layers.size(); ++layer) {
+    const LayerLists& ll = layers[layer];
+    const uint64_t nm = ll.members.size();
+    if (ll.deg.empty()) continue;
+    parallel_range(nm, threads, [&](uint64_t i, Scratch&) {
+      uint32_t* deg;
+      uint32_t* l = b.list_ptr(ll.members[i], layer, &deg);
+      const uint32_t d = ll.deg[i];
+      for (uint32_t j = 0; j < d; ++j) l[j] = ll.members[ll.lists[i * ll.cap + j]];
+      *deg = d;
+    });
+    const uint32_t cap = b.cap(layer);
+    parallel_range(ll.too_big.size(), threads, [&](uint64_t t, Scratch& s) {
+      const uint32_t i = ll.too_big[t];
+      const uint32_t v = ll.members[i];
+      s.nbuf.clear();
+      const uint32_t od = ll.own_deg[i];
+      for (uint32_t j = 0; j < od; ++j) s.nbuf.push_back(ll.members[ll.own[(uint64_t)i * ll.own_width + j]]);
+      for (uint32_t e = ll.in_start[i]; e < ll.in_start[i + 1]; ++e) {
+        const uint32_t u = ll.members[ll.incoming[e]];
+        if (std::find(s.nbuf.begin(), s.nbuf.begin() + od, u) == s.nbuf.begin() + od) s.nbuf.push_back(u);
+      }
+      s.with_d.clear();
+      for (uint32_t u : s.nbuf) s.with_d.push_back(pack(dist_prepared(b.row(u), b.row(v), dim), u));
+      std::sort(s.with_d.begin(), s.with_d.end());
+      b.select_diverse(s.with_d.data(), s.with_d.size(), cap, s);
+      uint32_t* deg;
+      uint32_t* l = b.list_ptr(v, layer, &deg);
+      std::memcpy(l, s.result.data(), s.result.size() * sizeof(uint32_t));
+      *deg = (uint32_t)s.result.size();
+    });
+  }
+  for (uint64_t i = 0; i < n; ++i)
+    if (g->entry == kEmptyEntry || g->top_layer[i] > (uint32_t)(g->entry >> 32)) g->entry = ((uint64_t)g->top_layer[i] << 32) | i;
+  b.entry.store(g->entry);
+  repair_layer0_reachability(b);
+  g->built = true;
+}
+
 // Layer-0 nodes a search from the entry point cannot arrive at (see mark_reachable). 0 for an empty graph.
 uint64_t count_unreachable(const Graph& g) {
   std::vector<uint8_t> seen;

@@ -131,6 +131,30 @@ cudaError_t launch_fallback_exact(const float* qn, uint32_t ldq, const uint32_t*
                                   const uint8_t* deleted, uint32_t k, uint32_t* ids, float* dist, int sm_count,
                                   cudaStream_t s);
 
+// `select_diverse` (src/index/lockfree_hnsw.rs:205-240) for a batch of (center row, candidate list) items on the device,
+// bit-identical to the host code of hnsw_build.cpp (see build_select.cu). Item i's center is row i of `ix.x32`; its
+// candidates are either cand[i][0..width) (CM_NO_ID padded; phase A: a node's own list, m = M) or own[i][0..own_deg[i])
+// followed by incoming[in_start[i]..in_start[i+1]) minus duplicates (phase B: the reverse edges, m = cap(layer); items
+// that fit are written out unselected, like add_backlink's append branch). Items with more than 1024 candidates are
+// listed in too_big ([0] = count) for the host.
+struct SelectDiverseLaunch {
+  uint32_t n_items = 0, m = 0;
+  const uint32_t* cand = nullptr;
+  uint32_t width = 0;
+  const uint32_t* own = nullptr;
+  const uint32_t* own_deg = nullptr;
+  uint32_t own_width = 0;
+  const uint32_t* in_start = nullptr;
+  const uint32_t* incoming = nullptr;
+  uint32_t* out = nullptr;       // [n_items][m]
+  uint32_t* out_deg = nullptr;   // [n_items]
+  uint32_t* too_big = nullptr;   // [1 + too_big_cap], zeroed by the caller
+  uint32_t too_big_cap = 0;
+  uint32_t* work_counter = nullptr;
+};
+bool select_diverse_supported(uint32_t dim_pad, uint32_t m);
+cudaError_t launch_select_diverse(const DeviceIndex& ix, const SelectDiverseLaunch& l, cudaStream_t s);
+
 // Copy the rows named by a device list into a compact matrix.
 cudaError_t launch_gather_rows(const float* src, uint32_t ld, const uint32_t* list, const uint32_t* count,
                                uint32_t cap, float* dst, cudaStream_t s);

@@ -686,3 +686,37 @@ def test_async_calls_on_different_streams_do_not_share_scratch():
     assert st.dev_status() == 0
     c = st.dev_counters()
     assert c["fallback_queries"] == 0 and c["rescored"] >= 10 * 1000 * 3
+
+
+@pytest.mark.parametrize("n,dim,M,kind", [(30000, 768, 16, "emb"), (20000, 64, 8, "uni"), (12000, 100, 16, "clustered")])
+def test_device_select_builds_the_same_graph_as_the_host_select(n, dim, M, kind):
+    """SURVEY.md §8f N2 on the device: `select_diverse` and the reverse-edge re-selection (src/index/lockfree_hnsw.rs:
+    205-280) run as one kernel over (center, candidates) items with the reference's exact fp32 arithmetic. From the same
+    predecessor candidates the device must produce BIT-FOR-BIT the lists the host code produces: every list of every
+    layer of every node, the entry point and the reachability verdict."""
+    import os
+    if kind == "emb":
+        data, _ = datasets.embedding_dataset(n, 1, 0x5E1)
+    elif kind == "uni":
+        data, _ = datasets.uniform_dataset(n, 1, dim, 0x5E1)
+    else:
+        rng = np.random.default_rng(5)
+        centres = rng.normal(size=(150, dim)).astype(np.float32)
+        data = (np.repeat(centres, n // 150, axis=0) + 0.05 * rng.normal(size=(n // 150 * 150, dim))).astype(np.float32)
+        data = data[rng.permutation(len(data))]
+        data[::50] = data[7]                                      # a hub: hundreds of rows identical to one row
+    cfg = default_config(dimensions=dim, max_connections=M, ef_construction=64)
+    os.environ["CM_BUILD_SELECT"] = "host"
+    try:
+        host = ChronoMindB200.from_matrix(data, cfg).build_graph_gpu(77, 0, 8)
+    finally:
+        del os.environ["CM_BUILD_SELECT"]
+    dev = ChronoMindB200.from_matrix(data, cfg).build_graph_gpu(77, 0, 8)
+    assert dev.check_invariants() == 0 and host.check_invariants() == 0
+    assert dev.entry() == host.entry() and dev.unreachable() == host.unreachable() == 0
+    for h in range(len(data)):
+        t = host.top_layer(h)
+        assert dev.top_layer(h) == t
+        for layer in range(t + 1):
+            a, b = dev.neighbors(h, layer), host.neighbors(h, layer)
+            assert np.array_equal(a, b), (h, layer, a, b)
