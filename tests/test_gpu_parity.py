@@ -699,7 +699,8 @@ def test_device_select_builds_the_same_graph_as_the_host_select(n, dim, M, kind)
         data, _ = datasets.embedding_dataset(n, 1, 0x5E1)
     elif kind == "uni":
         data, _ = datasets.uniform_dataset(n, 1, dim, 0x5E1)
-    else:
+        data[::8] = data[3]                                       # 2,500 copies of one row: targets with more incoming edges
+    else:                                                         # than the kernel sorts go to the host (too_big)
         rng = np.random.default_rng(5)
         centres = rng.normal(size=(150, dim)).astype(np.float32)
         data = (np.repeat(centres, n // 150, axis=0) + 0.05 * rng.normal(size=(n // 150 * 150, dim))).astype(np.float32)
