@@ -505,16 +505,23 @@ def run_ours(args, rank, world, local_rank):
             for i in range(steps):
                 out[0] = step_fn(warmup + i)
         else:
+            errors = []
+
             def worker(t):
-                for i in range(t, steps, callers):
-                    r = step_fn(warmup + i)
-                    if i == steps - 1:
-                        out[0] = r
+                try:
+                    for i in range(t, steps, callers):
+                        r = step_fn(warmup + i)
+                        if i == steps - 1:
+                            out[0] = r
+                except BaseException as e:                       # noqa: BLE001 — re-raised on the timing thread
+                    errors.append(e)
             ts = [threading.Thread(target=worker, args=(t,)) for t in range(callers)]
             for t in ts:
                 t.start()
             for t in ts:
                 t.join()
+            if errors:
+                raise errors[0]
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
         if sampler:
