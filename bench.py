@@ -554,11 +554,15 @@ def run_ours(args, rank, world, local_rank):
 
         # Pass 1, one batch in flight: the dominant kernel's own duration (CUDA events around each launch) for the roofline.
         ms_seq, res, launches, (kernel_ms, kernel_n) = timed_device(step_device, args.warmup, args.steps, pipelined=False)
-        ms, kernel_ms_pipe, kernel_n_pipe = ms_seq, None, None
+        ms, kernel_ms_pipe, kernel_n_pipe, ms_pipe, in_flight = ms_seq, None, None, None, 1
         if n_streams > 1:
-            # Pass 2, two batches in flight (the headline): same K steps over alternating streams. A kernel's event bracket
-            # now also contains whatever co-runs with it, so it is reported but not used for the roofline.
-            ms, res, launches, (kernel_ms_pipe, kernel_n_pipe) = timed_device(step_device, args.warmup, args.steps, pipelined=True)
+            # Pass 2, two batches in flight: same K steps over alternating streams. A kernel's event bracket now also
+            # contains whatever co-runs with it, so it is reported but not used for the roofline. The headline quotes the
+            # faster of the two serving modes and says which (overlap pays when the per-batch tail is a visible share of
+            # the step — small shards; with long scans on many ranks the desynchronised collectives cost more than it hides).
+            ms_pipe, res_p, launches_p, (kernel_ms_pipe, kernel_n_pipe) = timed_device(step_device, args.warmup, args.steps, pipelined=True)
+            if ms_pipe < ms_seq:
+                ms, res, launches, in_flight = ms_pipe, res_p, launches_p, n_streams
         last_batch = (args.warmup + args.steps - 1) % QUERY_BATCHES
         dev_ids = res[0].cpu().numpy().view(np.uint32).copy()      # what the timed device path returned last
         dev_dist = res[1].cpu().numpy().copy()
@@ -578,7 +582,7 @@ def run_ours(args, rank, world, local_rank):
         burst = peaks.get("bf16_tflops") or 1650.0
         sustained = peaks.get("bf16_tflops_sustained") or 1400.0
         exact = {
-            "ms": ms, "ms_seq": ms_seq, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
+            "ms": ms, "ms_seq": ms_seq, "ms_pipe": ms_pipe, "in_flight": in_flight, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
             "dev_ids": dev_ids, "dev_dist": dev_dist, "last_batch": last_batch, "tc": tc, "unresolved": unresolved + unresolved_status,
             "counters": counters, "dev_counters": dev_ctr, "dev_steps": args.warmup + args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
@@ -590,8 +594,8 @@ def run_ours(args, rank, world, local_rank):
                                          % (shard.shape[0] * DIM * 2 + nq * DIM * 2),
                          "kernel": "scan_tc (tcgen05 bf16)" if tc else "k_exact_dist (fp32 CUDA cores, bit-exact chain)",
                          "kernel_ms_avg": kern_avg_ms, "kernel_launches_per_step": kernel_n / args.steps,
-                         "timed_in": "a one-batch-in-flight pass of the same K steps (%.3f ms/step); in the headline's two-in-flight pass the "
-                                     "kernel's event bracket also holds the previous batch's co-running tail: %s ms"
+                         "timed_in": "the one-batch-in-flight pass of K steps (%.3f ms/step); in the two-in-flight pass the kernel's "
+                                     "event bracket also holds the previous batch's co-running tail: %s ms"
                                      % (ms_seq / args.steps, ("%.3f" % (kernel_ms_pipe / max(kernel_n_pipe, 1))) if kernel_ms_pipe else "n/a")
                                      if n_streams > 1 else "the timed region",
                          "algorithmic_flop_per_launch": flops_per_launch,
@@ -753,9 +757,11 @@ def run_ours(args, rank, world, local_rank):
                                 "fallback_queries_device_steps": exact["dev_counters"]["fallback_queries"],
                                 "rescored_per_query_per_shard_device_steps": exact["dev_counters"]["rescored"] / (nq * exact["dev_steps"]),
                                 "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
-                                "batches_in_flight": {"device": n_streams, "e2e_caller_threads": e2e_callers,
+                                "batches_in_flight": {"device": exact["in_flight"], "e2e_caller_threads": e2e_callers,
                                                       "device_qps_one_in_flight": nq * args.steps / (exact["ms_seq"] * 1e-3),
                                                       "ms_per_step_one_in_flight": exact["ms_seq"] / args.steps,
+                                                      "device_qps_two_in_flight": (nq * args.steps / (exact["ms_pipe"] * 1e-3)) if exact["ms_pipe"] else None,
+                                                      "headline": "the faster of the two passes (both K timed steps after W warm-up steps)",
                                                       "note": "consecutive 10k-query batches alternate over CUDA streams (device) / caller threads "
                                                               "(e2e): the rescore, exchange and copies of one batch overlap the scan of the next; "
                                                               "--streams 1 --callers 1 measures one batch at a time"},
