@@ -3,7 +3,7 @@
     python -m chronomind_b200 query --file store.chrono --vector "[0.1, 0.2, 0.3, 0.4]" [--limit 10]
                                     [--context LABEL] [--normalize] [--device 0] [--seed S] [--threads T] [--build gpu|host]
 
-Loads the snapshot (`load_snapshot`, src/persistence.rs:73-123), rebuilds the HNSW graph — GPU-assisted by default,
+Loads the snapshot (`load_snapshot`, src/persistence.rs:73-123), rebuilds the HNSW graph — GPU-assisted by default (predecessor kNN, select and link on the device),
 `--build host` replays the reference's one-by-one insertion — or reads the `<file>.graph` sidecar when present,
 uploads to the GPU and prints the reference
 CLI's lines. There is no CPU search path: without a CUDA device the command fails.
