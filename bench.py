@@ -568,7 +568,12 @@ def run_ours(args, rank, world, local_rank):
         dev_dist = res[1].cpu().numpy().copy()
         unresolved_status = st.dev_status()                        # queries the async path could not resolve (0 normally)
         dev_ctr = st.dev_counters()                                # of every device-resident step so far (warm-up included)
-        e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps, callers=e2e_callers)
+        e2e_s, _ = timed_host(step_e2e, args.warmup, args.steps, callers=1)
+        e2e_modes = {"1": nq * args.steps / e2e_s}
+        if e2e_callers > 1:                                    # both serving modes are timed; the line quotes the faster
+            e2e_s2, _ = timed_host(step_e2e, args.warmup, args.steps, callers=e2e_callers)
+            e2e_modes[str(e2e_callers)] = nq * args.steps / e2e_s2
+            e2e_s = min(e2e_s, e2e_s2)
         if world == 1:
             step_e2e(0)                                            # once more on THIS thread: its counters are thread-local
         counters = engine.last_counters() if world == 1 else {}    # of the last host-buffer call (the e2e leg)
@@ -582,7 +587,7 @@ def run_ours(args, rank, world, local_rank):
         burst = peaks.get("bf16_tflops") or 1650.0
         sustained = peaks.get("bf16_tflops_sustained") or 1400.0
         exact = {
-            "ms": ms, "ms_seq": ms_seq, "ms_pipe": ms_pipe, "in_flight": in_flight, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
+            "ms": ms, "ms_seq": ms_seq, "ms_pipe": ms_pipe, "in_flight": in_flight, "e2e_modes": e2e_modes, "qps": nq * args.steps / (ms * 1e-3), "e2e_qps": nq * args.steps / e2e_s, "launches": launches,
             "dev_ids": dev_ids, "dev_dist": dev_dist, "last_batch": last_batch, "tc": tc, "unresolved": unresolved + unresolved_status,
             "counters": counters, "dev_counters": dev_ctr, "dev_steps": args.warmup + args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
@@ -757,7 +762,7 @@ def run_ours(args, rank, world, local_rank):
                                 "fallback_queries_device_steps": exact["dev_counters"]["fallback_queries"],
                                 "rescored_per_query_per_shard_device_steps": exact["dev_counters"]["rescored"] / (nq * exact["dev_steps"]),
                                 "parallelism": "corpus sharded by id over %d GPU(s), NCCL allgather + device merge" % world if world > 1 else "1 GPU",
-                                "batches_in_flight": {"device": exact["in_flight"], "e2e_caller_threads": e2e_callers,
+                                "batches_in_flight": {"device": exact["in_flight"], "e2e_qps_by_caller_threads": exact["e2e_modes"],
                                                       "device_qps_one_in_flight": nq * args.steps / (exact["ms_seq"] * 1e-3),
                                                       "ms_per_step_one_in_flight": exact["ms_seq"] / args.steps,
                                                       "device_qps_two_in_flight": (nq * args.steps / (exact["ms_pipe"] * 1e-3)) if exact["ms_pipe"] else None,
