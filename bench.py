@@ -494,24 +494,20 @@ def run_ours(args, rank, world, local_rank):
         (`&self` + Send + Sync; the reference's own benches time search from T threads, benches/comparison.rs:125-139) —
         one thread's H2D / D2H then overlaps another's kernels. Every call still moves its own batch in and its own
         result out inside the timed region. Returns (seconds, result of the last call)."""
-        for i in range(min(warmup, 2)):
-            step_fn(i)
-        barrier()
-        if sampler:
-            sampler.region(True)
         out = [None]
-        t0 = time.perf_counter()
-        if callers <= 1:
-            for i in range(steps):
-                out[0] = step_fn(warmup + i)
-        else:
+
+        def run(first, count):
+            if callers <= 1:
+                for i in range(first, first + count):
+                    out[0] = step_fn(i)
+                return
             errors = []
 
             def worker(t):
                 try:
-                    for i in range(t, steps, callers):
-                        r = step_fn(warmup + i)
-                        if i == steps - 1:
+                    for i in range(first + t, first + count, callers):
+                        r = step_fn(i)
+                        if i == first + count - 1:
                             out[0] = r
                 except BaseException as e:                       # noqa: BLE001 — re-raised on the timing thread
                     errors.append(e)
@@ -522,6 +518,14 @@ def run_ours(args, rank, world, local_rank):
                 t.join()
             if errors:
                 raise errors[0]
+        # warm up at the SAME concurrency: every caller thread's workspace (hundreds of MB of scratch, allocated on first
+        # use) must exist before the timed region, not be cudaMalloc'ed inside it
+        run(0, max(min(warmup, 3), 2 * callers))
+        barrier()
+        if sampler:
+            sampler.region(True)
+        t0 = time.perf_counter()
+        run(warmup, steps)
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
         if sampler:
