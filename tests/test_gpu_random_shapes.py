@@ -61,11 +61,16 @@ def test_random_shapes_exact_and_hnsw_match_the_oracle(seed):
     assert c["dist_evals"] == int(octr[0]) and c["expansions"] == int(octr[1]) and c["list_entries"] == int(octr[2]), seed
     assert c["failures"] == 0
     assert not dele[hi[hi != NO_ID]].any()
-    # exhaustive ef: the index must equal the linear scan exactly (tests/property_test.rs:196-229)
+    # exhaustive ef (tests/property_test.rs:196-229): the traversal must equal the oracle's, and — whenever the graph the
+    # reference's own insertion built reaches every live node (duplicate rows can leave a node without an incoming edge:
+    # `select_diverse` rejects a candidate at distance 0 from a chosen one) — the linear scan exactly
     if n <= 1000:
         live = int((dele == 0).sum())
         efx = min(1024, n + 8)
         xi, xd = st.search_index(q[:3], efx, efx)
-        li, ld = oracle.brute_force(prepared, q[:3], efx, mode="prepared", deleted=dele)
+        ei, ed, _, _ = orc.search_batch(q[:3], efx, efx)
+        assert np.array_equal(xi, ei) and np.array_equal(bits(xd), bits(ed)), seed
         reach = min(live, efx)
-        assert np.array_equal(xi[:, :reach], li[:, :reach]) and np.array_equal(bits(xd[:, :reach]), bits(ld[:, :reach])), seed
+        if np.all((ei != NO_ID).sum(axis=1) == reach):
+            li, ld = oracle.brute_force(prepared, q[:3], efx, mode="prepared", deleted=dele)
+            assert np.array_equal(xi[:, :reach], li[:, :reach]) and np.array_equal(bits(xd[:, :reach]), bits(ld[:, :reach])), seed
