@@ -104,6 +104,7 @@ struct Workspace {
   DevBuf qraw, qn, D, pool_ids, pool_dist, out_ids, out_a, out_b, small, gtable, qnorm, qctx;
   DevBuf qbf16, tc_state, cand, qflag;  // tensor-core scan: bf16 queries, tau/count arrays, candidates, fallback queries
   DevBuf bias;                          // search_in_context: per-row temporal bias of the call
+  DevBuf ctxsort;                       // search_in_context: query order / grouped context ids / per-pair tile ranges
   DevBuf vmap, vmap_epoch;              // HNSW at large ef: visited byte maps in HBM (one slab per CTA) and their epochs
   cudaStream_t stream = nullptr;  // host-buffer variants
   // Exact scan: everything after K1 (rescore, fallback, counters) runs on a LOW-priority side stream, forked from and
@@ -120,7 +121,7 @@ struct Workspace {
   unsigned hnsw_grid = 0;
   void release() {
     for (DevBuf* b : {&qraw, &qn, &D, &pool_ids, &pool_dist, &out_ids, &out_a, &out_b, &small, &gtable, &qnorm, &qctx, &qbf16,
-                      &tc_state, &cand, &qflag, &bias, &vmap, &vmap_epoch})
+                      &tc_state, &cand, &qflag, &bias, &ctxsort, &vmap, &vmap_epoch})
       b->release();
     if (stream) cudaStreamDestroy(stream);
     if (tail_stream) cudaStreamDestroy(tail_stream);
@@ -229,7 +230,8 @@ constexpr size_t kSmallBytes = 256 + kFlagCap * 4;
 static void free_device(DeviceIndex& d) {
   if (d.device < 0) return;
   cudaSetDevice(d.device);
-  for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.xraw, (void*)d.norm2_raw, (void*)d.ctx,
+  for (void* p : {(void*)d.x32, d.xbf16, (void*)d.deleted, (void*)d.xraw, (void*)d.norm2_raw, (void*)d.ctx, d.xbf16_ctx,
+                  (void*)d.ctx_sorted, (void*)d.perm, (void*)d.inv_perm,
                   (void*)d.ts_secs, (void*)d.ts_nanos, (void*)d.decay,
                   (void*)d.nbr0, (void*)d.deg0, (void*)d.upper_base, (void*)d.nbr_up, (void*)d.deg_up, (void*)d.status})
     if (p) cudaFree(p);
@@ -601,25 +603,41 @@ static cm_status search_in_context_tc(const cm_index* idx, Workspace* ws, const 
   tl_used_tc = true;
   tl_scan_bounded = true;  // no in-stream fallback here: any flagged query means "redo"
   tl_counters.exact_engine = 2;
+  // Context-sorted layout (two or more contexts): the scan runs over the copy of the rows ordered by context, the queries
+  // are grouped by context (device-side sort per chunk), and every query-tile pair only visits the tiles of its contexts.
+  const bool sorted = d.xbf16_ctx != nullptr;
+  const uint32_t chunk = sorted ? scan_tc_context_chunk() : kTcQueryChunk;
   const uint32_t nq_pad_all = scan_tc_pad_queries(nq);
+  uint32_t *order = nullptr, *qctx_sorted = nullptr, *pair_lo = nullptr, *pair_hi = nullptr;
+  if (sorted) {
+    const uint32_t n_pairs_all = ((nq + chunk - 1) / chunk) * (chunk / 256);
+    CM_CUDA(ws->ctxsort.ensure(((size_t)nq * 2 + (size_t)n_pairs_all * 2) * 4));
+    order = ws->ctxsort.as<uint32_t>();
+    qctx_sorted = order + nq;
+    pair_lo = qctx_sorted + nq;
+    pair_hi = pair_lo + n_pairs_all;
+    CM_CUDA(launch_group_queries_by_context(want, nq, order, qctx_sorted, s));
+    CM_CUDA(launch_context_pair_ranges(d, qctx_sorted, nq, pair_lo, pair_hi, s));
+  }
   CM_CUDA(ws->qn.ensure((size_t)nq * d.dim_pad * sizeof(float)));
   CM_CUDA(ws->qbf16.ensure((size_t)nq_pad_all * d.k_pad * 2));
   if (prepare_queries_fused_supported(q, d.dim)) {
-    CM_CUDA(launch_prepare_queries(q, nq, d.dim, ws->qn.as<float>(), d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, bad_row, s));
+    CM_CUDA(launch_prepare_queries(q, nq, d.dim, ws->qn.as<float>(), d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, bad_row, s,
+                                   order));
   } else {
     CM_CUDA(launch_preprocess_rows(q, nq, d.dim, d.dim, ws->qn.as<float>(), d.dim_pad, bad_row, s));
-    CM_CUDA(launch_to_bf16(ws->qn.as<float>(), nq, d.dim, d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, nullptr, false, s));
+    CM_CUDA(launch_to_bf16(ws->qn.as<float>(), nq, d.dim, d.dim_pad, ws->qbf16.p, nq_pad_all, d.k_pad, nullptr, false, s, order));
   }
   CM_CUDA(ws->qnorm.ensure((size_t)nq * 4));
   CM_CUDA(launch_pair_dot(q, q, nq, d.dim, d.dim, ws->qnorm.as<float>(), s));
   CM_CUDA(ws->bias.ensure(d.n_pad * sizeof(float)));
-  CM_CUDA(launch_context_bias(d, w, base, now_secs, now_nanos, ws->bias.as<float>(), s));
+  CM_CUDA(launch_context_bias(d, w, base, now_secs, now_nanos, ws->bias.as<float>(), s, sorted ? d.perm : nullptr));
   const uint32_t cap = scan_tc_cand_cap(k);
   CM_CUDA(ws->small.ensure(kSmallBytes));
   uint8_t* small = ws->small.as<uint8_t>();
   CM_CUDA(cudaMemsetAsync(small + 80, 0, 16, s));  // call totals
-  for (uint32_t q0 = 0; q0 < nq; q0 += kTcQueryChunk) {
-    const uint32_t nb = std::min(kTcQueryChunk, nq - q0);
+  for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+    const uint32_t nb = std::min(chunk, nq - q0);
     const uint32_t nq_pad = scan_tc_pad_queries(nb);
     CM_CUDA(ws->tc_state.ensure((size_t)nq_pad * 8));
     CM_CUDA(ws->cand.ensure((size_t)nq_pad * cap * 8));
@@ -637,18 +655,29 @@ static cm_status search_in_context_tc(const cm_index* idx, Workspace* ws, const 
     sl.cand = ws->cand.as<unsigned long long>();
     sl.cap = cap;
     sl.bias = ws->bias.as<float>();
-    sl.row_ctx = d.ctx;
-    sl.q_ctx = want + q0;
+    sl.row_ctx = sorted ? d.ctx_sorted : d.ctx;
+    sl.q_ctx = sorted ? qctx_sorted + q0 : want + q0;
+    if (sorted) {
+      sl.x_bf16 = d.xbf16_ctx;
+      sl.pair_lo = pair_lo + q0 / 256;
+      sl.pair_hi = pair_hi + q0 / 256;
+      // expected range of a pair: the contexts its 256 grouped queries span (if the batch spreads evenly over the
+      // contexts) plus one for the straddle, as a fraction of the corpus — only sizes the corpus splits
+      const uint64_t C = d.n_contexts;
+      const uint64_t span = std::min<uint64_t>(C, (256ull * C + nb - 1) / nb + 1);
+      sl.pair_tiles_avg = (uint32_t)std::max<uint64_t>(1, (d.n_pad / 256) * span / C);
+    }
     {
       ProfileScope prof(s);
       CM_CUDA(launch_scan_tc(d, sl, s));
     }
     ContextRescoreLaunch rl;
-    rl.q_raw = q + (size_t)q0 * d.dim;
+    // (sorted: the scan's query i is the caller's row order[q0 + i]; inputs and outputs are addressed through it)
+    rl.q_raw = sorted ? q : q + (size_t)q0 * d.dim;
     rl.ldq = d.dim;
     rl.nq = nb;
     rl.k = k;
-    rl.qnorm2 = ws->qnorm.as<float>() + q0;
+    rl.qnorm2 = sorted ? ws->qnorm.as<float>() : ws->qnorm.as<float>() + q0;
     rl.w = w;
     rl.base = base;
     rl.now_secs = now_secs;
@@ -657,12 +686,16 @@ static cm_status search_in_context_tc(const cm_index* idx, Workspace* ws, const 
     rl.cand_cnt = cand_cnt;
     rl.cand = sl.cand;
     rl.cap = cap;
-    rl.ids = ids + (size_t)q0 * k;
-    rl.score = score + (size_t)q0 * k;
+    rl.ids = sorted ? ids : ids + (size_t)q0 * k;
+    rl.score = sorted ? score : score + (size_t)q0 * k;
     rl.rescored_total = reinterpret_cast<unsigned long long*>(small + 64);
     rl.flag_count = reinterpret_cast<uint32_t*>(small + 72);
     rl.flag_list = ws->qflag.as<uint32_t>();
     rl.flag_cap = nq_pad;
+    if (sorted) {
+      rl.perm = d.perm;
+      rl.q_order = order + q0;
+    }
     CM_CUDA(launch_rescore_context(d, rl, s));
     // every flagged query is unresolved here; the host-buffer caller (bad_row != nullptr) reads the count and redoes
     // the call, the asynchronous one reports through the status word
@@ -1001,7 +1034,7 @@ cm_status cm_index_sync_deleted(cm_index* idx) {
   uint32_t* handles = nullptr;
   CM_CUDA(cudaMalloc(&handles, m * 4));
   cudaError_t e = cudaMemcpy(handles, idx->pending_removed.data(), m * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = launch_apply_tombstones(handles, (uint32_t)m, d.deleted, d.xbf16, d.k_pad, nullptr);
+  if (e == cudaSuccess) e = launch_apply_tombstones(handles, (uint32_t)m, d.deleted, d.xbf16, d.k_pad, d.xbf16_ctx, d.inv_perm, nullptr);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(handles);
   if (e != cudaSuccess) return cuda_fail(e, "cm_index_sync_deleted");
@@ -1081,6 +1114,34 @@ cm_status cm_index_upload(cm_index* idx, int device) {
   d.k_pad = scan_tc_pad_k(d.dim);
   CM_CUDA(cudaMalloc(&d.xbf16, d.n_pad * d.k_pad * 2));
   CM_CUDA(launch_to_bf16(d.x32, n, d.dim, d.dim_pad, d.xbf16, d.n_pad, d.k_pad, n ? d.deleted : nullptr, true, nullptr));
+  d.n_contexts = 0;
+  if (!idx->ctx.empty() && n) {
+    // Context-sorted copy for `search_in_context`: rows ordered by (context, handle), so that a context is a contiguous
+    // row range and a batch of queries grouped by context only scans the tiles that hold its contexts.
+    std::vector<uint32_t> perm(n), inv(n);
+    for (uint64_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+    const std::vector<uint32_t>& cx = idx->ctx;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return cx[a] < cx[b]; });
+    idx->ctx_sorted.resize(n);
+    for (uint64_t p = 0; p < n; ++p) {
+      idx->ctx_sorted[p] = cx[perm[p]];
+      inv[perm[p]] = (uint32_t)p;
+      if (p == 0 || idx->ctx_sorted[p] != idx->ctx_sorted[p - 1]) ++d.n_contexts;
+    }
+    // (one context: the plain layout already is the sorted one; CM_CONTEXT_UNSORTED=1 keeps the mask-only scan, for A/B runs)
+    if (d.n_contexts >= 2 && !getenv("CM_CONTEXT_UNSORTED")) {
+      CM_CUDA(cudaMalloc(&d.perm, d.n_pad * 4));
+      CM_CUDA(cudaMalloc(&d.inv_perm, rows * 4));
+      CM_CUDA(cudaMalloc(&d.ctx_sorted, d.n_pad * 4));
+      CM_CUDA(cudaMemset(d.perm, 0, d.n_pad * 4));
+      CM_CUDA(cudaMemset(d.ctx_sorted, 0xFF, d.n_pad * 4));
+      CM_CUDA(cudaMemcpy(d.perm, perm.data(), n * 4, cudaMemcpyHostToDevice));
+      CM_CUDA(cudaMemcpy(d.inv_perm, inv.data(), n * 4, cudaMemcpyHostToDevice));
+      CM_CUDA(cudaMemcpy(d.ctx_sorted, idx->ctx_sorted.data(), n * 4, cudaMemcpyHostToDevice));
+      CM_CUDA(cudaMalloc(&d.xbf16_ctx, d.n_pad * d.k_pad * 2));
+      CM_CUDA(launch_to_bf16(d.x32, n, d.dim, d.dim_pad, d.xbf16_ctx, d.n_pad, d.k_pad, d.deleted, true, nullptr, d.perm));
+    }
+  }
   const Graph& g = idx->graph;
   d.has_graph = g.built;
   if (g.built) {

@@ -145,7 +145,13 @@ struct DeviceIndex {
   // store-level context scan (`search_in_context`): raw (un-preprocessed) rows, their squared norms, context ids
   float* xraw = nullptr;      // [n][dim_pad], only when the index carries contexts
   float* norm2_raw = nullptr; // [n]
-  uint32_t* ctx = nullptr;    // [n]
+  uint32_t* ctx = nullptr;    // [n_pad] (padding = CM_NO_ID)
+  // the same rows SORTED BY CONTEXT (position p holds handle perm[p]): a query only has to scan the tiles of its context
+  void* xbf16_ctx = nullptr;     // [n_pad][k_pad] bf16, NaN-masked like xbf16
+  uint32_t* ctx_sorted = nullptr;  // [n_pad] context id per position (padding = CM_NO_ID)
+  uint32_t* perm = nullptr;      // [n_pad] position -> handle
+  uint32_t* inv_perm = nullptr;  // [n] handle -> position
+  uint32_t n_contexts = 0;       // distinct context ids (the sorted copy exists from 2 up)
   uint64_t* ts_secs = nullptr;
   uint32_t* ts_nanos = nullptr;
   float* decay = nullptr;
@@ -185,6 +191,7 @@ struct cm_index {
   std::vector<std::string> ext_ids; // snapshot-loaded only
   std::vector<float> raw;           // [n][dim] rows as stored (`StoredMemory.data`), only with contexts
   std::vector<uint32_t> ctx;        // [n] context id per handle (empty: no contexts)
+  std::vector<uint32_t> ctx_sorted; // context ids in (context, handle) order: the row ranges of the context-sorted device copy
   std::vector<std::string> ctx_labels;  // snapshot-loaded: id -> `MemoryAttributes.context`
   std::vector<float> importance;    // snapshot-loaded: `MemoryAttributes.importance`
   uint64_t live = 0;

@@ -19,17 +19,22 @@ cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uin
 // out16 [n_pad16][k_pad] bf16 (zero padded rows and columns) in one pass. Needs dim % 4 == 0, 16-byte aligned x and
 // rows short enough for 16 of them in shared memory (prepare_queries_fused_supported); x must not alias out.
 bool prepare_queries_fused_supported(const float* x, uint32_t dim);
+// src_rows (optional, device [n]): output row i is built from x row src_rows[i] (bad_row reports the x row).
 cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, float* out, uint32_t ld_out, void* out16,
-                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s);
+                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s,
+                                   const uint32_t* src_rows = nullptr);
 
 // fp32 -> bf16 copy of prepared rows into the tensor-core scan layout [n_pad][k_pad] (zero padded).
 // mask_rows (corpus copies): tombstoned rows (deleted[row] != 0) and padding rows score NaN in the scan.
+// row_map (optional, device [n]): output row i is x row row_map[i] (a permuted copy; `deleted` is indexed by x row).
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
-                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s);
+                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s,
+                           const uint32_t* row_map = nullptr);
 
 // Tombstone `m` handles on the device replica (deleted byte + NaN mask of the bf16 row).
+// (xbf16_ctx / inv_perm: the context-sorted bf16 copy and handle -> position in it, when the index carries contexts)
 cudaError_t launch_apply_tombstones(const uint32_t* handles, uint32_t m, uint8_t* deleted, void* xbf16, uint32_t k_pad,
-                                    cudaStream_t s);
+                                    void* xbf16_ctx, const uint32_t* inv_perm, cudaStream_t s);
 
 // distance_prepared for n row pairs (src/metric.rs:219-224).
 cudaError_t launch_pair_distance(const float* a, const float* b, uint64_t n, uint32_t dim, uint32_t ld, float* out,

@@ -102,7 +102,8 @@ constexpr int PQ_THREADS = 256;
 __global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __restrict__ x, uint32_t n, uint32_t dim,
                                                                 float* __restrict__ out, uint32_t ld_out,
                                                                 __nv_bfloat16* __restrict__ out16, uint32_t n_pad16,
-                                                                uint32_t k_pad, uint32_t* bad_row) {
+                                                                uint32_t k_pad, uint32_t* bad_row,
+                                                                const uint32_t* __restrict__ src_rows) {
   extern __shared__ __align__(128) unsigned char pq_smem[];  // PQ_ROWS x row_stride
   __shared__ unsigned long long mbar;
   __shared__ float norms[PQ_ROWS];
@@ -120,7 +121,8 @@ __global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __r
     if (tid == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * row_bytes) : "memory");
     if (tid < cnt) {
-      const float* src = x + (uint64_t)(row0 + tid) * dim;
+      // out row i = x row src_rows[i] when a gather order is given (queries grouped by context)
+      const float* src = x + (uint64_t)(src_rows ? src_rows[row0 + tid] : row0 + tid) * dim;
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
           ::"r"((uint32_t)__cvta_generic_to_shared(pq_smem + (size_t)tid * row_stride)), "l"(src), "r"(row_bytes), "r"(bar)
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __r
         if (c < dim) a = rs[c];
         if (c + 1 < dim) b = rs[c + 1];
         // validate_query (src/store.rs:386-390): remember the first row with a NaN/Inf component
-        if (bad_row && (!isfinite(a) || !isfinite(b))) atomicMin(bad_row, row);
+        if (bad_row && (!isfinite(a) || !isfinite(b))) atomicMin(bad_row, src_rows ? src_rows[row] : row);
         if (!degenerate) {
           if (c < dim) a = __fdiv_rn(a, nr);
           if (c + 1 < dim) b = __fdiv_rn(b, nr);
@@ -186,14 +188,15 @@ bool prepare_queries_fused_supported(const float* x, uint32_t dim) {
 }
 
 cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, float* out, uint32_t ld_out, void* out16,
-                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s) {
+                                   uint32_t n_pad16, uint32_t k_pad, uint32_t* bad_row, cudaStream_t s,
+                                   const uint32_t* src_rows) {
   const uint32_t rows = n_pad16 > n ? n_pad16 : n;
   if (rows == 0) return cudaSuccess;
   const size_t smem = (size_t)PQ_ROWS * (dim * 4 + 16);
   cudaError_t e = cudaFuncSetAttribute(k_prepare_queries, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   k_prepare_queries<<<(rows + PQ_ROWS - 1) / PQ_ROWS, PQ_THREADS, smem, s>>>(x, n, dim, out, ld_out, (__nv_bfloat16*)out16,
-                                                                             n_pad16, k_pad, bad_row);
+                                                                             n_pad16, k_pad, bad_row, src_rows);
   count_launch();
   return cudaGetLastError();
 }
@@ -205,25 +208,26 @@ cudaError_t launch_prepare_queries(const float* x, uint32_t n, uint32_t dim, flo
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_to_bf16(const float* __restrict__ x, uint64_t n, uint32_t dim, uint32_t ld_in,
                           __nv_bfloat16* __restrict__ out, uint64_t n_pad, uint32_t k_pad,
-                          const uint8_t* __restrict__ deleted, int mask_rows) {
+                          const uint8_t* __restrict__ deleted, int mask_rows, const uint32_t* __restrict__ row_map) {
   uint64_t total = n_pad * (uint64_t)(k_pad / 2);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t row = i / (k_pad / 2);
     uint32_t c = (uint32_t)(i % (k_pad / 2)) * 2;
     float a = 0.0f, b = 0.0f;
+    const uint64_t src = (row_map && row < n) ? row_map[row] : row;  // out row `row` = x row row_map[row] (permuted copies)
     if (row < n) {
-      if (c < dim) a = x[row * ld_in + c];
-      if (c + 1 < dim) b = x[row * ld_in + c + 1];
+      if (c < dim) a = x[src * ld_in + c];
+      if (c + 1 < dim) b = x[src * ld_in + c + 1];
     }
-    if (mask_rows && c == 0 && (row >= n || (deleted && deleted[row]))) a = __int_as_float(0x7FC00000);
+    if (mask_rows && c == 0 && (row >= n || (deleted && deleted[src]))) a = __int_as_float(0x7FC00000);
     reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
   }
 }
 
 cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld_in, void* out, uint64_t n_pad,
-                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s) {
+                           uint32_t k_pad, const uint8_t* deleted, bool mask_rows, cudaStream_t s, const uint32_t* row_map) {
   if (n_pad == 0) return cudaSuccess;
-  k_to_bf16<<<148 * 8, 256, 0, s>>>(x, n, dim, ld_in, (__nv_bfloat16*)out, n_pad, k_pad, deleted, mask_rows ? 1 : 0);
+  k_to_bf16<<<148 * 8, 256, 0, s>>>(x, n, dim, ld_in, (__nv_bfloat16*)out, n_pad, k_pad, deleted, mask_rows ? 1 : 0, row_map);
   count_launch();
   return cudaGetLastError();
 }
@@ -232,17 +236,20 @@ cudaError_t launch_to_bf16(const float* x, uint64_t n, uint32_t dim, uint32_t ld
 // tombstone byte the HNSW final-list filter and the fp32 scans read, and NaN-mask column 0 of the bf16 row so the
 // tensor-core scans never emit it again. The node keeps routing traffic, as in the reference.
 __global__ void k_apply_tombstones(const uint32_t* __restrict__ handles, uint32_t m, uint8_t* __restrict__ deleted,
-                                   __nv_bfloat16* __restrict__ xbf16, uint32_t k_pad) {
+                                   __nv_bfloat16* __restrict__ xbf16, uint32_t k_pad, __nv_bfloat16* __restrict__ xbf16_ctx,
+                                   const uint32_t* __restrict__ inv_perm) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const uint32_t h = handles[i];
     deleted[h] = 1;
     xbf16[(uint64_t)h * k_pad] = __float2bfloat16(__int_as_float(0x7FC00000));
+    if (xbf16_ctx) xbf16_ctx[(uint64_t)inv_perm[h] * k_pad] = __float2bfloat16(__int_as_float(0x7FC00000));  // context-sorted copy
   }
 }
 cudaError_t launch_apply_tombstones(const uint32_t* handles, uint32_t m, uint8_t* deleted, void* xbf16, uint32_t k_pad,
-                                    cudaStream_t s) {
+                                    void* xbf16_ctx, const uint32_t* inv_perm, cudaStream_t s) {
   if (m == 0) return cudaSuccess;
-  k_apply_tombstones<<<(m + 255) / 256, 256, 0, s>>>(handles, m, deleted, (__nv_bfloat16*)xbf16, k_pad);
+  k_apply_tombstones<<<(m + 255) / 256, 256, 0, s>>>(handles, m, deleted, (__nv_bfloat16*)xbf16, k_pad, (__nv_bfloat16*)xbf16_ctx,
+                                                     inv_perm);
   count_launch();
   return cudaGetLastError();
 }

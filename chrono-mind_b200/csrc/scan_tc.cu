@@ -71,6 +71,7 @@ constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kThreads = 256;
 constexpr uint32_t kSlotChunk = 8;  // candidate slots reserved per atomic
+constexpr uint32_t kCtxSortChunk = 16384;  // queries grouped by context per single-CTA sort (128 KB of keys)
 // Bound on |tensor-core bf16 score - fp32 reference dot| for (at most) unit-length rows of `dim` elements:
 //   operand rounding   both operands to bf16 (unit roundoff 2^-9): |sum(a^b^) - sum(ab)| <= (2^-8 + 2^-18) sum|ab| <= 0.0039101
 //   accumulation       every UMMA K-step adds 16 exact products into an fp32 accumulator of magnitude <= 1; allowing a
@@ -226,7 +227,19 @@ struct ScanArgs {
   const float* bias;             // [n_pad]
   const uint32_t* row_ctx;       // [n_pad]
   const uint32_t* q_ctx;         // [nq]
+  // per query-tile-pair tile range [pair_lo[m], pair_hi[m]) instead of [0, n_tiles): rows sorted by context, queries
+  // grouped by context — a pair only scans the tiles that hold its queries' contexts
+  const uint32_t* pair_lo;
+  const uint32_t* pair_hi;
 };
+
+// Tile range [t0, t1) of work unit (m, sp).
+__device__ __forceinline__ void unit_tiles(const ScanArgs& a, uint32_t m, uint32_t sp, uint32_t& t0, uint32_t& t1) {
+  const uint32_t lo = a.pair_lo ? a.pair_lo[m] : 0u;
+  const uint32_t len = a.pair_lo ? a.pair_hi[m] - lo : a.n_tiles;
+  t0 = lo + (uint32_t)((uint64_t)sp * len / a.splits);
+  t1 = lo + (uint32_t)((uint64_t)(sp + 1) * len / a.splits);
+}
 
 // Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists [k][128] | barriers | tmem ptr.
 // Both CTAs of a pair use the same offsets (the MMA descriptors and multicast commits rely on it).
@@ -319,8 +332,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
-        uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-        const uint32_t t1_all = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        uint32_t t0, t1_all;
+        unit_tiles(a, m, sp, t0, t1_all);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         const uint32_t t1 = kPred ? min(t1_all, a.q_base / BN + m + 1) : t1_all;  // predecessors: up to the diagonal tile
         const int32_t q_row = (int32_t)(m * PAIR_M + rank * BM);
@@ -349,8 +362,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t sp = u / a.m_pairs;
-        uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-        uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+        uint32_t t0, t1;
+        unit_tiles(a, u % a.m_pairs, sp, t0, t1);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         if (kPred) t1 = min(t1, a.q_base / BN + u % a.m_pairs + 1);  // predecessors: up to the diagonal tile
         for (uint32_t t = t0; t < t1; ++t) {
@@ -393,8 +406,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t u = cluster_id; u < units; u += n_clusters) {
       const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
-      uint32_t t0 = (uint32_t)((uint64_t)sp * a.n_tiles / a.splits);
-      uint32_t t1 = (uint32_t)((uint64_t)(sp + 1) * a.n_tiles / a.splits);
+      uint32_t t0, t1;
+      unit_tiles(a, m, sp, t0, t1);
       if (a.join) t0 = max(t0, m);  // self-join keeps row > query: tiles below the diagonal are skipped
       if (kPred) t1 = min(t1, a.q_base / BN + m + 1);  // predecessors: up to the diagonal tile
       const uint32_t q = m * PAIR_M + rank * BM + row_in_cta;
@@ -732,10 +745,64 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_context_bias(const unsigned long long* __restrict__ ts_secs, const uint32_t* __restrict__ ts_nanos,
                                const float* __restrict__ decay, uint64_t n, uint64_t n_pad, float w, float base,
-                               unsigned long long now_secs, uint32_t now_nanos, float* __restrict__ bias) {
+                               unsigned long long now_secs, uint32_t now_nanos, float* __restrict__ bias,
+                               const uint32_t* __restrict__ perm) {
   const float scale = __fdiv_rn(2.0f, __fsub_rn(1.0f, w));
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (uint64_t)gridDim.x * blockDim.x)
-    bias[i] = i < n ? -__fmul_rn(scale, temporal_term_dev(ts_secs[i], ts_nanos[i], decay[i], now_secs, now_nanos, w, base)) : 0.0f;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t h = (perm && i < n) ? perm[i] : i;  // bias of scan row i = attributes of handle perm[i]
+    bias[i] = i < n ? -__fmul_rn(scale, temporal_term_dev(ts_secs[h], ts_nanos[h], decay[h], now_secs, now_nanos, w, base)) : 0.0f;
+  }
+}
+
+// Context-sorted layout: group the queries of a call by context and give every query-tile pair the tile range that
+// holds its contexts.
+//   k_group_queries_by_context   one CTA per chunk of <= kCtxSortChunk queries: bitonic sort of (context, caller row)
+//                                keys in shared memory -> order[i] = caller row of scan query i, qctx[i] = its context
+//   k_context_pair_ranges        one thread per query-tile pair: binary search of the pair's first / last context in the
+//                                context ids of the sorted rows -> [lo, hi) in corpus tiles (empty when no row has them)
+constexpr uint32_t GQ_THREADS = 1024;
+__global__ void __launch_bounds__(GQ_THREADS) k_group_queries_by_context(const uint32_t* __restrict__ want, uint32_t nq,
+                                                                          uint32_t chunk, uint32_t* __restrict__ order,
+                                                                          uint32_t* __restrict__ qctx) {
+  extern __shared__ __align__(16) unsigned long long gq_keys[];
+  const uint32_t q0 = blockIdx.x * chunk, nb = min(chunk, nq - q0);
+  const uint32_t P = next_pow2(nb < 2 ? 2 : nb);
+  for (uint32_t i = threadIdx.x; i < P; i += GQ_THREADS)
+    gq_keys[i] = i < nb ? (((unsigned long long)want[q0 + i] << 32) | (q0 + i)) : kKeyMax;
+  block_bitonic_sort(gq_keys, P);
+  for (uint32_t i = threadIdx.x; i < nb; i += GQ_THREADS) {
+    order[q0 + i] = (uint32_t)gq_keys[i];
+    qctx[q0 + i] = (uint32_t)(gq_keys[i] >> 32);
+  }
+}
+
+__global__ void k_context_pair_ranges(const uint32_t* __restrict__ qctx, uint32_t nq, uint32_t chunk,
+                                      const uint32_t* __restrict__ row_ctx, uint32_t n, uint32_t n_pairs,
+                                      uint32_t* __restrict__ pair_lo, uint32_t* __restrict__ pair_hi) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  // pairs are numbered per chunk: chunk c owns pairs [c * pairs_per_chunk, ...), its queries start at c * chunk
+  const uint32_t ppc = (chunk + PAIR_M - 1) / PAIR_M;
+  const uint32_t c = p / ppc, first = c * chunk + (p % ppc) * PAIR_M;
+  const uint32_t chunk_end = min(nq, (c + 1) * chunk);
+  uint32_t lo = 0, hi = 0;
+  if (first < chunk_end) {
+    const uint32_t c_first = qctx[first], c_last = qctx[min(first + PAIR_M, chunk_end) - 1];
+    uint32_t a = 0, b = n;  // lower_bound(c_first)
+    while (a < b) {
+      const uint32_t mid = a + (b - a) / 2;
+      if (row_ctx[mid] < c_first) a = mid + 1; else b = mid;
+    }
+    const uint32_t row_lo = a;
+    b = n;                  // upper_bound(c_last), from row_lo on
+    while (a < b) {
+      const uint32_t mid = a + (b - a) / 2;
+      if (row_ctx[mid] <= c_last) a = mid + 1; else b = mid;
+    }
+    if (a > row_lo) lo = row_lo / BN, hi = (a + BN - 1) / BN;
+  }
+  pair_lo[p] = lo;
+  pair_hi[p] = hi;
 }
 
 struct ContextRescoreArgs {
@@ -761,6 +828,8 @@ struct ContextRescoreArgs {
   uint32_t* flag_list;
   uint32_t flag_cap;
   unsigned long long* rescored_total;
+  const uint32_t* perm;     // candidate row (scan order) -> handle; nullptr: identity
+  const uint32_t* q_order;  // scan query index -> the caller's query row; nullptr: identity
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextRescoreArgs a) {
@@ -774,6 +843,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
   __shared__ unsigned long long mbar;
   __shared__ uint32_t n_surv, n_keep;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t qo = a.q_order ? a.q_order[q] : q;  // the caller's row of this query (inputs and outputs live there)
   const uint32_t cnt_raw = a.cand_cnt[q];
   const uint32_t cnt = min(cnt_raw, a.cap);
   const uint32_t tk = a.tau_key[q];
@@ -781,7 +851,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
     n_surv = 0, n_keep = 0;
     rg_mbar_init(&mbar);
   }
-  for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.q_raw[(uint64_t)q * a.ldq + e];
+  for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.q_raw[(uint64_t)qo * a.ldq + e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
     const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
@@ -809,20 +879,23 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
   if (bad) {
     if (tid == 0) {
       uint32_t slot = atomicAdd(a.flag_count, 1u);
-      if (slot < a.flag_cap) a.flag_list[slot] = q;
+      if (slot < a.flag_cap) a.flag_list[slot] = qo;
     }
     for (uint32_t i = tid; i < a.k; i += RS_THREADS) {  // visibly invalid until the caller's fp32 redo replaces it
-      a.ids[(uint64_t)q * a.k + i] = CM_NO_ID_DEV;
-      a.score[(uint64_t)q * a.k + i] = __int_as_float(0x7FC00000);
+      a.ids[(uint64_t)qo * a.k + i] = CM_NO_ID_DEV;
+      a.score[(uint64_t)qo * a.k + i] = __int_as_float(0x7FC00000);
     }
     return;
   }
   const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
   for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
-  for (uint32_t i = tid; i < keep; i += RS_THREADS) rows[i] = (uint32_t)(~keys[i]);
+  for (uint32_t i = tid; i < keep; i += RS_THREADS) {
+    const uint32_t r = (uint32_t)(~keys[i]);
+    rows[i] = a.perm ? a.perm[r] : r;  // from here on: handles
+  }
   __syncthreads();
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
-  const float nb = a.qnorm2[q];
+  const float nb = a.qnorm2[qo];
   uint32_t phase = 0;
   for (uint32_t r0 = 0; r0 < keep; r0 += a.rows) {
     const uint32_t cntr = min(a.rows, keep - r0);
@@ -848,8 +921,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
   for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
     unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
     bool ok = key != kKeyMax;
-    a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
-    a.score[(uint64_t)q * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+    a.ids[(uint64_t)qo * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+    a.score[(uint64_t)qo * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
   }
   if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)keep);
 }
@@ -917,7 +990,7 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   CUtensorMap map_q, map_x;
   const uint32_t nq_pad = scan_tc_pad_queries(l.nq);
   if (!make_map(&map_q, l.q_bf16, nq_pad, ix.k_pad, BM)) return cudaErrorInvalidValue;
-  if (!make_map(&map_x, ix.xbf16, ix.n_pad, ix.k_pad, BN_HALF)) return cudaErrorInvalidValue;
+  if (!make_map(&map_x, l.x_bf16 ? l.x_bf16 : ix.xbf16, ix.n_pad, ix.k_pad, BN_HALF)) return cudaErrorInvalidValue;
   const uint32_t clusters = (uint32_t)std::max(1, ix.sm_count / 2);
   ScanArgs a;
   a.nq = l.nq;
@@ -947,6 +1020,10 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.bias = l.bias;
   a.row_ctx = l.row_ctx;
   a.q_ctx = l.q_ctx;
+  a.pair_lo = l.pair_lo;
+  a.pair_hi = l.pair_hi;
+  // context-sorted ranges are short: size the splits for the expected range length, not for the whole corpus
+  if (l.pair_lo) a.splits = pick_splits(a.m_pairs, std::max(1u, std::min(l.pair_tiles_avg, a.n_tiles)), clusters, l.k, l.cap);
   const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
   a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
   // Leave room on the SM for one rescore CTA (K2, ~34 KB): a caller that pipelines batches over two streams then gets
@@ -1016,10 +1093,36 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
 }
 
 cudaError_t launch_context_bias(const DeviceIndex& ix, float w, float base, uint64_t now_secs, uint32_t now_nanos, float* bias,
-                                cudaStream_t s) {
+                                cudaStream_t s, const uint32_t* perm) {
   if (ix.n_pad == 0) return cudaSuccess;
   k_context_bias<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(ix.ts_secs), ix.ts_nanos, ix.decay, ix.n,
-                                          ix.n_pad, w, base, now_secs, now_nanos, bias);
+                                          ix.n_pad, w, base, now_secs, now_nanos, bias, perm);
+  count_launch();
+  return cudaGetLastError();
+}
+
+uint32_t scan_tc_context_chunk() { return kCtxSortChunk; }
+
+cudaError_t launch_group_queries_by_context(const uint32_t* want, uint32_t nq, uint32_t* order, uint32_t* qctx,
+                                            cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  const uint32_t chunks = (nq + kCtxSortChunk - 1) / kCtxSortChunk;
+  const size_t smem = (size_t)next_pow2(std::min(nq, kCtxSortChunk) < 2 ? 2 : std::min(nq, kCtxSortChunk)) * 8;
+  cudaError_t e = cudaFuncSetAttribute(k_group_queries_by_context, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kCtxSortChunk * 8));
+  if (e != cudaSuccess) return e;
+  k_group_queries_by_context<<<chunks, GQ_THREADS, smem, s>>>(want, nq, kCtxSortChunk, order, qctx);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_context_pair_ranges(const DeviceIndex& ix, const uint32_t* qctx, uint32_t nq, uint32_t* pair_lo,
+                                       uint32_t* pair_hi, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  const uint32_t chunks = (nq + kCtxSortChunk - 1) / kCtxSortChunk;
+  const uint32_t n_pairs = chunks * (kCtxSortChunk / PAIR_M);
+  k_context_pair_ranges<<<(n_pairs + 127) / 128, 128, 0, s>>>(qctx, nq, kCtxSortChunk, ix.ctx_sorted, (uint32_t)ix.n, n_pairs,
+                                                              pair_lo, pair_hi);
   count_launch();
   return cudaGetLastError();
 }
@@ -1053,6 +1156,8 @@ cudaError_t launch_rescore_context(const DeviceIndex& ix, const ContextRescoreLa
   a.flag_list = l.flag_list;
   a.flag_cap = l.flag_cap;
   a.rescored_total = l.rescored_total;
+  a.perm = l.perm;
+  a.q_order = l.q_order;
   a.rs_max = l.k <= 16 ? 2048u : (l.k <= 64 ? 4096u : 8192u);
   // the stored rows are not unit length and the reference divides by fp32 norms: a little slack on top of the scan's bound
   a.eps2 = 2.0f * (eps_for_dim(ix.dim) + 2e-5f);

@@ -35,6 +35,12 @@ struct ScanTcLaunch {
   const float* bias = nullptr;        // [pad_rows(n)]
   const uint32_t* row_ctx = nullptr;  // [pad_rows(n)]
   const uint32_t* q_ctx = nullptr;    // [nq]
+  // context-sorted layout: scan `x_bf16` (a permuted copy of the corpus, same shape) instead of the index's own copy,
+  // and give every query-tile pair its own tile range [pair_lo[m], pair_hi[m]) (device arrays, one entry per pair)
+  const void* x_bf16 = nullptr;
+  const uint32_t* pair_lo = nullptr;
+  const uint32_t* pair_hi = nullptr;
+  uint32_t pair_tiles_avg = 0;        // mean range length (sizes the splits)
 };
 cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s);
 
@@ -60,7 +66,14 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
 // `search_in_context` on the tensor cores (see scan_tc.cu): the per-row bias of one call, and the exact decision on the
 // stored rows.
 cudaError_t launch_context_bias(const DeviceIndex& ix, float w, float base, uint64_t now_secs, uint32_t now_nanos, float* bias,
-                                cudaStream_t s);
+                                cudaStream_t s, const uint32_t* perm = nullptr);
+// Context-sorted layout: queries grouped by context in chunks of scan_tc_context_chunk() (order[i] = caller row of scan
+// query i, qctx[i] = its context id), and per query-tile pair the corpus tile range that holds the pair's contexts
+// (pairs numbered chunk by chunk: chunk c owns pairs [c * chunk / 256, (c + 1) * chunk / 256)).
+uint32_t scan_tc_context_chunk();
+cudaError_t launch_group_queries_by_context(const uint32_t* want, uint32_t nq, uint32_t* order, uint32_t* qctx, cudaStream_t s);
+cudaError_t launch_context_pair_ranges(const DeviceIndex& ix, const uint32_t* qctx, uint32_t nq, uint32_t* pair_lo,
+                                       uint32_t* pair_hi, cudaStream_t s);
 struct ContextRescoreLaunch {
   const float* q_raw;        // queries as given [nq][ldq]
   uint32_t ldq, nq, k;
@@ -78,6 +91,8 @@ struct ContextRescoreLaunch {
   uint32_t* flag_list;
   uint32_t flag_cap;
   unsigned long long* rescored_total;
+  const uint32_t* perm = nullptr;     // candidate row (scan order) -> handle
+  const uint32_t* q_order = nullptr;  // scan query index -> caller's query row (q_raw, qnorm2, ids, score are indexed by it)
 };
 cudaError_t launch_rescore_context(const DeviceIndex& ix, const ContextRescoreLaunch& l, cudaStream_t s);
 

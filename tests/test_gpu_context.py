@@ -127,3 +127,40 @@ def test_snapshot_contexts_and_cli_query(tmp_path):
     out = subprocess.run([sys.executable, "-m", "chronomind_b200", "query", "-f", p, "-v", "0.1,0.2", "-l", "3"],
                          capture_output=True, text=True, cwd=ROOT, env=env)
     assert out.returncode == 1 and "InvalidDimensions" in out.stderr
+
+
+def test_search_in_context_sorted_layout_large_batches_sparse_ids_and_tombstones():
+    """The context-sorted layout (rows ordered by context on the device, queries grouped by context per 16,384-query
+    chunk, per-pair tile ranges): more queries than one sort chunk, context ids that are neither dense nor small, an
+    unknown context, and tombstones that reach the sorted copy through `cm_index_sync_deleted` — bit for bit the fp32
+    context scan, and the oracle on a slice."""
+    from chronomind_b200.engine import last_counters
+    n, dim, k, nq = 40000, 64, 10, 17000
+    rng = np.random.default_rng(2024)
+    raw = (rng.normal(size=(n, dim)) * rng.uniform(0.2, 5.0, size=(n, 1))).astype(np.float32)
+    labels = np.array([7, 3_000_000_000, 12, 99_999, 0, 4_000_000], dtype=np.uint32)          # sparse ids, uneven sizes
+    ctx = labels[rng.choice(len(labels), size=n, p=[0.5, 0.2, 0.15, 0.1, 0.04, 0.01])]
+    dele = (rng.uniform(size=n) < 0.05).astype(np.uint8)
+    ts_s, ts_n, dec = datasets.temporal_attrs(n, 5, NOW[0])
+    st = ChronoMindB200.from_matrix(raw, default_config(dimensions=dim), ts_s, ts_n, dec, dele).set_contexts(raw, ctx).upload(0)
+    q = (rng.normal(size=(nq, dim)) * 2.0).astype(np.float32)
+    want = np.concatenate([labels, [555]]).astype(np.uint32)[rng.integers(0, len(labels) + 1, size=nq)]   # 555: no members
+    for rnd in range(2):
+        ia, sa = st.set_exact_engine(2).search_in_context(want, q, k, now=NOW, temporal_weight=0.3, base_decay_rate=0.1)
+        ca = last_counters()
+        ib, sb = st.set_exact_engine(1).search_in_context(want, q, k, now=NOW, temporal_weight=0.3, base_decay_rate=0.1)
+        assert ca["exact_engine"] == 2 and ca["fallback_queries"] == 0
+        assert np.array_equal(ia, ib) and np.array_equal(bits(sa), bits(sb)), rnd
+        assert np.all(ia[want == 555] == NO_ID)
+        live = ia != NO_ID
+        assert np.all(ctx[ia[live]] == np.broadcast_to(want[:, None], ia.shape)[live]) and not dele[ia[live]].any()
+        sl = slice(16300, 16500)                                    # straddles the sort-chunk boundary
+        rc, wi, ws = oracle.search_in_context(raw, ctx, q[sl], want[sl], k, 0.3, 0.1, ts_s, ts_n, dec, NOW[0], NOW[1],
+                                              deleted=dele, threads=8)
+        assert rc == 0 and assert_order_matches_up_to_ties(ia[sl], wi, sa[sl], ws) <= 0.001 * wi.size
+        if rnd == 0:                                                # tombstone the current winners, sync, search again
+            gone = np.unique(ia[:500, 0][ia[:500, 0] != NO_ID])
+            for h in gone:
+                assert st.remove(int(h))
+            dele[gone] = 1
+            st.sync_deleted()

@@ -29,7 +29,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    for n_ctx in (4, 1000):
+    for n_ctx in [int(v) for v in os.environ.get("CM_CONTEXTS", "4,1000").split(",")]:
         rng = np.random.default_rng(n_ctx)
         ctx = rng.integers(0, n_ctx, size=n).astype(np.uint32)
         want = rng.integers(0, n_ctx, size=nq).astype(np.uint32)
