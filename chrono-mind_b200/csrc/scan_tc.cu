@@ -455,8 +455,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // main pass below emits ~k rows instead of all 256. Tombstoned and padding rows score NaN (see
         // launch_to_bf16) and never enter a list or pass a threshold.
         // (biased mode: a sparse context may never fill its running top-k — after two tiles the few members are simply
-        // emitted instead of paying the extra pass over the accumulator on every tile)
-        const bool cold = q_valid && tau == -INFINITY && (!kBiased || t < t0 + 2);
+        // emitted instead of paying the extra pass over the accumulator on every tile. On the context-SORTED layout a
+        // tile is either foreign to the query or dense with members of its context: the pre-pass runs exactly on the
+        // member tiles, wherever in the unit the context starts — without it the first tile of a context would be
+        // emitted row by row through the divergent hit loop, ~50k cycles per tile with the whole warp waiting.)
+        bool cold = q_valid && tau == -INFINITY;
+        if (kBiased) cold = cold && (a.pair_lo ? (tcx[0] <= my_ctx && my_ctx <= tcx[BN - 1]) : t < t0 + 2);
         bool listed = a.join != 0;  // this tile's rows are already in the running top-k (join: there is none)
         if (__any_sync(0xFFFFFFFFu, cold)) {
 #pragma unroll 1
