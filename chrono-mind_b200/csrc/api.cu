@@ -169,6 +169,18 @@ struct WorkspacePool {
     std::lock_guard<std::mutex> g(mu);
     free_list.push_back(w);
   }
+  // Is the caller keeping more than one batch in flight? True when another workspace is leased right now (a second
+  // host thread inside a call) or still has device work pending (an asynchronous call on another stream).
+  bool overlapped(const Workspace* mine) {
+    std::lock_guard<std::mutex> g(mu);
+    for (Workspace* w : all) {
+      if (w == mine) continue;
+      const bool is_free = std::find(free_list.begin(), free_list.end(), w) != free_list.end();
+      if (!is_free) return true;
+      if (w->pending && w->done && cudaEventQuery(w->done) == cudaErrorNotReady) return true;
+    }
+    return false;
+  }
   ~WorkspacePool() {
     for (Workspace* w : all) {
       w->release();
@@ -362,6 +374,10 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   else
     CM_CUDA(launch_to_bf16(pq.qn, nq, d.dim, pq.ld, ws->qbf16.p, nq_pad, d.k_pad, nullptr, false, s));
   ScanTcLaunch sl;
+  // A caller with a second batch in flight gets a scan that leaves room on every SM for one rescore CTA (the tail of
+  // the other batch then runs UNDER this scan); a single batch in flight gets all of the shared memory for resident
+  // query blocks.
+  sl.leave_room = ((WorkspacePool*)idx->workspace_pool)->overlapped(ws);
   sl.q_bf16 = q_bf16;
   sl.nq = nq;
   sl.k = k;

@@ -33,15 +33,19 @@
 //     tiles on or above the diagonal, pairs (query < row) appended to one list.
 //
 // Kernel organisation (persistent, one CTA per SM, clusters of 2 = one CTA pair per TPC, 8 warps per CTA):
-//   warp 0  TMA producer (one lane, both CTAs) — ring of {Q tile 128x64, X tile 128x64} bf16, 32 KB per stage
-//           per CTA; the pair's loads all complete on the LEADER's full barrier
+//   warp 0  TMA producer (one lane, both CTAs) — 16 KB operand blocks (128 rows x 64 bf16, 128B-swizzled): the first
+//           q_res k-blocks of the CTA's 128 query rows are loaded ONCE per work unit and stay resident; the remaining
+//           query blocks and every corpus block stream through a ring of `slots` blocks. One full / empty barrier
+//           pair per k-block (not per block: a second commit per k-block cost 20 %); the pair's loads all complete
+//           on the LEADER's full barrier
 //   warp 1  MMA issuer   (one lane, leader CTA only) — tcgen05.mma.cta_group::2.kind::f16, M=256 N=256 K=16:
 //           CTA r supplies Q rows [128r, 128r+128) and X rows [128r, 128r+128) of the tile and receives the
 //           accumulator rows of ITS queries against all 256 X rows
 //   warp 2  TMEM allocator — 512 columns = two 128x256 fp32 accumulators (double buffered) per CTA
 //   warps 4-7 epilogue (128 threads) — thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time
-// Operand traffic: each CTA fetches 32 KB per 2·128·256·64 FLOP (128 FLOP/B, vs 85 for a 1-CTA 128x256 tile),
-// which is what keeps the L2->SM path (≈6.3 KB/clk chip-wide) below the tensor pipe's demand.
+// Operand traffic: all-streamed, each CTA fetches 32 KB per 2·128·256·64 FLOP (128 FLOP/B, vs 85 for a 1-CTA 128x256
+// tile) = 64 B/clk per SM at full tensor rate, more than the L2 -> SM path delivers chip-wide (≈6.3-7.1 KB/clk =
+// 43-48 B/clk per SM). With 7 of a 768-wide row's 12 query blocks resident the stream drops to 17/24 of that.
 //
 // Work unit = (query tile pair m, corpus split s): the pair scans tiles [s·T/S, (s+1)·T/S) for its 256 queries,
 // so a thread's running top-k covers a long row range and its threshold converges after a few tiles. Units are
@@ -65,9 +69,13 @@ constexpr uint32_t PAIR_M = 256;    // query rows per CTA pair (UMMA M)
 constexpr uint32_t BN = 256;        // corpus rows per tile (UMMA N)
 constexpr uint32_t BN_HALF = 128;   // corpus rows each CTA stages
 constexpr uint32_t BK = 64, UMMA_K = 16;
-constexpr uint32_t kMaxStages = 6, kAccStages = 2;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN_HALF * BK * 2;
-constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+constexpr uint32_t kAccStages = 2;
+// Operand blocks: one k-block (BK columns) of a CTA's 128 query rows or of its 128 corpus rows = 16 KB, 128B-swizzled.
+// A CTA keeps the first `q_res` k-blocks of its query rows RESIDENT for a whole work unit and streams everything else
+// (the remaining query blocks and every corpus block) through a ring of `slots` such blocks.
+constexpr uint32_t kBlockBytes = BM * BK * 2;
+static_assert(BM == BN_HALF, "query and corpus blocks share the ring");
+constexpr uint32_t kMaxSlots = 13;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kThreads = 256;
 constexpr uint32_t kSlotChunk = 8;  // candidate slots reserved per atomic
@@ -206,7 +214,7 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], uint32_t i) {
 }
 
 struct ScanArgs {
-  uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, stages;
+  uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, slots, q_res;
   float eps2;                    // 2 * eps_for_dim(dim): the candidate margin
   uint32_t* tau_key;             // [m_pairs*256] ordered-uint threshold per query (0 = none yet)
   uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
@@ -241,10 +249,12 @@ __device__ __forceinline__ void unit_tiles(const ScanArgs& a, uint32_t m, uint32
   t1 = lo + (uint32_t)((uint64_t)(sp + 1) * len / a.splits);
 }
 
-// Shared-memory carve-up (dynamic): [stages x (A|B)] 1024-aligned | local top-k lists [k][128] | barriers | tmem ptr.
+// Shared-memory carve-up (dynamic): [q_res resident query blocks | ring of `slots` blocks] 1024-aligned | local top-k
+// lists [k][128] | barriers | tmem ptr.
 // Both CTAs of a pair use the same offsets (the MMA descriptors and multicast commits rely on it).
 struct ScanSmemTail {
-  unsigned long long full[kMaxStages], empty[kMaxStages], tmem_full[kAccStages], tmem_empty[kAccStages];
+  unsigned long long full[kMaxSlots], empty[kMaxSlots], tmem_full[kAccStages], tmem_empty[kAccStages];
+  unsigned long long res_full, res_free;  // resident query blocks of the current unit: landed / no longer read
   uint32_t tmem_base;
 };
 
@@ -287,8 +297,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves the slack). The
   // dynamic window starts at the same offset in both CTAs of the pair, so the carve-up matches.
   uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  float* lists = reinterpret_cast<float*>(tiles + a.stages * kStageBytes);  // [k][128]
-  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(tiles + a.stages * kStageBytes + (size_t)a.k * 128 * 4);
+  const uint32_t kRes = a.q_res, kSlots = a.slots;
+  uint8_t* ring = tiles + kRes * kBlockBytes;
+  float* lists = reinterpret_cast<float*>(ring + kSlots * kBlockBytes);  // [k][128]
+  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(ring + kSlots * kBlockBytes + (size_t)a.k * 128 * 4);
   // biased mode: the current tile's 256 row biases and context ids, one slot per accumulator stage
   float* tile_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + ((sizeof(ScanSmemTail) + 15) & ~(size_t)15));
   uint32_t* tile_ctx = reinterpret_cast<uint32_t*>(tile_bias + kAccStages * BN);
@@ -297,17 +309,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
   const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const uint32_t units = a.m_pairs * a.splits;
-  const uint32_t kStages = a.stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_x);
   }
   if (warp == 1 && lane == 0) {
-    for (uint32_t s = 0; s < kStages; ++s) {
+    for (uint32_t s = 0; s < kMaxSlots; ++s) {
       mbar_init(smem_u32(&tail->full[s]), 1);    // leader's producer: arrive.expect_tx for the pair's bytes
       mbar_init(smem_u32(&tail->empty[s]), 1);   // one multicast commit per use
     }
+    mbar_init(smem_u32(&tail->res_full), 1);
+    mbar_init(smem_u32(&tail->res_free), 1);
     for (uint32_t s = 0; s < kAccStages; ++s) {
       mbar_init(smem_u32(&tail->tmem_full[s]), 1);   // one multicast commit per tile
       mbar_init(smem_u32(&tail->tmem_empty[s]), 8);  // leader's copy: 4 epilogue warps x 2 CTAs
@@ -329,28 +342,51 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =============================================================================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      // Ring bookkeeping (mirrored by the MMA issuer): k-block number i of this cluster's stream owns barrier pair
+      // i % kMaxSlots and takes 1 granule (corpus block only: its query block is resident) or 2 (query block, then corpus
+      // block) of the `kSlots`-granule ring, in order. A granule is free again when the k-block that used it has retired
+      // (its MMAs' commit on `empty`), and k-blocks retire in order, so one cursor replays the frees.
+      uint32_t issue = 0, retire = 0, gpos = 0, gfree = kSlots, res_units = 0;
+      const uint32_t kbs = a.k_blocks;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
         uint32_t t0, t1_all;
         unit_tiles(a, m, sp, t0, t1_all);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         const uint32_t t1 = kPred ? min(t1_all, a.q_base / BN + m + 1) : t1_all;  // predecessors: up to the diagonal tile
+        if (t0 >= t1) continue;
         const int32_t q_row = (int32_t)(m * PAIR_M + rank * BM);
+        if (kRes) {
+          // The unit's resident query blocks: once the previous unit's last MMA has retired (res_free), one bulk of
+          // kRes blocks per CTA, accounted on the leader's res_full.
+          if (res_units) mbar_wait(smem_u32(&tail->res_free), (res_units - 1) & 1);
+          const uint32_t bar_local = smem_u32(&tail->res_full);
+          if (rank == 0) mbar_expect_tx(bar_local, 2 * kRes * kBlockBytes);
+          const uint32_t bar = map_to_cta(bar_local, 0);
+          for (uint32_t kb = 0; kb < kRes; ++kb)
+            tma_load_2d_pair(smem_u32(tiles + kb * kBlockBytes), &map_q, bar, (int32_t)(kb * BK), q_row);
+          ++res_units;
+        }
         for (uint32_t t = t0; t < t1; ++t) {
           const int32_t x_row = (int32_t)(t * BN + rank * BN_HALF);
-          for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-            mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
-            const uint32_t bar_local = smem_u32(&tail->full[stage]);
-            if (rank == 0) mbar_expect_tx(bar_local, 2 * kStageBytes);  // both CTAs' Q and X tiles
-            const uint32_t bar = map_to_cta(bar_local, 0);
-            const uint32_t sa = smem_u32(tiles + stage * kStageBytes);
-            tma_load_2d_pair(sa, &map_q, bar, (int32_t)(kb * BK), q_row);
-            tma_load_2d_pair(sa + kStageBytesA, &map_x, bar, (int32_t)(kb * BK), x_row);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
+          for (uint32_t kb = 0; kb < kbs; ++kb) {
+            const uint32_t g = kb < kRes ? 1u : 2u;
+            while (gfree < g || issue - retire >= kMaxSlots) {  // retire the oldest k-block in flight
+              mbar_wait(smem_u32(&tail->empty[retire % kMaxSlots]), (retire / kMaxSlots) & 1);
+              gfree += (retire % kbs) < kRes ? 1u : 2u;
+              ++retire;
             }
+            const uint32_t bar_local = smem_u32(&tail->full[issue % kMaxSlots]);
+            if (rank == 0) mbar_expect_tx(bar_local, 2 * g * kBlockBytes);  // this k-block's bytes of both CTAs
+            const uint32_t bar = map_to_cta(bar_local, 0);
+            if (g == 2) {  // streamed query block first, then the corpus block
+              tma_load_2d_pair(smem_u32(ring + gpos * kBlockBytes), &map_q, bar, (int32_t)(kb * BK), q_row);
+              if (++gpos == kSlots) gpos = 0;
+            }
+            tma_load_2d_pair(smem_u32(ring + gpos * kBlockBytes), &map_x, bar, (int32_t)(kb * BK), x_row);
+            if (++gpos == kSlots) gpos = 0;
+            gfree -= g;
+            ++issue;
           }
         }
       }
@@ -359,39 +395,51 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ===== MMA issuer (leader CTA) ==============================================================================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(PAIR_M, BN);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t issue = 0, gpos = 0, acc = 0, acc_phase = 0, res_phase = 0;
       for (uint32_t u = cluster_id; u < units; u += n_clusters) {
         const uint32_t sp = u / a.m_pairs;
         uint32_t t0, t1;
         unit_tiles(a, u % a.m_pairs, sp, t0, t1);
         if (a.join) t0 = max(t0, u % a.m_pairs);  // self-join keeps row > query: tiles below the diagonal are skipped
         if (kPred) t1 = min(t1, a.q_base / BN + u % a.m_pairs + 1);  // predecessors: up to the diagonal tile
+        if (t0 >= t1) continue;
+        if (kRes) {
+          mbar_wait(smem_u32(&tail->res_full), res_phase);  // this unit's resident query blocks have landed (both CTAs)
+          res_phase ^= 1;
+          tc_fence_after();
+        }
         for (uint32_t t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&tail->tmem_empty[acc]), acc_phase ^ 1);  // both epilogues drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-            mbar_wait(smem_u32(&tail->full[stage]), phase);
+            const uint32_t bi = issue % kMaxSlots;
+            mbar_wait(smem_u32(&tail->full[bi]), (issue / kMaxSlots) & 1);
             tc_fence_after();
-            const uint32_t sa = smem_u32(tiles + stage * kStageBytes);
-            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kStageBytesA);
+            uint64_t adesc;
+            if (kb < kRes) {
+              adesc = make_smem_desc(smem_u32(tiles + kb * kBlockBytes));
+            } else {
+              adesc = make_smem_desc(smem_u32(ring + gpos * kBlockBytes));
+              if (++gpos == kSlots) gpos = 0;
+            }
+            const uint64_t bdesc = make_smem_desc(smem_u32(ring + gpos * kBlockBytes));
+            if (++gpos == kSlots) gpos = 0;
 #pragma unroll
             for (uint32_t kk = 0; kk < BK / UMMA_K; ++kk) {
               // advancing 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 start field
               umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
             }
-            umma_commit_pair(smem_u32(&tail->empty[stage]));  // frees the stage in both CTAs when the MMAs retire
+            umma_commit_pair(smem_u32(&tail->empty[bi]));  // retires the k-block in both CTAs when these MMAs are done
             if (kb + 1 == a.k_blocks) umma_commit_pair(smem_u32(&tail->tmem_full[acc]));
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
+            ++issue;
           }
           if (++acc == kAccStages) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
+        if (kRes) umma_commit_pair(smem_u32(&tail->res_free));  // the resident blocks may be overwritten once these retire
       }
     }
   } else if (warp >= 4) {
@@ -1029,18 +1077,26 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   // context-sorted ranges are short: size the splits for the expected range length, not for the whole corpus
   if (l.pair_lo) a.splits = pick_splits(a.m_pairs, std::max(1u, std::min(l.pair_tiles_avg, a.n_tiles)), clusters, l.k, l.cap);
   const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
-  a.stages = (uint32_t)std::min<size_t>(kMaxStages, (kMaxSmem - fixed) / kStageBytes);
-  // Leave room on the SM for one rescore CTA (K2, ~34 KB): a caller that pipelines batches over two streams then gets
-  // the rescore / exchange / merge of batch i for free under the scan of batch i + 1 — the scan is tensor-bound and
-  // touches 3 % of the DRAM bandwidth, the rescore is the opposite. Five stages (3 us of prefetch at full rate against
-  // ~1 us of L2 latency) measured the same as six. CM_SCAN_STAGES overrides (experiments).
-  if (l.k <= 16 && a.stages > 5) a.stages = 5;
-  if (const char* env = getenv("CM_SCAN_STAGES")) {
+  // Shared-memory budget in 16 KB operand blocks: `q_res` resident query blocks + a ring of `slots` streamed blocks.
+  // Every resident block removes one query block per corpus tile from the L2 -> SM stream (all-streamed the kernel asks
+  // for 64 B/clk per SM at full tensor rate, against ~43-48 B/clk per SM the L2 delivers chip-wide). The ring needs six
+  // blocks to cover the L2 latency (sweep in profiles/r02_scan_qres_sweep.txt: 7 resident + 6 streamed is the best split
+  // of the 13 blocks that fit beside k = 10 lists; 6 + 5 or 9 + 4 starve the MMA). CM_SCAN_QRES / CM_SCAN_SLOTS override.
+  const size_t room = l.leave_room && l.k <= 16 ? 40 * 1024 : 0;  // K2 (~34 KB + 1 KB reserved) beside this kernel
+  const uint32_t blocks_max = (uint32_t)std::min<size_t>(kMaxSlots + 16, (kMaxSmem - fixed - room) / kBlockBytes);
+  if (blocks_max < 4) return cudaErrorInvalidValue;
+  const uint32_t ring_min = std::min(6u, blocks_max);
+  uint32_t q_res = std::min<uint32_t>(std::min<uint32_t>(a.k_blocks, 7), blocks_max - ring_min), slots = 0;
+  if (const char* env = getenv("CM_SCAN_QRES"))
+    q_res = std::min<uint32_t>(std::min<uint32_t>(a.k_blocks, (uint32_t)std::max(0, atoi(env))), blocks_max - 3);
+  slots = std::min<uint32_t>(kMaxSlots, blocks_max - q_res);
+  if (const char* env = getenv("CM_SCAN_SLOTS")) {
     const uint32_t f = (uint32_t)atoi(env);
-    if (f >= 2 && f <= kMaxStages && fixed + (size_t)f * kStageBytes <= kMaxSmem) a.stages = f;
+    if (f >= 3 && f <= slots) slots = f;
   }
-  if (a.stages < 2) return cudaErrorInvalidValue;
-  const size_t smem = fixed + (size_t)a.stages * kStageBytes;
+  a.q_res = q_res;
+  a.slots = slots;
+  const size_t smem = fixed + (size_t)(q_res + slots) * kBlockBytes;
   auto kernel = biased ? scan_tc_kernel<true, false> : (l.pred ? scan_tc_kernel<false, true> : scan_tc_kernel<false, false>);
   if (biased && l.pred) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);

@@ -41,6 +41,8 @@ struct ScanTcLaunch {
   const uint32_t* pair_lo = nullptr;
   const uint32_t* pair_hi = nullptr;
   uint32_t pair_tiles_avg = 0;        // mean range length (sizes the splits)
+  // keep ~40 KB of every SM's shared memory free: a rescore CTA of ANOTHER batch in flight can then co-reside with the scan
+  bool leave_room = false;
 };
 cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStream_t s);
 
