@@ -102,3 +102,55 @@ class ChunkedCorpus:
 
     def queries(self, nq: int, stream: int = 0) -> np.ndarray:
         return self._rows(np.random.default_rng([self.seed, 2, stream]), nq)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic stores as the reference's own snapshot files
+# ---------------------------------------------------------------------------------------------------------------------
+def write_snapshot(path: str, rows: np.ndarray, ts_secs, ts_nanos, decay_rate, context_ids=None, n_contexts: int = 1,
+                   importance=None, config: dict | None = None, chunk: int = 32768) -> dict:
+    """Write `rows` (one memory per row, in row order) as a ChronoMind snapshot v2 file — the container of
+    `save_snapshot` (src/persistence.rs:41-64: "CHRONO1" | version 2 | crc32(body) LE | body) around the bincode 1.3.3
+    encoding of `SnapshotBody{config, memories}` (src/config.rs:11-25,43-71; src/types.rs:13-18,32-49,68-73; SURVEY.md
+    App. B) — so that a million-record synthetic store reaches the engine through `cm_index_from_snapshot`, the way a
+    ChronoMind deployment's data would. Ids are "m%09d", contexts "ctx%05d" (fixed widths make a record a fixed-size
+    numpy struct: the file is streamed out at memory speed), relationships empty, access_count 0, last_access =
+    timestamp. Returns {"bytes", "records", "crc32"}. The byte layout is asserted equal to the checker's record-by-record
+    writer in tests/test_host_engine.py."""
+    import struct
+    import zlib
+    n, dim = rows.shape
+    cfg = {"dimensions": dim, "max_memories": max(n, 100_000), "base_decay_rate": 0.1, "temporal_weight": 0.3,
+           "similarity_threshold": 0.95, "max_relationships": 50, "max_connections": 16, "ef_construction": 200,
+           "ef_search": 50}
+    cfg.update(config or {})
+    rec = np.dtype([("idlen", "<u8"), ("id", "S10"), ("dlen", "<u8"), ("data", "<f4", (dim,)), ("ts_s", "<u8"),
+                    ("ts_n", "<u4"), ("imp", "<f4"), ("clen", "<u8"), ("ctx", "S8"), ("decay", "<f4"), ("nrel", "<u8"),
+                    ("acc", "<u4"), ("la_s", "<u8"), ("la_n", "<u4")])
+    assert rec.itemsize == 8 + 10 + 8 + 4 * dim + 12 + 4 + 8 + 8 + 4 + 8 + 4 + 12
+    head = struct.pack("<QQfffQQQQ", cfg["dimensions"], cfg["max_memories"], cfg["base_decay_rate"], cfg["temporal_weight"],
+                       cfg["similarity_threshold"], cfg["max_relationships"], cfg["max_connections"],
+                       cfg["ef_construction"], cfg["ef_search"]) + struct.pack("<Q", n)
+    ctx_labels = np.char.mod("ctx%05d", np.arange(max(1, n_contexts))).astype("S8")
+    crc = zlib.crc32(head)
+    with open(path, "wb") as f:
+        f.write(b"CHRONO1" + bytes([2]) + b"\0\0\0\0")          # checksum patched in below
+        f.write(head)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            r = np.zeros(e - s, dtype=rec)
+            r["idlen"], r["dlen"], r["clen"] = 10, dim, 8
+            r["id"] = np.char.mod("m%09d", np.arange(s, e)).astype("S10")
+            r["data"] = rows[s:e]
+            r["ts_s"], r["ts_n"] = ts_secs[s:e], ts_nanos[s:e]
+            r["la_s"], r["la_n"] = ts_secs[s:e], ts_nanos[s:e]
+            r["imp"] = 0.5 if importance is None else importance[s:e]
+            r["ctx"] = ctx_labels[0] if context_ids is None else ctx_labels[context_ids[s:e]]
+            r["decay"] = decay_rate[s:e]
+            b = r.tobytes()
+            crc = zlib.crc32(b, crc)
+            f.write(b)
+        total = f.tell()
+        f.seek(8)
+        f.write(struct.pack("<I", crc & 0xFFFFFFFF))
+    return {"bytes": total, "records": n, "crc32": crc & 0xFFFFFFFF}

@@ -368,3 +368,27 @@ def test_group_needs_cuda_devices():
     with pytest.raises(CmError) as e:
         ShardedChronoMindB200([0])
     assert e.value.kind == "Cuda"
+
+
+def test_fast_snapshot_writer_is_byte_identical_to_the_codec(tmp_path):
+    """`datasets.write_snapshot` (the vectorised writer the bench and the scale tests feed the snapshot reader with) against
+    the checker's record-by-record bincode restatement: same bytes, and the product's reader decodes it to the same store."""
+    n, dim = 300, 12
+    rng = np.random.default_rng(5)
+    rows = rng.normal(size=(n, dim)).astype(np.float32)
+    ts_s, ts_n, dec = datasets.temporal_attrs(n, 3, 1_790_000_000)
+    ctx = rng.integers(0, 7, size=n).astype(np.uint32)
+    imp = rng.uniform(0, 1, size=n).astype(np.float32)
+    p = str(tmp_path / "fast.chrono")
+    info = datasets.write_snapshot(p, rows, ts_s, ts_n, dec, ctx, 7, imp, config={"ef_construction": 100, "max_memories": 1000})
+    mems = [sc.Memory(id="m%09d" % i, data=rows[i].tolist(), ts_secs=int(ts_s[i]), ts_nanos=int(ts_n[i]), importance=float(imp[i]),
+                      context="ctx%05d" % ctx[i], decay_rate=float(dec[i]), last_access_secs=int(ts_s[i]),
+                      last_access_nanos=int(ts_n[i])) for i in range(n)]
+    want = sc.encode_snapshot(sc.Config(dimensions=dim, max_memories=1000, index=sc.IndexParams(16, 100, 50)), mems)
+    got = open(p, "rb").read()
+    assert got == want and info["bytes"] == len(want) and info["records"] == n
+    st = ChronoMindB200.from_snapshot(p)
+    assert len(st) == n and st.config.dimensions == dim and st.config.index.ef_construction == 100
+    assert st.external_id(0) == "m000000000" and st.external_id(n - 1) == "m%09d" % (n - 1)
+    assert st.context_label(5) == "ctx%05d" % ctx[5] and abs(st.importance(17) - imp[17]) < 1e-7
+    st.close()
