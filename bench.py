@@ -135,6 +135,25 @@ def recall_at_k(got, want):
     return float(np.mean([len(set(a) & set(b)) / want.shape[1] for a, b in zip(got.tolist(), want.tolist())]))
 
 
+def order_mismatches_beyond_ties(got_ids, want_ids, got_scores, want_scores, rel=1e-5, atol=1e-7):
+    """north_star's parity rule for scored lists: scores within 1e-5 relative, ids equal wherever the oracle's neighbouring
+    scores differ by more than that. Returns the number of positions that BREAK the rule (0 = parity)."""
+    gs, ws = np.asarray(got_scores, np.float64), np.asarray(want_scores, np.float64)
+    fin = np.isfinite(ws)
+    bad = int((fin != np.isfinite(gs)).sum())
+    tol = rel * np.abs(np.where(fin, ws, 0.0)) + atol
+    bad += int((np.abs(np.where(fin, gs - ws, 0.0)) > tol).sum())
+    k = want_ids.shape[1]
+    for r, j in zip(*np.nonzero(np.asarray(got_ids) != np.asarray(want_ids))):
+        near = j == k - 1
+        if j > 0:
+            near |= abs(ws[r, j] - ws[r, j - 1]) <= tol[r, j]
+        if j + 1 < k:
+            near |= abs(ws[r, j] - ws[r, j + 1]) <= tol[r, j]
+        bad += 0 if near else 1
+    return bad
+
+
 def frontier_ef(per_ef, gate=0.95):
     """Smallest ef whose recall@10 reaches the gate (the metric's operating point); None when none does."""
     ok = sorted(int(e) for e, r in per_ef.items() if r["recall_at_10"] >= gate)
@@ -383,8 +402,33 @@ def run_ours(args, rank, world, local_rank):
     ts_s, ts_n, decay = datasets.temporal_attrs(n_rows, 1, NOW[0])              # indexed by GLOBAL handle
     t0 = time.time()
     cfg = default_config(dimensions=DIM, ef_construction=args.efc)
-    st = ChronoMindB200.from_matrix(shard, cfg, sharding.shard_attrs(ts_s, rank, world), sharding.shard_attrs(ts_n, rank, world),
-                                    sharding.shard_attrs(decay, rank, world)).set_shard(rank, world)
+    use_snapshot = world == 1 and (args.source == "snapshot" or (args.source == "auto" and n_rows * DIM * 4 <= (4 << 30)))
+    source, ctx_rows = "matrix handed to cm_index_from_matrix", None
+    if use_snapshot:
+        # BASELINE configs[2]: "from reference snapshot". The synthetic store goes through the reference's own file format:
+        # save_snapshot's container (src/persistence.rs:41-64) written by datasets.write_snapshot, read back by the
+        # engine's load_snapshot restatement (cm_index_from_snapshot: header, CRC-32, bincode body, validate per record).
+        ctx_rows = np.random.default_rng(SEED ^ 0xC7).integers(0, max(1, args.contexts), size=n_rows).astype(np.uint32)
+        snap_path = "/tmp/chronomind_bench_%d_%dx%d.chrono" % (os.getpid(), n_rows, DIM)
+        try:
+            tw = time.time()
+            info = datasets.write_snapshot(snap_path, shard, ts_s, ts_n, decay, ctx_rows, max(1, args.contexts),
+                                           config={"ef_construction": args.efc, "max_memories": max(n_rows, 100_000)})
+            tw = time.time() - tw
+            tl = time.time()
+            st = ChronoMindB200.from_snapshot(snap_path)
+            tl = time.time() - tl
+        finally:
+            if os.path.exists(snap_path):
+                os.unlink(snap_path)
+        assert len(st) == n_rows and st.config.dimensions == DIM and st.external_id(n_rows - 1) == "m%09d" % (n_rows - 1)
+        source = ("CHRONO1 v2 snapshot file, %.2f GB, %d records over %d contexts: written in %.1fs, loaded by cm_index_from_snapshot "
+                  "in %.1fs (%.2f GB/s: read + CRC-32 + bincode decode + validate + preprocess)"
+                  % (info["bytes"] / 1e9, n_rows, max(1, args.contexts), tw, tl, info["bytes"] / 1e9 / tl))
+        log("[bench] source: " + source)
+    else:
+        st = ChronoMindB200.from_matrix(shard, cfg, sharding.shard_attrs(ts_s, rank, world), sharding.shard_attrs(ts_n, rank, world),
+                                        sharding.shard_attrs(decay, rank, world)).set_shard(rank, world)
     graph_how = graph_s = None
     if want_hnsw:
         graph_how, graph_s = build_or_load_graph(st, args, graph_cache_path(n_rows, DIM, args.data, args.efc, rank, world),
@@ -704,6 +748,35 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_bytes": "dist_evals*dim*4 + list_entries*4 + dim*4 per query, counters == CPU oracle's at equal ef",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md"},
             "l2": "%.2f GB fp32 rows per GPU gathered at random: larger than L2; %d query batches rotated" % (shard.shape[0] * DIM * 4 / 1e9, nb)}
+    # ---- search_in_context block (only a snapshot-loaded store carries contexts) -------------------------
+    context = None
+    if ctx_rows is not None and args.contexts > 1 and K <= 128:
+        c_steps = max(3, min(args.steps, 10))
+        rngc = np.random.default_rng(SEED ^ 0xC8)
+        want_labels = [rngc.integers(0, args.contexts, size=nq) for _ in range(2)]
+        label_to_id = np.array([st.context_id("ctx%05d" % c) for c in range(args.contexts)], dtype=np.uint32)   # ids = order of first appearance
+        want_ids = [label_to_id[w] for w in want_labels]
+
+        def step_ctx(i):
+            return st.search_in_context(want_ids[i % 2], q_host[i % 2].numpy(), K, now=NOW, temporal_weight=TEMPORAL_W,
+                                        base_decay_rate=BASE_DECAY)
+        step_ctx(0)
+        engine.profile_enable(True)
+        engine.profile_read()
+        c_secs, c_res = timed_host(step_ctx, 2, c_steps, callers=1)
+        c_kms, c_kn = engine.profile_read()
+        engine.profile_enable(False)
+        c_res = step_ctx(1)
+        cc = engine.last_counters()
+        context = {"workload": "ChronoMind::search_in_context, %d-query batch over %d contexts of the %dx%d store, k=%d, w=%.1f, host buffers"
+                               % (nq, args.contexts, n_rows, DIM, K, TEMPORAL_W),
+                   "e2e_qps": nq * c_steps / c_secs, "ms_per_batch": 1000.0 * c_secs / c_steps, "engine": cc["exact_engine"],
+                   "fallback_queries": cc["fallback_queries"], "rescored_per_query": cc["rescored"] / nq,
+                   "scan_kernel_ms_avg": c_kms / max(c_kn, 1),
+                   "layout": "rows sorted by context on the device, queries grouped by context per call, per-pair tile ranges",
+                   "_last": (want_labels[1], c_res)}
+        log("[bench] search_in_context: %.0f q/s e2e (%.2f ms per batch, biased scan %.2f ms)"
+            % (context["e2e_qps"], context["ms_per_batch"], context["scan_kernel_ms_avg"]))
     clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline + parity of the timed results (rank 0, N = 1) --------------------------------------------------
@@ -750,6 +823,16 @@ def run_ours(args, rank, world, local_rank):
             hnsw["cpu_baseline"] = {k: cpu[k] for k in ("value", "sample", "hnsw_parity_ids_dists_counters")}
         elif exact is not None:
             cpu.update({"value": cpu["brute_force_qps"], "sample": cpu["brute_force_sample"], "engine": "brute force (oracle port)"})
+        if context is not None:
+            import oracle
+            want_l, (gi, gs) = context.pop("_last")
+            ns = 64
+            t1 = time.time()
+            rc, wi, ws = oracle.search_in_context(shard, ctx_rows, queries_all[nq:nq + ns], want_l[:ns].astype(np.uint32), K, TEMPORAL_W,
+                                                  BASE_DECAY, ts_s, ts_n, decay, NOW[0], NOW[1], threads=threads_all)
+            bad = order_mismatches_beyond_ties(gi[:ns], wi, gs[:ns], ws) if rc == 0 else -1
+            context["parity_on_sample"] = {"queries": ns, "oracle_rc": rc, "order_mismatches_beyond_1e-5_ties": bad,
+                                           "cpu_qps": ns / (time.time() - t1)}
         log("[bench] cpu baseline + parity in %.1fs: %s" % (time.time() - t0, cpu))
 
     if rank == 0:
@@ -793,6 +876,10 @@ def run_ours(args, rank, world, local_rank):
         line["clocks"] = clocks
         if hnsw is not None:
             line["hnsw"] = hnsw
+        if context is not None:
+            context.pop("_last", None)
+            line["search_in_context"] = context
+        line["config"]["source"] = source
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -890,6 +977,11 @@ def main():
     ap.add_argument("--recall-sample", type=int, default=256, help="reference arm: queries whose brute-force truth picks the operating ef")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW block (graph build + ef sweep)")
+    ap.add_argument("--source", default="auto", choices=["auto", "snapshot", "matrix"],
+                    help="how the corpus reaches the engine at N = 1: 'snapshot' writes it as a CHRONO1 v2 file (save_snapshot's "
+                         "container) and loads that through cm_index_from_snapshot, like a ChronoMind deployment's data; 'matrix' "
+                         "hands the rows over directly; auto = snapshot up to 4 GB of rows")
+    ap.add_argument("--contexts", type=int, default=64, help="contexts the snapshot's records are spread over (search_in_context block)")
     ap.add_argument("--no-graph-cache", action="store_true", help="neither read nor write the /tmp graph sidecar")
     ap.add_argument("--abi-group", action="store_true",
                     help="drive the N GPUs from ONE process through cm_group_* (NCCL inside the library) instead of torchrun ranks")

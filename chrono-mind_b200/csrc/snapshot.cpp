@@ -10,6 +10,7 @@
 // Error mapping follows load_snapshot: short/bad magic/version/checksum -> InvalidSnapshot, open/read
 // failures -> Io, body decode failures -> Serialization; then Config::validate (src/config.rs:97-143) and
 // Memory::validate (src/types.rs:93-121) as `ChronoMind::new` / `insert` would apply them.
+#include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -190,6 +191,8 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   out->memories.clear();
   out->memories.reserve((size_t)count);
   out->vectors.clear();
+  // one allocation for the usual file (every record `dimensions` floats); never more than the body can hold
+  out->vectors.reserve((size_t)std::min<uint64_t>(count * cfg.dimensions, c.left / 4));
   for (uint64_t i = 0; i < count; ++i) {
     SnapshotMemory m;
     if (!c.str(&m.id) || !valid_utf8(m.id)) return ser("bad memory id string");

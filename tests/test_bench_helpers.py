@@ -45,3 +45,15 @@ def test_both_arms_name_the_same_workload():
     a = bench.workload_string(1_000_000, 768, "emb", 10_000, 10)
     assert "1000000x768" in a and "recall@10>=0.95" in a and "configs[1 and 2]" in a
     assert bench.workload_string(10_000_000, 768, "emb", 10_000, 10).endswith("configs[3])")
+
+
+def test_order_mismatches_beyond_ties_counts_only_unexplained_positions():
+    want_ids = np.array([[1, 2, 3, 4]])
+    want_sc = np.array([[0.1, 0.2, 0.2 + 1e-9, 0.5]])
+    assert bench.order_mismatches_beyond_ties(want_ids, want_ids, want_sc, want_sc) == 0
+    swapped = np.array([[1, 3, 2, 4]])                       # a swap inside the near-tie: explained
+    assert bench.order_mismatches_beyond_ties(swapped, want_ids, want_sc, want_sc) == 0
+    wrong = np.array([[9, 2, 3, 4]])                         # a different id with a clear gap around it
+    assert bench.order_mismatches_beyond_ties(wrong, want_ids, want_sc, want_sc) == 1
+    off = want_sc * (1 + 1e-3)                               # scores off by more than 1e-5 relative
+    assert bench.order_mismatches_beyond_ties(want_ids, want_ids, off, want_sc) == 4
