@@ -114,7 +114,9 @@ cm_status cm_index_set_attrs(cm_index* idx, const uint64_t* ts_secs, const uint3
 /* Store-level contexts (`MemoryAttributes.context`, src/types.rs:32-49) for cm_search_in_context: `raw_x` [n][dim]
  * are the rows AS STORED (`StoredMemory.data`, not preprocessed — `search_in_context` calls `metric.distance` on
  * them), `context_ids` [n] one id per handle. Snapshot-loaded indexes carry both already (ids in order of first
- * appearance, see cm_index_context_id). `context_ids` may be NULL (one context). Must precede cm_index_upload. */
+ * appearance, see cm_index_context_id). `context_ids` may be NULL (one context). Must precede cm_index_upload.
+ * With two or more distinct ids the upload also keeps a copy of the bf16 rows ORDERED BY CONTEXT (2 bytes per element
+ * of device memory): a batch of context searches then only scans the row ranges of the contexts it asks for. */
 cm_status cm_index_set_contexts(cm_index* idx, const float* raw_x, const uint32_t* context_ids);
 /* Context id of a label of a snapshot-loaded index; CM_NO_ID when no memory carries it. */
 uint32_t cm_index_context_id(const cm_index* idx, const char* label);
