@@ -109,6 +109,7 @@ struct SnapshotMemory {
   std::string id;
   uint64_t data_offset;  // into SnapshotData::vectors (floats)
   uint64_t data_len;     // floats in the record (== config.dimensions once validated)
+  bool data_finite = true;  // no NaN/Inf among them
   uint64_t ts_secs;
   uint32_t ts_nanos;
   float importance;

@@ -15,6 +15,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 
 #include "cm_internal.h"
 
@@ -51,6 +56,80 @@ uint32_t crc32(const uint8_t* p, size_t n) {
   while (n--) c = T.t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
   return ~c;
 }
+
+// crc(A || B) from crc(A), crc(B) and |B|: multiply crc(A) by x^(8|B|) modulo the CRC polynomial, by squaring a
+// GF(2) 32x32 operator (the classic combine construction), then xor crc(B).
+uint32_t gf2_times(const uint32_t* mat, uint32_t vec) {
+  uint32_t sum = 0;
+  for (; vec; vec >>= 1, ++mat)
+    if (vec & 1) sum ^= *mat;
+  return sum;
+}
+void gf2_square(uint32_t* sq, const uint32_t* mat) {
+  for (int n = 0; n < 32; ++n) sq[n] = gf2_times(mat, mat[n]);
+}
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) return crc1;
+  uint32_t even[32], odd[32];
+  odd[0] = 0xEDB88320u;  // operator for one zero BIT
+  for (uint32_t n = 1, row = 1; n < 32; ++n, row <<= 1) odd[n] = row;
+  gf2_square(even, odd);  // two bits
+  gf2_square(odd, even);  // four bits
+  do {                    // apply len2 zero BYTES: first squaring gives the one-byte operator
+    gf2_square(even, odd);
+    if (len2 & 1) crc1 = gf2_times(even, crc1);
+    len2 >>= 1;
+    if (!len2) break;
+    gf2_square(odd, even);
+    if (len2 & 1) crc1 = gf2_times(odd, crc1);
+    len2 >>= 1;
+  } while (len2);
+  return crc1 ^ crc2;
+}
+
+unsigned host_threads() {
+  unsigned t = std::thread::hardware_concurrency();
+  return t ? (t > 32 ? 32 : t) : 1;
+}
+
+// fn(part, parts) on `parts` threads.
+template <class F>
+void run_parts(unsigned parts, F fn) {
+  if (parts <= 1) {
+    fn(0u, 1u);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < parts; ++t) th.emplace_back(fn, t, parts);
+  fn(0u, parts);
+  for (auto& x : th) x.join();
+}
+
+// CRC of a large buffer: slices in parallel, combined in order.
+uint32_t crc32_parallel(const uint8_t* p, size_t n) {
+  const unsigned parts = n < (8u << 20) ? 1u : host_threads();
+  if (parts == 1) return crc32(p, n);
+  std::vector<uint32_t> part_crc(parts);
+  std::vector<size_t> part_len(parts);
+  const size_t step = (n / parts + 63) & ~(size_t)63;
+  run_parts(parts, [&](unsigned t, unsigned) {
+    const size_t lo = std::min(n, (size_t)t * step), hi = t + 1 == parts ? n : std::min(n, lo + step);
+    part_len[t] = hi - lo;
+    part_crc[t] = crc32(p + lo, hi - lo);
+  });
+  uint32_t c = part_crc[0];
+  for (unsigned t = 1; t < parts; ++t) c = crc32_combine(c, part_crc[t], part_len[t]);
+  return c;
+}
+
+// The snapshot file, mapped read-only (no 3 GB copy for a million 768-d records).
+struct MappedFile {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  ~MappedFile() {
+    if (p && n) munmap(const_cast<uint8_t*>(p), n);
+  }
+};
 
 struct Cursor {
   const uint8_t* p;
@@ -126,29 +205,40 @@ cm_status validate_config(const cm_config& c) {  // src/config.rs:97-143
 }
 
 cm_status read_snapshot(const char* path, SnapshotData* out) {
-  FILE* f = std::fopen(path, "rb");
-  if (!f) {
-    set_error(std::string("io error: ") + std::strerror(errno) + ": " + path);
-    return CM_ERR_IO;
-  }
-  std::vector<uint8_t> blob;
+  MappedFile file;
   {
-    std::fseek(f, 0, SEEK_END);
-    long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    if (sz < 0) {
-      std::fclose(f);
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) {
+      set_error(std::string("io error: ") + std::strerror(errno) + ": " + path);
+      return CM_ERR_IO;
+    }
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0 || sb.st_size < 0) {
+      ::close(fd);
       set_error("io error: cannot size snapshot");
       return CM_ERR_IO;
     }
-    blob.resize((size_t)sz);
-    size_t got = sz ? std::fread(blob.data(), 1, (size_t)sz, f) : 0;
-    std::fclose(f);
-    if (got != (size_t)sz) {
-      set_error("io error: short read");
-      return CM_ERR_IO;
+    file.n = (size_t)sb.st_size;
+    if (file.n) {
+      void* m = ::mmap(nullptr, file.n, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) {
+        ::close(fd);
+        file.n = 0;
+        set_error(std::string("io error: ") + std::strerror(errno) + ": " + path);
+        return CM_ERR_IO;
+      }
+      file.p = static_cast<const uint8_t*>(m);
+      ::madvise(m, file.n, MADV_SEQUENTIAL);
     }
+    ::close(fd);
   }
+  struct Blob {  // what the header checks below read
+    const uint8_t* p;
+    size_t n;
+    size_t size() const { return n; }
+    const uint8_t* data() const { return p; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+  } blob{file.p, file.n};
   auto invalid = [](const std::string& m) {
     set_error("invalid snapshot: " + m);
     return CM_ERR_INVALID_SNAPSHOT;
@@ -161,7 +251,7 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   if (blob.size() < 12) return invalid("missing body checksum");
   uint32_t expected;
   std::memcpy(&expected, blob.data() + 8, 4);
-  uint32_t actual = crc32(blob.data() + 12, blob.size() - 12);
+  uint32_t actual = crc32_parallel(blob.data() + 12, blob.size() - 12);
   if (actual != expected) {
     char buf[128];
     std::snprintf(buf, sizeof buf, "body checksum mismatch (expected %08x, got %08x): the file is corrupt", expected,
@@ -191,8 +281,9 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   out->memories.clear();
   out->memories.reserve((size_t)count);
   out->vectors.clear();
-  // one allocation for the usual file (every record `dimensions` floats); never more than the body can hold
-  out->vectors.reserve((size_t)std::min<uint64_t>(count * cfg.dimensions, c.left / 4));
+  std::vector<const uint8_t*> payload;  // where each record's floats sit in the file
+  payload.reserve((size_t)count);
+  uint64_t total_floats = 0;
   for (uint64_t i = 0; i < count; ++i) {
     SnapshotMemory m;
     if (!c.str(&m.id) || !valid_utf8(m.id)) return ser("bad memory id string");
@@ -200,10 +291,12 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
     if (!c.ok || len > c.left / 4) return ser("vector length exceeds body size");
     // decode first, judge later: bincode reads the whole body before `load_snapshot` inserts anything, so a
     // truncated tail is a Serialization error even when an earlier record would fail validation
-    m.data_offset = out->vectors.size();
+    m.data_offset = total_floats;
     m.data_len = len;
-    out->vectors.resize(m.data_offset + len);
-    c.take(out->vectors.data() + m.data_offset, len * 4);
+    payload.push_back(c.p);  // copied (and checked for NaN/Inf) in parallel once every record's place is known
+    total_floats += len;
+    c.p += len * 4;
+    c.left -= len * 4;
     m.ts_secs = c.u64();
     m.ts_nanos = c.u32();
     m.importance = c.f32();
@@ -224,6 +317,22 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   }
   // bincode::deserialize tolerates trailing bytes.
 
+  // The payloads: one allocation, copied by all host threads; the NaN/Inf test `Memory::validate` needs rides along.
+  out->vectors.resize((size_t)total_floats);
+  {
+    float* dst = out->vectors.data();
+    std::vector<SnapshotMemory>& mem = out->memories;
+    const uint64_t n = mem.size();
+    run_parts(n < 4096 ? 1u : host_threads(), [&](unsigned t, unsigned parts) {
+      for (uint64_t i = n * t / parts, e = n * (t + 1) / parts; i < e; ++i) {
+        float* d = dst + mem[i].data_offset;
+        std::memcpy(d, payload[i], mem[i].data_len * 4);
+        bool fin = true;
+        for (uint64_t j = 0; j < mem[i].data_len; ++j) fin &= std::isfinite(d[j]);
+        mem[i].data_finite = fin;
+      }
+    });
+  }
   return validate_config(cfg);  // ChronoMind::new (src/store.rs:188) — before any insert
 }
 
@@ -244,12 +353,10 @@ cm_status validate_snapshot_memory(const SnapshotData& snap, uint64_t i) {
     set_error(buf);
     return CM_ERR_INVALID_DIMENSIONS;
   }
-  const float* v = snap.vectors.data() + m.data_offset;
-  for (uint64_t j = 0; j < cfg.dimensions; ++j)
-    if (!std::isfinite(v[j])) {
-      set_error("invalid vector data: vector " + m.id + " contains NaN or infinite components");
-      return CM_ERR_INVALID_VECTOR;
-    }
+  if (!m.data_finite) {  // computed by the parallel payload pass of read_snapshot
+    set_error("invalid vector data: vector " + m.id + " contains NaN or infinite components");
+    return CM_ERR_INVALID_VECTOR;
+  }
   if (!std::isfinite(m.importance) || m.importance < 0.0f || m.importance > 1.0f) {
     set_error("invalid importance value: must be within [0.0, 1.0]");
     return CM_ERR_INVALID_IMPORTANCE;

@@ -392,3 +392,37 @@ def test_fast_snapshot_writer_is_byte_identical_to_the_codec(tmp_path):
     assert st.external_id(0) == "m000000000" and st.external_id(n - 1) == "m%09d" % (n - 1)
     assert st.context_label(5) == "ctx%05d" % ctx[5] and abs(st.importance(17) - imp[17]) < 1e-7
     st.close()
+
+
+def test_large_snapshot_takes_the_parallel_reader_paths(tmp_path):
+    """Files beyond 8 MB are checksummed in slices (CRC-32 combine) and their payloads copied by all host threads: the
+    result must be what the small-file path gives — same store, and a flipped byte anywhere is still a checksum error."""
+    n, dim = 12_000, 256
+    rng = np.random.default_rng(8)
+    rows = rng.normal(size=(n, dim)).astype(np.float32)
+    ts_s, ts_n, dec = datasets.temporal_attrs(n, 8, 1_790_000_000)
+    ctx = rng.integers(0, 5, size=n).astype(np.uint32)
+    p = str(tmp_path / "big.chrono")
+    info = datasets.write_snapshot(p, rows, ts_s, ts_n, dec, ctx, 5)
+    assert info["bytes"] > (8 << 20)
+    st = ChronoMindB200.from_snapshot(p)
+    assert len(st) == n and st.external_id(n - 1) == "m%09d" % (n - 1) and st.context_label(n - 1) == "ctx%05d" % ctx[n - 1]
+    want = oracle.preprocess_rows(rows)
+    for h in (0, 1, 4095, 4096, n // 2, n - 1):                   # across the reader's thread slices
+        assert np.array_equal(st.vector(h).view(np.uint32), want[h].view(np.uint32))
+    st.close()
+    blob = bytearray(open(p, "rb").read())
+    for pos in (12 + 100, len(blob) // 3, len(blob) - 5):
+        bad = bytearray(blob)
+        bad[pos] ^= 0x40
+        q = str(tmp_path / "bad.chrono")
+        open(q, "wb").write(bad)
+        with pytest.raises(CmError) as e:
+            ChronoMindB200.from_snapshot(q)
+        assert e.value.kind == "InvalidSnapshot" and "checksum" in str(e.value)
+    nan_rows = rows.copy()
+    nan_rows[7777, 3] = np.nan                                     # found by the parallel payload pass, reported per record
+    datasets.write_snapshot(p, nan_rows, ts_s, ts_n, dec, ctx, 5)
+    with pytest.raises(CmError) as e:
+        ChronoMindB200.from_snapshot(p)
+    assert e.value.kind == "InvalidVector" and "m000007777" in str(e.value)
