@@ -1085,7 +1085,8 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   const size_t room = l.leave_room && l.k <= 16 ? 40 * 1024 : 0;  // K2 (~34 KB + 1 KB reserved) beside this kernel
   const uint32_t blocks_max = (uint32_t)std::min<size_t>(kMaxSlots + 16, (kMaxSmem - fixed - room) / kBlockBytes);
   if (blocks_max < 4) return cudaErrorInvalidValue;
-  const uint32_t ring_min = std::min(6u, blocks_max);
+  // (11 blocks beside a rescore CTA: 4 + 7 measured 11.10 ms against 11.19 for 5 + 6 and 11.17 all-streamed)
+  const uint32_t ring_min = std::min(room ? 7u : 6u, blocks_max);
   uint32_t q_res = std::min<uint32_t>(std::min<uint32_t>(a.k_blocks, 7), blocks_max - ring_min), slots = 0;
   if (const char* env = getenv("CM_SCAN_QRES"))
     q_res = std::min<uint32_t>(std::min<uint32_t>(a.k_blocks, (uint32_t)std::max(0, atoi(env))), blocks_max - 3);
