@@ -55,6 +55,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "device_common.cuh"
@@ -69,7 +70,7 @@ constexpr uint32_t PAIR_M = 256;    // query rows per CTA pair (UMMA M)
 constexpr uint32_t BN = 256;        // corpus rows per tile (UMMA N)
 constexpr uint32_t BN_HALF = 128;   // corpus rows each CTA stages
 constexpr uint32_t BK = 64, UMMA_K = 16;
-constexpr uint32_t kAccStages = 2;
+constexpr uint32_t kAccStages = 2;    // the epilogue derives stage and phase from a tile counter: stage = seq & 1
 // Operand blocks: one k-block (BK columns) of a CTA's 128 query rows or of its 128 corpus rows = 16 KB, 128B-swizzled.
 // A CTA keeps the first `q_res` k-blocks of its query rows RESIDENT for a whole work unit and streams everything else
 // (the remaining query blocks and every corpus block) through a ring of `slots` such blocks.
@@ -77,8 +78,8 @@ constexpr uint32_t kBlockBytes = BM * BK * 2;
 static_assert(BM == BN_HALF, "query and corpus blocks share the ring");
 constexpr uint32_t kMaxSlots = 13;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kThreads = 256;
-constexpr uint32_t kSlotChunk = 8;  // candidate slots reserved per atomic
+constexpr uint32_t kThreads = 256;      // 8 warps; the kEpi2 instantiations add a second epilogue warp-quad (384 threads)
+constexpr uint32_t kThreadsEpi2 = 384;
 constexpr uint32_t kCtxSortChunk = 16384;  // queries grouped by context per single-CTA sort (128 KB of keys)
 // Bound on |tensor-core bf16 score - fp32 reference dot| for (at most) unit-length rows of `dim` elements:
 //   operand rounding   both operands to bf16 (unit roundoff 2^-9): |sum(a^b^) - sum(ab)| <= (2^-8 + 2^-18) sum|ab| <= 0.0039101
@@ -216,6 +217,9 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], uint32_t i) {
 struct ScanArgs {
   uint32_t nq, m_pairs, n_tiles, k_blocks, k, splits, slots, q_res;
   float eps2;                    // 2 * eps_for_dim(dim): the candidate margin
+  uint32_t diag_no_hits;         // CM_SCAN_DIAG=1 (measurement only, results invalid): every threshold is +inf
+  uint32_t slot_chunk;           // candidate slots reserved per atomic (8; 32 for k > 32: the reply is a ~1 us stall)
+  uint32_t ladder_n;             // kLadder: buckets of the threshold ladder (shared memory [ladder_n][128] u16 replaces the lists)
   uint32_t* tau_key;             // [m_pairs*256] ordered-uint threshold per query (0 = none yet)
   uint32_t* cand_cnt;            // [m_pairs*256] slots reserved per query
   unsigned long long* cand;      // [m_pairs*256][cap]  (ordered score key << 32 | row); 0 = unused slot
@@ -290,8 +294,52 @@ struct LocalTopK {
   }
 };
 
-template <bool kBiased, bool kPred>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// Running threshold of one thread for LARGE k (kLadder instantiations, k > 32): a histogram of the scores seen so far
+// over a fixed ladder of bounds b(j) = j * 2 / n - 1, instead of the exact top-k list. "At least k distinct live rows
+// scored >= b(j)" proves s_(k) >= b(j), so tau = b(j) - 2 eps is a valid lower bound of s_(k) - 2 eps exactly like the
+// list's k-th best — only up to one ladder step (2 / n) looser, i.e. a few tens of per cent more candidates for K2 to
+// drop. What it buys: recording a score is one 16-bit increment and raising the threshold one load per step, where the
+// list pays an O(k) rescan per improving score with the whole warp waiting on the busiest lane (at k = 100 the
+// epilogue of configs[4] spent ~5,500 of its ~6,000 cycles per tile there).
+//   hist[i]  scores recorded in bucket i, recorded only while i > j (a score below b(j + 1) can never matter again)
+//   above    recorded scores >= b(j + 1) = sum of hist[i] over i > j
+// Only this thread's own bound is tracked: a higher threshold published by another unit of the same query simply
+// filters the hits; the ladder catches up through empty buckets, one load each.
+struct Ladder {
+  unsigned short* hist;  // this thread's column of [n][128]
+  uint32_t n, k, above;
+  int j;                 // current bound b(j); -1: none yet
+  float scale, step;     // n / 2, 2 / n
+  float b_next;          // b(j + 1); -inf before the first bound, +inf at the top of the ladder
+  __device__ __forceinline__ void reset() {
+    for (uint32_t i = 0; i < n; ++i) hist[i * 128] = 0;
+    above = 0;
+    j = -1;
+    b_next = -INFINITY;
+  }
+  __device__ __forceinline__ void record(float s) {  // s >= b_next, not NaN
+    const uint32_t i = (uint32_t)fminf(fmaxf((s + 1.0f) * scale, 0.0f), (float)(n - 1));
+    hist[i * 128] += 1;
+    ++above;
+  }
+  // (s + 1) * scale may round a score a hair below b(i) up into bucket i: the 2^-20 covers that (<= 2^-23 absolute)
+  __device__ __forceinline__ float tau(float eps2) const {
+    return j >= 0 ? (float)j * step - 1.0f - eps2 - 9.5367431640625e-07f : -INFINITY;
+  }
+  __device__ __forceinline__ bool advance() {
+    bool moved = false;
+    while (above >= k && j < (int)n - 1) {
+      ++j;                      // >= k recorded scores reach b(j)
+      above -= hist[j * 128];   // what is left reaches b(j + 1)
+      moved = true;
+    }
+    if (moved) b_next = j < (int)n - 1 ? (float)(j + 1) * step - 1.0f : INFINITY;
+    return moved;
+  }
+};
+
+template <bool kBiased, bool kPred, bool kLadder, bool kEpi2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEpi2 ? kThreadsEpi2 : kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves the slack). The
@@ -300,7 +348,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t kRes = a.q_res, kSlots = a.slots;
   uint8_t* ring = tiles + kRes * kBlockBytes;
   float* lists = reinterpret_cast<float*>(ring + kSlots * kBlockBytes);  // [k][128]
-  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(ring + kSlots * kBlockBytes + (size_t)a.k * 128 * 4);
+  ScanSmemTail* tail = reinterpret_cast<ScanSmemTail*>(ring + kSlots * kBlockBytes +
+                                                       (kEpi2 ? 2 : 1) * (kLadder ? (size_t)a.ladder_n * 128 * 2 : (size_t)a.k * 128 * 4));
   // biased mode: the current tile's 256 row biases and context ids, one slot per accumulator stage
   float* tile_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + ((sizeof(ScanSmemTail) + 15) & ~(size_t)15));
   uint32_t* tile_ctx = reinterpret_cast<uint32_t*>(tile_bias + kAccStages * BN);
@@ -446,12 +495,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ===== epilogue: threshold select straight out of TMEM =======================================================
     const uint32_t quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const uint32_t row_in_cta = quarter * 32 + lane;   // accumulator row == TMEM lane
+    // kEpi2 (short rows: a tile's MMAs take a few hundred cycles and ONE warp per scheduler, with every ALU and memory
+    // latency exposed, cannot keep up): two epilogue warp-quads, quad e draining accumulator stage e — consecutive tiles
+    // alternate between them, so two tiles are filtered at a time and each scheduler has two warps to interleave. A
+    // query's two threads keep separate running thresholds (each over the rows it saw: both valid lower bounds) and
+    // meet through tau_key like the units of different clusters do.
+    const uint32_t quad = kEpi2 ? (warp - 4) >> 2 : 0;
+    constexpr bool kTuned = kEpi2 || kLadder;  // the shapes whose epilogue is the bound
     LocalTopK top;
-    top.list = lists + row_in_cta;
+    top.list = lists + (size_t)quad * a.k * 128 + row_in_cta;
     top.k = a.k;
+    Ladder lad;
+    lad.hist = reinterpret_cast<unsigned short*>(lists) + (size_t)quad * a.ladder_n * 128 + row_in_cta;
+    lad.n = a.ladder_n;
+    lad.k = a.k;
+    lad.scale = 0.5f * (float)a.ladder_n;
+    lad.step = 2.0f / (float)a.ladder_n;  // ladder_n is a power of two: every bound is exact in fp32
     const uint32_t empty_bar0 = map_to_cta(smem_u32(&tail->tmem_empty[0]), 0);
     const uint32_t empty_bar1 = map_to_cta(smem_u32(&tail->tmem_empty[1]), 0);
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t seq = 0;  // tiles this cluster has scanned so far: tile `seq` lands in accumulator stage seq & 1
     for (uint32_t u = cluster_id; u < units; u += n_clusters) {
       const uint32_t m = u % a.m_pairs, sp = u / a.m_pairs;
       uint32_t t0, t1;
@@ -468,18 +530,30 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       top.filled = 0;
       top.min_pos = 0;
       top.kth = -INFINITY;
+      if constexpr (kLadder) lad.reset();
       uint32_t slot_next = 0, slots_left = 0;
+      // large k: the next chunk of slots is reserved while half of the current one is still free, so the atomic's reply
+      // (a ~1 us stall of the whole warp when waited for in place) is back before it is needed
+      uint32_t slot_ahead = 0;
+      bool have_ahead = false;
+      const bool look_ahead = a.slot_chunk > 8;
       uint32_t npend = 0;
       float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, pend3 = 0.0f;
+      uint32_t tk_next = 0;     // the shared threshold, fetched one tile ahead (an L2 round trip per tile otherwise)
+      bool tk_ready = false;
       for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t acc = seq & 1, acc_phase = (seq >> 1) & 1;
+        ++seq;
+        if (kEpi2 && acc != quad) continue;  // the other quad's tile
         float tau = INFINITY;  // padding queries: nothing passes
         if (q_valid && a.join) {
           tau = a.join_tau;
         } else if (q_valid) {
-          const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
+          const uint32_t tk = (kTuned && tk_ready) ? tk_next : *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
           const float g = tk ? key_to_float(tk) : -INFINITY;
-          tau = fmaxf(g, top.filled == top.k ? top.kth - a.eps2 : -INFINITY);
+          tau = fmaxf(g, kLadder ? lad.tau(a.eps2) : (top.filled == top.k ? top.kth - a.eps2 : -INFINITY));
         }
+        if (a.diag_no_hits) tau = INFINITY;
         const uint64_t row0 = (uint64_t)t * BN;
         const bool diag = kPred && t == a.q_base / BN + m;  // the only tile that holds rows at or after the query
         const float* tb = tile_bias + acc * BN;
@@ -497,6 +571,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         mbar_wait(smem_u32(&tail->tmem_full[acc]), acc_phase);
         tc_fence_after();
+        if (kTuned && q_valid && !a.join) {  // next tile's view of the shared threshold: a tile stale at worst, still a lower bound
+          tk_next = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
+          tk_ready = true;
+        }
         const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * BN;
         bool improved = false;
         // Cold start (no threshold yet): first build the running top-k from this tile WITHOUT emitting, so the
@@ -522,13 +600,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               for (int i = 0; i < 32; ++i) {
                 float s = __uint_as_float(r[i]);
                 if (kBiased) s = tcx[c + i] == my_ctx ? s + tb[c + i] : __int_as_float(0x7FC00000);
-                if (s == s && (!diag || row0 + c + i < q_row_id)) top.insert(s);
+                if (s == s && (!diag || row0 + c + i < q_row_id)) {
+                  if constexpr (kLadder) lad.record(s);  // no bound yet: every live row counts
+                  else top.insert(s);
+                }
               }
             }
           }
           if (cold) {
             listed = true;
-            if (top.filled == top.k) {
+            if constexpr (kLadder) {
+              if (lad.advance()) {
+                tau = lad.tau(a.eps2);
+                improved = true;
+              }
+            } else if (top.filled == top.k) {
               tau = top.kth - a.eps2;
               improved = true;
             }
@@ -544,13 +630,43 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (int i = 0; i < 32; ++i)
               r[i] = tcx[c + i] == my_ctx ? __float_as_uint(__uint_as_float(r[i]) + tb[c + i]) : 0x7FC00000u;
           }
-          float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+          // kTuned (epilogue-bound shapes): four independent chains each — a lone warp per scheduler issues a dependent
+          // chain at ALU latency. The long-row kernel keeps the round-1 single chains (its epilogue has slack, and the
+          // A/B on the 768-d headline put the tuned form 0.5 % behind).
+          float mx;
+          if constexpr (kTuned) {
+            float mx0 = __uint_as_float(r[0]), mx1 = __uint_as_float(r[1]), mx2 = __uint_as_float(r[2]), mx3 = __uint_as_float(r[3]);
 #pragma unroll
-          for (int i = 2; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));  // fmaxf drops NaN
+            for (int i = 4; i < 32; i += 4) {  // fmaxf drops NaN
+              mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+              mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+            }
+            mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          } else {
+            mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+#pragma unroll
+            for (int i = 2; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));  // fmaxf drops NaN
+          }
           if (mx >= tau) {  // rare: ~1e-4 of the scores reach a converged threshold
+            // (a two-level search — scan only the strided class whose partial maximum passes, 8 compares and a 7-select
+            // pick — was measured 15-50 % SLOWER, also on the 768-d headline: four divergent regions instead of one)
             uint32_t mask = 0;
+            if constexpr (kTuned) {
+              uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[i]) >= tau) ? (1u << i) : 0u;
+              for (int i = 0; i < 32; i += 4) {
+                mk0 |= (__uint_as_float(r[i]) >= tau) ? (1u << i) : 0u;
+                mk1 |= (__uint_as_float(r[i + 1]) >= tau) ? (2u << i) : 0u;
+                mk2 |= (__uint_as_float(r[i + 2]) >= tau) ? (4u << i) : 0u;
+                mk3 |= (__uint_as_float(r[i + 3]) >= tau) ? (8u << i) : 0u;
+              }
+              mask = (mk0 | mk1) | (mk2 | mk3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[i]) >= tau) ? (1u << i) : 0u;
+            }
             while (mask) {
               const uint32_t i = __ffs(mask) - 1;
               mask &= mask - 1;
@@ -564,18 +680,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 }
               } else if (s >= tau) {  // tau may have risen inside this loop
                 if (slots_left == 0) {
-                  slot_next = atomicAdd(&a.cand_cnt[q], kSlotChunk);
-                  slots_left = kSlotChunk;
+                  slot_next = have_ahead ? slot_ahead : atomicAdd(&a.cand_cnt[q], a.slot_chunk);
+                  have_ahead = false;
+                  slots_left = a.slot_chunk;
                 }
                 if (slot_next < a.cap)
                   my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)(row0 + c + i);
                 ++slot_next;
                 --slots_left;
+                if (look_ahead && !have_ahead && slots_left == a.slot_chunk / 2) {
+                  slot_ahead = atomicAdd(&a.cand_cnt[q], a.slot_chunk);
+                  have_ahead = true;
+                }
                 // The running top-k is NOT updated per hit: an O(k) insert inside this divergent loop stalls the whole
                 // warp for one lane's hit (32x the cost at k = 100). Scores that would improve it are parked in
                 // registers and inserted after the tile by all lanes together; only a full park (threshold still
                 // converging: hits are frequent) is flushed in place, four inserts at a time.
-                if (!listed && (top.filled < top.k || s > top.kth)) {
+                if constexpr (kLadder) {
+                  if (!listed && s >= lad.b_next) lad.record(s);
+                } else if (!listed && (top.filled < top.k || s > top.kth)) {
                   if (npend == 4) {
                     improved |= top.insert(pend0);
                     improved |= top.insert(pend1);
@@ -590,6 +713,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                   else pend3 = s;
                   ++npend;
                 }
+              }
+            }
+            if constexpr (kLadder) {  // k recorded scores reach the next bound: raise the threshold right here
+              if (lad.above >= lad.k && lad.advance()) {
+                tau = fmaxf(tau, lad.tau(a.eps2));
+                improved = true;
               }
             }
           }
@@ -614,10 +743,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? empty_bar1 : empty_bar0);
-        if (++acc == kAccStages) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
         // parked scores -> running top-k (all lanes insert together: the cost is the busiest lane's, not the sum)
         if (npend > 0) improved |= top.insert(pend0);
         if (npend > 1) improved |= top.insert(pend1);
@@ -625,9 +750,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (npend > 3) improved |= top.insert(pend3);
         npend = 0;
         // publish the lower bound s_(k) - 2 eps for the other clusters working on this query
-        if (improved && q_valid && top.filled == top.k) atomicMax(&a.tau_key[q], total_key(top.kth - a.eps2));
+        if constexpr (kLadder) {
+          if (improved && q_valid && lad.j >= 0) atomicMax(&a.tau_key[q], total_key(lad.tau(a.eps2)));
+        } else if (improved && q_valid && top.filled == top.k) {
+          atomicMax(&a.tau_key[q], total_key(top.kth - a.eps2));
+        }
       }
       // reserved but unused candidate slots: mark empty
+      if (have_ahead && slots_left == 0) slot_next = slot_ahead, slots_left = a.slot_chunk, have_ahead = false;
+      if (have_ahead)  // a whole reserved chunk that was never started
+        for (uint32_t i = 0; i < a.slot_chunk; ++i)
+          if (slot_ahead + i < a.cap) my_cand[slot_ahead + i] = 0ull;
       while (slots_left) {
         if (slot_next < a.cap) my_cand[slot_next] = 0ull;
         ++slot_next;
@@ -675,6 +808,7 @@ struct RescoreArgs {
   uint32_t region;        // bytes of the shared keys / row-buffer region (128-byte multiple)
   uint32_t pred;          // predecessor mode: query q has only pred_base + q rows to choose from
   uint32_t pred_base;
+  uint32_t debug;         // CM_RS_DEBUG: print why a query was flagged
   uint32_t* ids;
   float* dist;
   uint32_t* flag_count;   // queries that need the fp32 fallback
@@ -682,6 +816,15 @@ struct RescoreArgs {
   uint32_t flag_cap;
   unsigned long long* rescored_total;
 };
+
+// Order statistics of a SMALL key set without a sort: thread i counts the keys below its own (all keys are distinct:
+// a row is a candidate of a query at most once). Broadcast reads, no barriers — the block-wide bitonic sort spends
+// ~15-28 barriers on the 13-30 keys a typical query has here, which was a third of this kernel's stall samples.
+__device__ __forceinline__ uint32_t rank_among(const unsigned long long* keys, uint32_t n, unsigned long long mine) {
+  uint32_t r = 0;
+  for (uint32_t j = 0; j < n; ++j) r += keys[j] < mine ? 1u : 0u;
+  return r;
+}
 
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   extern __shared__ __align__(128) unsigned char rs_smem[];
@@ -694,24 +837,38 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   unsigned long long* dkeys = reinterpret_cast<unsigned long long*>(rs_smem + a.region);  // [RS2_MAX] (distance, row)
   uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);                         // [RS2_MAX] rows to re-score
   float* qs = reinterpret_cast<float*>(rows + RS2_MAX);                                  // [ldq]
-  __shared__ unsigned long long mbar;
+  __shared__ unsigned long long mbar, qbar;
+  __shared__ unsigned long long kth_key;
   __shared__ uint32_t n_surv, n_keep;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  // The prepared query row arrives by ONE bulk copy that completes on its own barrier while the candidates are read
+  // and ranked (a per-thread load loop here was 12 % of the kernel's stall samples, all of it exposed latency).
+  const float* q_src = a.qn + (uint64_t)q * a.ldq;
+  const bool bulk_q = !a.approx && (a.ldq & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.qn) & 15u) == 0;
+  if (tid == 0) {
+    n_surv = 0, n_keep = 0;
+    kth_key = 0ull;
+    rg_mbar_init(&mbar);
+    if (bulk_q) {
+      rg_mbar_init(&qbar);
+      const uint32_t bytes = ((a.dim + 3u) & ~3u) * 4u;
+      const uint32_t bar = rg_smem_u32(&qbar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(rg_smem_u32(qs)), "l"(q_src), "r"(bytes), "r"(bar) : "memory");
+    }
+  }
   const uint32_t cnt_raw = a.cand_cnt[q];
   const uint32_t cnt = min(cnt_raw, a.cap);
   const uint32_t tk = a.tau_key[q];
-  if (tid == 0) {
-    n_surv = 0, n_keep = 0;
-    rg_mbar_init(&mbar);
-  }
-  if (!a.approx)  // the bf16 ranking of `approx` never looks at the fp32 query
-    for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.qn[(uint64_t)q * a.ldq + e];
+  if (!a.approx && !bulk_q)  // the bf16 ranking of `approx` never looks at the fp32 query
+    for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = q_src[e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
     const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
     if (c != 0ull && (uint32_t)(c >> 32) >= tk) {
       uint32_t slot = atomicAdd(&n_surv, 1u);
-      if (slot < a.rs_max) keys[slot] = ~c;  // ascending sort of ~c == descending score
+      if (slot < a.rs_max) keys[slot] = ~c;  // ascending order of ~c == descending score
     }
   }
   __syncthreads();
@@ -719,24 +876,43 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
   uint32_t need = (uint32_t)(a.n_live < a.k ? a.n_live : a.k);
   if (a.pred) need = min(a.k, a.pred_base + q);
   bool bad = cnt_raw > a.cap || ns > a.rs_max || ns < need;
-  uint32_t keep = 0;
+  const bool small = ns <= RS_THREADS;   // one key per thread: ranks by counting instead of a sort
+  uint32_t keep = 0, my_rank = 0;
+  unsigned long long my_key = kKeyMax;
   if (!bad) {
-    const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
-    for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
-    block_bitonic_sort(keys, P);
-    // s_(k): the k-th largest bf16 score (all of the bf16 top-k are in the list, see the header comment)
+    if (small) {
+      if (tid < ns) {
+        my_key = keys[tid];
+        my_rank = rank_among(keys, ns, my_key);
+        if (my_rank == a.k - 1) kth_key = my_key;  // s_(k): the k-th largest bf16 score (the whole bf16 top-k is in the list)
+      }
+    } else {
+      const uint32_t P = next_pow2(ns);
+      for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
+      block_bitonic_sort(keys, P);
+      if (tid == 0 && ns >= a.k) kth_key = keys[a.k - 1];
+    }
+    __syncthreads();
     uint32_t thr = 0;  // ns < k only when fewer than k rows are live: keep everything
-    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - a.eps2);
-    for (uint32_t i = tid; i < ns; i += RS_THREADS)
-      if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);  // sorted: the kept set is a prefix
+    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~kth_key) >> 32)) - a.eps2);
+    if (small) {  // the kept set is a prefix of the score order: its size is the largest kept rank + 1
+      if (tid < ns && (uint32_t)((~my_key) >> 32) >= thr) atomicMax(&n_keep, my_rank + 1);
+    } else {
+      for (uint32_t i = tid; i < ns; i += RS_THREADS)
+        if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);
+    }
     __syncthreads();
     keep = n_keep;
     bad = !a.approx && keep > RS2_MAX;
   }
+  if (bulk_q) rg_mbar_wait(rg_smem_u32(&qbar), 0);  // landed long ago; no CTA may exit with a copy into its memory pending
   if (bad) {
     if (tid == 0) {
       uint32_t slot = atomicAdd(a.flag_count, 1u);
       if (slot < a.flag_cap) a.flag_list[slot] = q;
+      if (a.debug)
+        printf("[rescore] query %u flagged: emitted %u (cap %u) above-threshold %u (max %u, need %u) keep %u tau_key %08x\n", q,
+               cnt_raw, a.cap, ns, a.rs_max, need, keep, tk);
     }
     // The fp32 fallback overwrites this row; if more queries are flagged than it absorbs the row stays
     // visibly invalid (CM_NO_ID / NaN) — never a plausible-looking wrong answer.
@@ -747,6 +923,18 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     return;
   }
   if (a.approx) {  // candidate generation for graph construction: bf16 ranking is enough, the host re-measures
+    if (small) {
+      if (tid < ns && my_rank < a.k) {
+        const unsigned long long c = ~my_key;
+        a.ids[(uint64_t)q * a.k + my_rank] = (uint32_t)c;
+        a.dist[(uint64_t)q * a.k + my_rank] = clamp02(1.0f - key_to_float((uint32_t)(c >> 32)));
+      }
+      for (uint32_t i = ns + tid; i < a.k; i += RS_THREADS) {
+        a.ids[(uint64_t)q * a.k + i] = CM_NO_ID_DEV;
+        a.dist[(uint64_t)q * a.k + i] = __int_as_float(0x7F800000);
+      }
+      return;
+    }
     for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
       const bool ok = i < ns;
       const unsigned long long c = ok ? ~keys[i] : 0ull;
@@ -755,11 +943,14 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     }
     return;
   }
-  const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
-  for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
-  for (uint32_t i = tid; i < keep; i += RS_THREADS) rows[i] = (uint32_t)(~keys[i]);
+  // rows to re-score, in score order (keys share their region with the row buffer: read them all before the barrier)
+  if (small) {
+    if (tid < ns && my_rank < keep) rows[my_rank] = (uint32_t)(~my_key);
+  } else {
+    for (uint32_t i = tid; i < keep; i += RS_THREADS) rows[i] = (uint32_t)(~keys[i]);
+  }
   __syncthreads();
-  // exact distances: rounds of RS_ROWS rows, bulk-copied into shared memory, one thread quad per row
+  // exact distances: rounds of a.rows rows, bulk-copied into shared memory, one thread quad per row
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
   uint32_t phase = 0;
   for (uint32_t r0 = 0; r0 < keep; r0 += a.rows) {
@@ -768,14 +959,32 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(RescoreArgs a) {
     const bool active = r_slot < cntr;
     const float d = rg_quad_distance(qs, rowbuf + (size_t)r_slot * row_stride, a.dim, c4, active);
     if (active && c4 == 0) dkeys[r0 + r_slot] = pack_key(d, rows[r0 + r_slot]);
-    __syncthreads();  // rowbuf free for the next round; dkeys visible to the sort
+    __syncthreads();  // rowbuf free for the next round; dkeys visible to the ordering below
   }
-  block_bitonic_sort(dkeys, P2);
-  for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
-    unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
-    bool ok = key != kKeyMax;
-    a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
-    a.dist[(uint64_t)q * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  // order by (TotalF32 distance, handle) and truncate to k
+  if (keep <= RS_THREADS) {
+    if (tid < keep) {
+      const unsigned long long key = dkeys[tid];
+      const uint32_t r = rank_among(dkeys, keep, key);
+      if (r < a.k) {
+        a.ids[(uint64_t)q * a.k + r] = (uint32_t)key;
+        a.dist[(uint64_t)q * a.k + r] = key_to_float((uint32_t)(key >> 32));
+      }
+    }
+    for (uint32_t i = keep + tid; i < a.k; i += RS_THREADS) {
+      a.ids[(uint64_t)q * a.k + i] = CM_NO_ID_DEV;
+      a.dist[(uint64_t)q * a.k + i] = __int_as_float(0x7F800000);
+    }
+  } else {
+    const uint32_t P2 = next_pow2(keep);
+    for (uint32_t i = keep + tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
+    block_bitonic_sort(dkeys, P2);
+    for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
+      unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
+      bool ok = key != kKeyMax;
+      a.ids[(uint64_t)q * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+      a.dist[(uint64_t)q * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+    }
   }
   if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)keep);
 }
@@ -892,18 +1101,32 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
   unsigned long long* dkeys = reinterpret_cast<unsigned long long*>(rs_smem + a.region);  // [RS2_MAX] (score, row)
   uint32_t* rows = reinterpret_cast<uint32_t*>(dkeys + RS2_MAX);
   float* qs = reinterpret_cast<float*>(rows + RS2_MAX);
-  __shared__ unsigned long long mbar;
+  __shared__ unsigned long long mbar, qbar;
+  __shared__ unsigned long long kth_key;
   __shared__ uint32_t n_surv, n_keep;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t qo = a.q_order ? a.q_order[q] : q;  // the caller's row of this query (inputs and outputs live there)
+  // the query row as given: one bulk copy completing on its own barrier while the candidates are read and ranked
+  const float* q_src = a.q_raw + (uint64_t)qo * a.ldq;
+  const bool bulk_q = (a.ldq & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.q_raw) & 15u) == 0;
+  if (tid == 0) {
+    n_surv = 0, n_keep = 0;
+    kth_key = 0ull;
+    rg_mbar_init(&mbar);
+    if (bulk_q) {
+      rg_mbar_init(&qbar);
+      const uint32_t bytes = ((a.dim + 3u) & ~3u) * 4u;
+      const uint32_t bar = rg_smem_u32(&qbar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(rg_smem_u32(qs)), "l"(q_src), "r"(bytes), "r"(bar) : "memory");
+    }
+  }
   const uint32_t cnt_raw = a.cand_cnt[q];
   const uint32_t cnt = min(cnt_raw, a.cap);
   const uint32_t tk = a.tau_key[q];
-  if (tid == 0) {
-    n_surv = 0, n_keep = 0;
-    rg_mbar_init(&mbar);
-  }
-  for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = a.q_raw[(uint64_t)qo * a.ldq + e];
+  if (!bulk_q)
+    for (uint32_t e = tid; e < a.dim; e += RS_THREADS) qs[e] = q_src[e];
   __syncthreads();
   for (uint32_t i = tid; i < cnt; i += RS_THREADS) {
     const unsigned long long c = a.cand[(uint64_t)q * a.cap + i];
@@ -915,19 +1138,36 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
   __syncthreads();
   const uint32_t ns = n_surv;
   bool bad = cnt_raw > a.cap || ns > a.rs_max;
-  uint32_t keep = 0;
+  const bool small = ns <= RS_THREADS;  // ranks by counting instead of a sort (see rescore_kernel)
+  uint32_t keep = 0, my_rank = 0;
+  unsigned long long my_key = kKeyMax;
   if (!bad) {
-    const uint32_t P = next_pow2(ns < 32 ? 32 : ns);
-    for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
-    block_bitonic_sort(keys, P);
+    if (small) {
+      if (tid < ns) {
+        my_key = keys[tid];
+        my_rank = rank_among(keys, ns, my_key);
+        if (my_rank == a.k - 1) kth_key = my_key;
+      }
+    } else {
+      const uint32_t P = next_pow2(ns);
+      for (uint32_t i = ns + tid; i < P; i += RS_THREADS) keys[i] = kKeyMax;
+      block_bitonic_sort(keys, P);
+      if (tid == 0 && ns >= a.k) kth_key = keys[a.k - 1];
+    }
+    __syncthreads();
     uint32_t thr = 0;  // fewer than k candidates: the whole context, keep everything
-    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~keys[a.k - 1]) >> 32)) - a.eps2);
-    for (uint32_t i = tid; i < ns; i += RS_THREADS)
-      if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);
+    if (ns >= a.k) thr = total_key(key_to_float((uint32_t)((~kth_key) >> 32)) - a.eps2);
+    if (small) {
+      if (tid < ns && (uint32_t)((~my_key) >> 32) >= thr) atomicMax(&n_keep, my_rank + 1);
+    } else {
+      for (uint32_t i = tid; i < ns; i += RS_THREADS)
+        if ((uint32_t)((~keys[i]) >> 32) >= thr) atomicMax(&n_keep, i + 1);
+    }
     __syncthreads();
     keep = n_keep;
     bad = keep > RS2_MAX;
   }
+  if (bulk_q) rg_mbar_wait(rg_smem_u32(&qbar), 0);  // no CTA may exit with a copy into its memory pending
   if (bad) {
     if (tid == 0) {
       uint32_t slot = atomicAdd(a.flag_count, 1u);
@@ -939,11 +1179,17 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
     }
     return;
   }
-  const uint32_t P2 = next_pow2(keep < 32 ? 32 : keep);
-  for (uint32_t i = tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
-  for (uint32_t i = tid; i < keep; i += RS_THREADS) {
-    const uint32_t r = (uint32_t)(~keys[i]);
-    rows[i] = a.perm ? a.perm[r] : r;  // from here on: handles
+  // rows to re-score in score order, as HANDLES from here on (keys share their region with the row buffer)
+  if (small) {
+    if (tid < ns && my_rank < keep) {
+      const uint32_t r = (uint32_t)(~my_key);
+      rows[my_rank] = a.perm ? a.perm[r] : r;
+    }
+  } else {
+    for (uint32_t i = tid; i < keep; i += RS_THREADS) {
+      const uint32_t r = (uint32_t)(~keys[i]);
+      rows[i] = a.perm ? a.perm[r] : r;
+    }
   }
   __syncthreads();
   const uint32_t r_slot = tid >> 2, c4 = tid & 3;
@@ -969,12 +1215,29 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_context_kernel(ContextResc
     }
     __syncthreads();
   }
-  block_bitonic_sort(dkeys, P2);
-  for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
-    unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
-    bool ok = key != kKeyMax;
-    a.ids[(uint64_t)qo * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
-    a.score[(uint64_t)qo * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+  if (keep <= RS_THREADS) {
+    if (tid < keep) {
+      const unsigned long long key = dkeys[tid];
+      const uint32_t r = rank_among(dkeys, keep, key);
+      if (r < a.k) {
+        a.ids[(uint64_t)qo * a.k + r] = (uint32_t)key;
+        a.score[(uint64_t)qo * a.k + r] = key_to_float((uint32_t)(key >> 32));
+      }
+    }
+    for (uint32_t i = keep + tid; i < a.k; i += RS_THREADS) {
+      a.ids[(uint64_t)qo * a.k + i] = CM_NO_ID_DEV;
+      a.score[(uint64_t)qo * a.k + i] = __int_as_float(0x7F800000);
+    }
+  } else {
+    const uint32_t P2 = next_pow2(keep);
+    for (uint32_t i = keep + tid; i < P2; i += RS_THREADS) dkeys[i] = kKeyMax;
+    block_bitonic_sort(dkeys, P2);
+    for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
+      unsigned long long key = i < P2 ? dkeys[i] : kKeyMax;
+      bool ok = key != kKeyMax;
+      a.ids[(uint64_t)qo * a.k + i] = ok ? (uint32_t)key : CM_NO_ID_DEV;
+      a.score[(uint64_t)qo * a.k + i] = ok ? key_to_float((uint32_t)(key >> 32)) : __int_as_float(0x7F800000);
+    }
   }
   if (tid == 0 && a.rescored_total) atomicAdd(a.rescored_total, (unsigned long long)keep);
 }
@@ -1025,10 +1288,11 @@ bool scan_tc_supported(const DeviceIndex& ix, uint32_t k) {
 // Corpus splits per query-tile pair: minimise waves x (tiles per unit + a few tiles of pipeline fill / cold start).
 // Every split of a query starts cold (its own running top-k) and emits ~k·(1 + ln(rows/k)) candidates before its
 // threshold converges, so the number of splits is also bounded by the candidate buffer: splits·k·16 <= cap.
-static uint32_t pick_splits(uint32_t m_pairs, uint32_t n_tiles, uint32_t clusters, uint32_t k, uint32_t cap) {
+static uint32_t pick_splits(uint32_t m_pairs, uint32_t n_tiles, uint32_t clusters, uint32_t k, uint32_t cap, uint32_t per_thread = 1) {
   uint32_t best = 1;
   uint64_t best_cost = ~0ull;
-  const uint32_t max_splits = std::max(1u, cap / (16u * k));
+  // (per_thread = 2: two epilogue threads per query and unit, each with its own threshold over half of the unit's rows)
+  const uint32_t max_splits = std::max(1u, cap / (16u * k * per_thread));
   for (uint32_t s = 1; s <= std::min<uint32_t>(std::min<uint32_t>(n_tiles, 128), max_splits); ++s) {
     uint64_t tiles_per = (n_tiles + s - 1) / s;
     uint64_t waves = ((uint64_t)m_pairs * s + clusters - 1) / clusters;
@@ -1076,7 +1340,19 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.pair_hi = l.pair_hi;
   // context-sorted ranges are short: size the splits for the expected range length, not for the whole corpus
   if (l.pair_lo) a.splits = pick_splits(a.m_pairs, std::max(1u, std::min(l.pair_tiles_avg, a.n_tiles)), clusters, l.k, l.cap);
-  const size_t fixed = 1024 + (size_t)l.k * 128 * 4 + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
+  // Large k without a bias: the per-thread threshold comes from a score histogram (Ladder) instead of an exact top-k list.
+  // 256 buckets (bound step 1/128) unless the operand ring needs the 32 KB more (rows of 8 or more k-blocks): 128 buckets.
+  bool ladder = !biased && !l.join && l.k > 32;
+  if (const char* env = getenv("CM_SCAN_LADDER")) ladder = ladder && atoi(env) != 0;
+  a.ladder_n = ladder ? (a.k_blocks >= 8 ? 128u : 256u) : 0u;
+  // Short rows (<= 3 k-blocks: a tile's MMAs take <= 1.5k cycles) are bound by the epilogue: second epilogue warp-quad.
+  bool epi2 = !biased && !l.join && !l.pred && a.k_blocks <= 3;
+  if (const char* env = getenv("CM_SCAN_EPI2")) epi2 = epi2 && atoi(env) != 0;
+  if (epi2) a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters, l.k, l.cap, 2);
+  a.slot_chunk = l.k > 32 ? 32u : 8u;
+  a.diag_no_hits = getenv("CM_SCAN_DIAG") != nullptr ? 1u : 0u;
+  const size_t lists_bytes = (epi2 ? 2 : 1) * (ladder ? (size_t)a.ladder_n * 128 * 2 : (size_t)l.k * 128 * 4);
+  const size_t fixed = 1024 + lists_bytes + sizeof(ScanSmemTail) + 32 + (biased ? (size_t)kAccStages * BN * 8 : 0);
   // Shared-memory budget in 16 KB operand blocks: `q_res` resident query blocks + a ring of `slots` streamed blocks.
   // Every resident block removes one query block per corpus tile from the L2 -> SM stream (all-streamed the kernel asks
   // for 64 B/clk per SM at full tensor rate, against ~43-48 B/clk per SM the L2 delivers chip-wide). The ring needs six
@@ -1098,13 +1374,16 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.q_res = q_res;
   a.slots = slots;
   const size_t smem = fixed + (size_t)(q_res + slots) * kBlockBytes;
-  auto kernel = biased ? scan_tc_kernel<true, false> : (l.pred ? scan_tc_kernel<false, true> : scan_tc_kernel<false, false>);
+  auto kernel = biased ? scan_tc_kernel<true, false, false, false>
+                : l.pred ? (ladder ? scan_tc_kernel<false, true, true, false> : scan_tc_kernel<false, true, false, false>)
+                : epi2   ? (ladder ? scan_tc_kernel<false, false, true, true> : scan_tc_kernel<false, false, false, true>)
+                         : (ladder ? scan_tc_kernel<false, false, true, false> : scan_tc_kernel<false, false, false, false>);
   if (biased && l.pred) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
   if (e != cudaSuccess) return e;
   const uint32_t units = a.m_pairs * a.splits;
   const unsigned grid = 2u * std::min(clusters, units);  // whole CTA pairs (__cluster_dims__(2,1,1))
-  kernel<<<grid, kThreads, smem, s>>>(map_q, map_x, a);
+  kernel<<<grid, epi2 ? kThreadsEpi2 : kThreads, smem, s>>>(map_q, map_x, a);
   count_launch();
   return cudaGetLastError();
 }
@@ -1134,12 +1413,14 @@ cudaError_t launch_rescore(const DeviceIndex& ix, const RescoreLaunch& l, cudaSt
   a.approx = l.approx ? 1u : 0u;
   a.pred = l.pred ? 1u : 0u;
   a.pred_base = l.pred_base;
+  a.debug = getenv("CM_RS_DEBUG") != nullptr;
   a.eps2 = 2.0f * eps_for_dim(ix.dim);
   const size_t row_stride = (size_t)ix.dim_pad * 4 + RG_ROW_PAD;
   const size_t other = (size_t)RS2_MAX * 12 + (size_t)ix.dim_pad * 4;
   // ~24 KB of row buffer (8 rows of 768 floats; a typical query re-scores ~15-30 rows = 2-4 rounds): the kernel is
   // latency-bound per CTA, so queries in flight per SM matter more than rounds.
   a.rows = std::min<uint32_t>(RS_ROWS, std::max<uint32_t>(4u, (uint32_t)((24u * 1024u + row_stride - 1) / row_stride)));
+  if (const char* env = getenv("CM_RS_ROWS")) a.rows = std::min<uint32_t>(RS_ROWS, std::max(1, atoi(env)));  // sweeps
   while (a.rows > 1 && a.rows * row_stride + other > 200 * 1024) --a.rows;   // very long rows: fewer per round
   a.region = (uint32_t)((std::max<size_t>(a.rows * row_stride, (size_t)a.rs_max * 8) + 127) & ~(size_t)127);
   const size_t smem = a.region + other;

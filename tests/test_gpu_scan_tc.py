@@ -68,6 +68,46 @@ def test_tc_scan_tombstones_duplicates_and_short_rows():
     assert np.all(np.sort(ids[:, :3], axis=1) == np.array([5, 77, 8000])) and np.all(ids[:, 3:] == NO_ID)
 
 
+def test_tc_scan_large_k_threshold_ladder_edge_cases():
+    """k > 32 takes the histogram threshold (Ladder) in K1's epilogue instead of the exact running top-k list: the
+    result must still be the exact top-k where that structure is stressed — every score negative (lowest buckets),
+    scores packed into one bucket (near-duplicates of the query), exact duplicates straddling the k-th place with
+    tombstones, fewer live rows than k, and rows identical to the query (top bucket, score 1.0)."""
+    rng = np.random.default_rng(41)
+    dim = 48
+    # (a) rows in a cone around +e0, queries around -e0: all scores in [-1, -0.5]
+    rows = datasets.unit_vectors(rng, 20000, dim) * 0.35
+    rows[:, 0] += 1.0
+    qs = datasets.unit_vectors(rng, 90, dim) * 0.35
+    qs[:, 0] -= 1.0
+    st = store(rows.astype(np.float32))
+    for k in (33, 100):
+        ids, d = st.search_exact(qs.astype(np.float32), k)
+        wi, wd = oracle.brute_force(oracle.preprocess_rows(rows.astype(np.float32)), qs.astype(np.float32), k, mode="prepared")
+        assert last_counters()["fallback_queries"] == 0
+        assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+    # (b) tight cluster around each query (scores within one ladder step of each other), exact duplicates across the
+    # k-th place, 30 % tombstones
+    base = datasets.unit_vectors(rng, 12000, dim)
+    centers = datasets.unit_vectors(rng, 8, dim)
+    for c in range(8):
+        base[c * 300:(c + 1) * 300] = centers[c] + 0.01 * rng.standard_normal((300, dim)).astype(np.float32)
+    base[5000:5100] = base[10]          # 101 identical rows inside cluster 0
+    base[6000:6040] = centers[3]        # rows identical to a query
+    dele = (rng.uniform(size=12000) < 0.3).astype(np.uint8)
+    q = np.vstack([centers, datasets.unit_vectors(rng, 60, dim)]).astype(np.float32)
+    st = store(base.astype(np.float32), dele)
+    for k in (48, 128):
+        ids, d = st.search_exact(q, k)
+        wi, wd = oracle.brute_force(oracle.preprocess_rows(base.astype(np.float32)), q, k, mode="prepared", deleted=dele)
+        assert np.array_equal(ids, wi) and np.array_equal(bits(d), bits(wd))
+    # (c) fewer live rows than k
+    dele = np.ones(12000, np.uint8)
+    dele[[3, 700, 11999]] = 0
+    ids, d = store(base.astype(np.float32), dele).search_exact(q, 64)
+    assert np.all(np.sort(ids[:, :3], axis=1) == np.array([3, 700, 11999])) and np.all(ids[:, 3:] == NO_ID)
+
+
 def test_tc_scan_nonfinite_query_falls_back_to_fp32():
     """A NaN query yields NaN scores on the tensor cores (nothing passes the threshold): K2 flags the query and the
     in-stream fp32 scan reproduces the reference's result for it; the other queries are unaffected."""
