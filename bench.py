@@ -251,7 +251,7 @@ def build_or_load_graph(st, args, path, seed, device, threads, have_cuda):
             log("[bench] stale graph sidecar ignored: %s" % e)
     if have_cuda and args.build == "gpu":
         st.build_graph_gpu(seed, device, threads)
-        how = "gpu-assisted (all-pairs kNN candidates on the device, select/link on the host)"
+        how = "gpu-assisted (predecessor kNN, select_diverse and reverse-edge re-selection on the device; reachability check on the host)"
     else:
         st.build_graph(seed, threads)
         how = "host (LockFreeHnsw::insert restatement, %d threads)" % threads
@@ -997,7 +997,7 @@ def main():
     ap.add_argument("--dim", type=int, default=DIM, help="vector dimension (default 768; 32 with --k 100 is BASELINE configs[4])")
     ap.add_argument("--k", type=int, default=K, help="neighbors per query (default 10)")
     ap.add_argument("--build", default="gpu", choices=["host", "gpu"],
-                    help="hnsw: graph construction — gpu-assisted (all-pairs kNN candidates on the device, select/link on the "
+                    help="hnsw: graph construction — gpu-assisted (predecessor kNN + select/link on the device, reachability on the "
                          "host) or host (LockFreeHnsw::insert restatement, all cores)")
     args = ap.parse_args()
 

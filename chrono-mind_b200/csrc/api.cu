@@ -906,9 +906,18 @@ cm_status cm_index_from_matrix(const float* x, uint64_t n, uint32_t dim, const c
 cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   if (!out || !path) return fail(CM_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
+  const bool timing = getenv("CM_LOAD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[index_from_snapshot] %-22s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
   SnapshotData snap;
   cm_status st = read_snapshot(path, &snap);
   if (st != CM_OK) return st;
+  lap("read_snapshot");
   uint64_t n = snap.memories.size();
   uint32_t dim = (uint32_t)snap.config.dimensions;
   // Replay `store.insert` record by record in file order (src/persistence.rs:117-119, src/store.rs:226-264):
@@ -936,10 +945,12 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
         return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
     }
   }
+  lap("validate + id replay");
   cm_index* idx = new_index(snap.config, n, dim);
   idx->deleted = std::move(deleted);
   idx->live = live;
   idx->x.resize(n * (uint64_t)dim);
+  lap("allocate rows");
   const float* src = snap.vectors.data();  // every record has exactly `dim` floats now: offsets are i * dim
   float* dst = idx->x.data();
   std::atomic<bool> finite{true};
@@ -949,6 +960,7 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
     if (!row_is_finite(dst + i * dim, dim)) fin->store(false, std::memory_order_relaxed);
   });
   idx->all_finite = finite.load();
+  lap("preprocess rows");
   idx->ext_ids.resize(n);
   // contexts in order of first appearance; the raw rows stay for search_in_context (metric.distance on stored data)
   idx->ctx.resize(n);
@@ -971,6 +983,7 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
     }
   }
   idx->raw = std::move(snap.vectors);
+  lap("attributes + contexts");
   *out = idx;
   return CM_OK;
 }

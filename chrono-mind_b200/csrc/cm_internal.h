@@ -8,6 +8,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/chronomind_b200.h"
@@ -102,6 +104,27 @@ void build_graph_from_layer_lists(const float* x, uint64_t n, uint32_t dim, cons
 void preprocess_row(const float* v, uint32_t n, float* out);
 float dist_prepared_host(const float* a, const float* b, uint32_t n);  // distance_prepared, AVX2+FMA lane order
 
+// Row matrices (gigabytes at the BASELINE sizes) are always filled right after they are sized — by all host threads —
+// so `resize` must not value-initialise them first: a single-threaded zero fill of 3 GB was two thirds of the snapshot
+// load time. `construct(p)` without arguments default-initialises (no store); everything else is std::allocator.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAllocator<U>;
+  };
+  using std::allocator<T>::allocator;
+  template <class U>
+  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+using RowMatrix = std::vector<float, DefaultInitAllocator<float>>;
+
 // ---------------------------------------------------------------------------------------------------------
 // Snapshot records (src/types.rs) as parsed by snapshot.cpp.
 // ---------------------------------------------------------------------------------------------------------
@@ -123,7 +146,7 @@ struct SnapshotMemory {
 struct SnapshotData {
   cm_config config;
   std::vector<SnapshotMemory> memories;
-  std::vector<float> vectors;  // the records' data back to back, file order (data_offset / data_len)
+  RowMatrix vectors;  // the records' data back to back, file order (data_offset / data_len)
 };
 // Returns CM_OK or the status load_snapshot would map to; message via set_error().
 cm_status read_snapshot(const char* path, SnapshotData* out);  // decode + Config::validate only
@@ -183,14 +206,14 @@ struct cm_index {
   cm_config config{};
   uint64_t n = 0;
   uint32_t dim = 0;
-  std::vector<float> x;             // [n][dim] preprocessed rows (host copy: graph build + upload source)
+  cm::RowMatrix x;                    // [n][dim] preprocessed rows (host copy: graph build + upload source)
   std::vector<uint8_t> deleted;     // [n]
   std::vector<uint32_t> pending_removed;  // tombstoned since the last upload / cm_index_sync_deleted
   std::vector<uint64_t> ts_secs;    // [n]
   std::vector<uint32_t> ts_nanos;   // [n]
   std::vector<float> decay;         // [n]
   std::vector<std::string> ext_ids; // snapshot-loaded only
-  std::vector<float> raw;           // [n][dim] rows as stored (`StoredMemory.data`), only with contexts
+  cm::RowMatrix raw;                  // [n][dim] rows as stored (`StoredMemory.data`), only with contexts
   std::vector<uint32_t> ctx;        // [n] context id per handle (empty: no contexts)
   std::vector<uint32_t> ctx_sorted; // context ids in (context, handle) order: the row ranges of the context-sorted device copy
   std::vector<std::string> ctx_labels;  // snapshot-loaded: id -> `MemoryAttributes.context`

@@ -18,6 +18,8 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <chrono>
+#include <cstdlib>
 #include <thread>
 #include <unistd.h>
 
@@ -205,6 +207,15 @@ cm_status validate_config(const cm_config& c) {  // src/config.rs:97-143
 }
 
 cm_status read_snapshot(const char* path, SnapshotData* out) {
+  // CM_LOAD_TIMING=1: stage times of the reader on stderr
+  const bool timing = getenv("CM_LOAD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[read_snapshot] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
   MappedFile file;
   {
     int fd = ::open(path, O_RDONLY);
@@ -252,6 +263,7 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
   uint32_t expected;
   std::memcpy(&expected, blob.data() + 8, 4);
   uint32_t actual = crc32_parallel(blob.data() + 12, blob.size() - 12);
+  lap("map + CRC-32");
   if (actual != expected) {
     char buf[128];
     std::snprintf(buf, sizeof buf, "body checksum mismatch (expected %08x, got %08x): the file is corrupt", expected,
@@ -316,6 +328,7 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
     out->memories.push_back(std::move(m));
   }
   // bincode::deserialize tolerates trailing bytes.
+  lap("record headers");
 
   // The payloads: one allocation, copied by all host threads; the NaN/Inf test `Memory::validate` needs rides along.
   out->vectors.resize((size_t)total_floats);
@@ -333,6 +346,7 @@ cm_status read_snapshot(const char* path, SnapshotData* out) {
       }
     });
   }
+  lap("payload copy + finite check");
   return validate_config(cfg);  // ChronoMind::new (src/store.rs:188) — before any insert
 }
 

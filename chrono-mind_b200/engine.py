@@ -274,7 +274,8 @@ class ChronoMindB200:
         return self
 
     def build_graph_gpu(self, layer_seed: int = 0x5EED, device: int = 0, threads: int = 0, n_candidates: int = 0):
-        """GPU-assisted construction: per-layer all-pairs kNN candidates on the device, select/link on the host."""
+        """GPU-assisted construction: per-layer predecessor kNN, select_diverse and reverse-edge re-selection on the device
+        (`cm_index_build_graph_gpu`); the host keeps the reverse-edge CSR and the reachability check."""
         _check(native().cm_index_build_graph_gpu(self._h, layer_seed & (2 ** 64 - 1), device, threads, n_candidates))
         return self
 

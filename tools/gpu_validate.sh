@@ -9,6 +9,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${ta
 CM_BUILD_TIMING=1 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.log; echo "reference rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.log; echo "bench rc=$?"
 timeout 600 python tools/bench_context.py > gpurun_out/${tag}_context.jsonl 2> gpurun_out/${tag}_context.log; echo "context rc=$?"
+# the per-rank work of the 8-GPU run (a 125k-row shard) on one GPU, and BASELINE configs[4]'s per-GPU shape
+timeout 300 python bench.py --rows 125000 --no-hnsw --no-cpu-baseline --steps 60 --warmup 5 --source matrix > gpurun_out/${tag}_bench_shard125k.json 2> gpurun_out/${tag}_bench_shard125k.log; echo "shard rc=$?"
+timeout 300 python bench.py --rows 4000000 --dim 32 --k 100 --data uniform --no-hnsw --no-cpu-baseline --steps 10 --warmup 3 --source matrix > gpurun_out/${tag}_bench_cfg4.json 2> gpurun_out/${tag}_bench_cfg4.log; echo "cfg4 rc=$?"
 # launch list (shares) of the exact step, one batch in flight
 timeout 300 python bench.py --steps 3 --warmup 2 --streams 1 --callers 1 --no-cpu-baseline --no-hnsw > gpurun_out/${tag}_plain1.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_exact.csv \
