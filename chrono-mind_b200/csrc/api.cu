@@ -366,7 +366,13 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   uint32_t* tau_key = ws->tc_state.as<uint32_t>();
   uint32_t* cand_cnt = tau_key + nq_pad;
   uint8_t* small = ws->small.as<uint8_t>();
-  CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
+  // CM_SCAN_WARM=1 (measurement only: valid only when the SAME batch is repeated): keep the previous launch's thresholds,
+  // i.e. time the scan without its cold start
+  static const bool warm_diag = getenv("CM_SCAN_WARM") != nullptr;
+  if (warm_diag)
+    CM_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq_pad * 4, s));
+  else
+    CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
   CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));  // this chunk's counters
   const void* q_bf16 = ws->qbf16.p;
   if (pq.bf16_ready)

@@ -532,13 +532,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       top.kth = -INFINITY;
       if constexpr (kLadder) lad.reset();
       uint32_t slot_next = 0, slots_left = 0;
-      // large k: the next chunk of slots is reserved while half of the current one is still free, so the atomic's reply
-      // (a ~1 us stall of the whole warp when waited for in place) is back before it is needed
+      // the next chunk of slots is reserved while half of the current one is still free, so the atomic's reply (a ~1 us
+      // stall of the whole warp when waited for in place: 4 % of a small-corpus launch's samples) is back before it is needed
       uint32_t slot_ahead = 0;
       bool have_ahead = false;
-      const bool look_ahead = a.slot_chunk > 8;
-      uint32_t npend = 0;
-      float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, pend3 = 0.0f;
+      const uint32_t look_at = a.slot_chunk / 2;  // slots left in the current chunk when the next one is requested
+      bool parked = false;
+      float pend0 = -INFINITY, pend1 = -INFINITY, pend2 = -INFINITY, pend3 = -INFINITY;
       uint32_t tk_next = 0;     // the shared threshold, fetched one tile ahead (an L2 round trip per tile otherwise)
       bool tk_ready = false;
       for (uint32_t t = t0; t < t1; ++t) {
@@ -549,7 +549,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (q_valid && a.join) {
           tau = a.join_tau;
         } else if (q_valid) {
-          const uint32_t tk = (kTuned && tk_ready) ? tk_next : *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
+          const uint32_t tk = tk_ready ? tk_next : *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
           const float g = tk ? key_to_float(tk) : -INFINITY;
           tau = fmaxf(g, kLadder ? lad.tau(a.eps2) : (top.filled == top.k ? top.kth - a.eps2 : -INFINITY));
         }
@@ -571,7 +571,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         mbar_wait(smem_u32(&tail->tmem_full[acc]), acc_phase);
         tc_fence_after();
-        if (kTuned && q_valid && !a.join) {  // next tile's view of the shared threshold: a tile stale at worst, still a lower bound
+        if (q_valid && !a.join) {  // next tile's view of the shared threshold: a tile stale at worst, still a lower bound
           tk_next = *reinterpret_cast<volatile uint32_t*>(a.tau_key + q);
           tk_ready = true;
         }
@@ -595,7 +595,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             __syncwarp();
             tmem_ld32(taddr + c, r);
             tmem_ld_wait();
-            if (cold) {
+            if (cold && !kBiased && !kLadder && a.k <= 16) {
+              // Small k: only the maximum of every 8 columns is offered to the list — 32 scores of 32 distinct rows per
+              // tile, plenty to fill it, and a k-th best of those is as valid a bound as one of all 256 (on average it is
+              // the ~11th best of the tile instead of the 10th). The warp executes an insert whenever ANY lane has one,
+              // which with all 256 scores was nearly every column: ~13k instructions per cold tile, now ~2k.
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float m = __int_as_float(0x7FC00000);
+#pragma unroll
+                for (int i = 8 * g; i < 8 * g + 8; ++i) {
+                  const float s = __uint_as_float(r[i]);
+                  if (!diag || row0 + c + i < q_row_id) m = fmaxf(m, s);  // fmaxf drops NaN (tombstoned / padding rows)
+                }
+                if (m == m) top.insert(m);
+              }
+            } else if (cold) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 float s = __uint_as_float(r[i]);
@@ -688,30 +703,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                   my_cand[slot_next] = ((unsigned long long)total_key(s) << 32) | (uint32_t)(row0 + c + i);
                 ++slot_next;
                 --slots_left;
-                if (look_ahead && !have_ahead && slots_left == a.slot_chunk / 2) {
+                if (!have_ahead && slots_left == look_at) {
                   slot_ahead = atomicAdd(&a.cand_cnt[q], a.slot_chunk);
                   have_ahead = true;
                 }
                 // The running top-k is NOT updated per hit: an O(k) insert inside this divergent loop stalls the whole
-                // warp for one lane's hit (32x the cost at k = 100). Scores that would improve it are parked in
-                // registers and inserted after the tile by all lanes together; only a full park (threshold still
-                // converging: hits are frequent) is flushed in place, four inserts at a time.
+                // warp for one lane's hit. The tile's FOUR BEST improving scores are parked in registers (pend0 >= pend1
+                // >= pend2 >= pend3) and inserted after the tile by all lanes together. Beyond the first tiles a tile
+                // improves a list at most a few times, and a score that is not offered only leaves the bound a little
+                // lower for a tile or two (the list always holds scores of k distinct rows seen: a valid bound). An
+                // earlier version flushed a full park in place — ~180 instructions with one lane active, up to dozens
+                // of times per tile and warp while thresholds converge: 47 us of every launch (1M x 768: -0.5 %,
+                // a 125k-row shard: -3 %).
                 if constexpr (kLadder) {
                   if (!listed && s >= lad.b_next) lad.record(s);
-                } else if (!listed && (top.filled < top.k || s > top.kth)) {
-                  if (npend == 4) {
-                    improved |= top.insert(pend0);
-                    improved |= top.insert(pend1);
-                    improved |= top.insert(pend2);
-                    improved |= top.insert(pend3);
-                    npend = 0;
+                } else if (!listed) {
+                  if (top.filled < top.k) {  // list not full yet (sparse tiles): cheap appends, no rescan until it fills
+                    improved |= top.insert(s);
                     if (top.filled == top.k) tau = fmaxf(tau, top.kth - a.eps2);
+                  } else if (s > top.kth && s > pend3) {
+                    pend3 = s;
+                    if (pend3 > pend2) { const float x = pend2; pend2 = pend3; pend3 = x; }
+                    if (pend2 > pend1) { const float x = pend1; pend1 = pend2; pend2 = x; }
+                    if (pend1 > pend0) { const float x = pend0; pend0 = pend1; pend1 = x; }
+                    parked = true;
                   }
-                  if (npend == 0) pend0 = s;
-                  else if (npend == 1) pend1 = s;
-                  else if (npend == 2) pend2 = s;
-                  else pend3 = s;
-                  ++npend;
                 }
               }
             }
@@ -744,11 +760,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? empty_bar1 : empty_bar0);
         // parked scores -> running top-k (all lanes insert together: the cost is the busiest lane's, not the sum)
-        if (npend > 0) improved |= top.insert(pend0);
-        if (npend > 1) improved |= top.insert(pend1);
-        if (npend > 2) improved |= top.insert(pend2);
-        if (npend > 3) improved |= top.insert(pend3);
-        npend = 0;
+        if (parked) {  // empty places hold -inf: insert() turns them away
+          improved |= top.insert(pend0);
+          improved |= top.insert(pend1);
+          improved |= top.insert(pend2);
+          improved |= top.insert(pend3);
+          parked = false;
+          pend0 = pend1 = pend2 = pend3 = -INFINITY;
+        }
         // publish the lower bound s_(k) - 2 eps for the other clusters working on this query
         if constexpr (kLadder) {
           if (improved && q_valid && lad.j >= 0) atomicMax(&a.tau_key[q], total_key(lad.tau(a.eps2)));
@@ -1347,8 +1366,10 @@ cudaError_t launch_scan_tc(const DeviceIndex& ix, const ScanTcLaunch& l, cudaStr
   a.ladder_n = ladder ? (a.k_blocks >= 8 ? 128u : 256u) : 0u;
   // Short rows (<= 3 k-blocks: a tile's MMAs take <= 1.5k cycles) are bound by the epilogue: second epilogue warp-quad.
   bool epi2 = !biased && !l.join && !l.pred && a.k_blocks <= 3;
-  if (const char* env = getenv("CM_SCAN_EPI2")) epi2 = epi2 && atoi(env) != 0;
+  if (const char* env = getenv("CM_SCAN_EPI2")) epi2 = (epi2 && atoi(env) != 0) || (atoi(env) == 2 && !biased && !l.join && !l.pred);  // 2: every row length
   if (epi2) a.splits = pick_splits(a.m_pairs, a.n_tiles, clusters, l.k, l.cap, 2);
+  if (const char* env = getenv("CM_SCAN_SPLITS"))  // experiments
+    if (!l.join && !l.pair_lo && atoi(env) > 0) a.splits = std::min<uint32_t>((uint32_t)atoi(env), a.n_tiles);
   a.slot_chunk = l.k > 32 ? 32u : 8u;
   a.diag_no_hits = getenv("CM_SCAN_DIAG") != nullptr ? 1u : 0u;
   const size_t lists_bytes = (epi2 ? 2 : 1) * (ladder ? (size_t)a.ladder_n * 128 * 2 : (size_t)l.k * 128 * 4);
