@@ -90,14 +90,16 @@ cudaError_t launch_preprocess_rows(const float* x, uint64_t n, uint32_t dim, uin
 // ---------------------------------------------------------------------------------------------------------
 // K0 for query batches, fused with the bf16 cast of the tensor-core scan: one pass over the queries instead of two
 // kernels (preprocess, then cast) that each stream them through HBM, and no per-tile barrier chain.
-// CTA = 16 rows. Each row (dim * 4 bytes, dim % 4 == 0) is landed whole in shared memory by ONE bulk copy
-// (cp.async.bulk, all 16 in flight at once); lane r then walks row r sequentially with LDS.128 — the reference's
-// scalar `map(|x| x * x).sum()` order, separately rounded multiply and add — and all 256 threads write the
+// CTA = PQ_ROWS rows. Each row (dim * 4 bytes, dim % 4 == 0) is landed whole in shared memory by ONE bulk copy
+// (cp.async.bulk, all of them in flight at once); lane r then walks row r sequentially with LDS.128 — the reference's
+// scalar `map(|x| x * x).sum()` order, separately rounded multiply and add — and all threads write the
 // normalised fp32 row and its bf16 copy (zero padded to the scan's [nq_pad][k_pad] layout). The row stride of
 // dim * 4 + 16 bytes puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups.
 // ---------------------------------------------------------------------------------------------------------
-constexpr uint32_t PQ_ROWS = 16;
-constexpr int PQ_THREADS = 256;
+// 8 rows and 128 threads per CTA: 24.7 KB of shared memory at dim 768 -> 9 CTAs per SM, so a 10,000-query batch (1,250
+// CTAs) is ONE wave; with 16 rows / 256 threads (4 per SM, 625 CTAs) a second, nearly empty wave doubled the kernel.
+constexpr uint32_t PQ_ROWS = 8;
+constexpr int PQ_THREADS = 128;
 
 __global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __restrict__ x, uint32_t n, uint32_t dim,
                                                                 float* __restrict__ out, uint32_t ld_out,
@@ -153,8 +155,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_prepare_queries(const float* __r
     }
   }
   __syncthreads();
-  // write phase: thread t handles element pairs (bf16x2 stores); 16 threads per row would under-use the CTA, so
-  // all 256 threads sweep the rows one after the other
+  // write phase: thread t handles element pairs (bf16x2 stores); all threads sweep the rows one after the other
   const uint32_t pairs16 = k_pad / 2;
   for (uint32_t r = 0; r < PQ_ROWS; ++r) {
     const uint32_t row = row0 + r;
