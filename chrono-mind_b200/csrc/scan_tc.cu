@@ -267,7 +267,7 @@ struct LocalTopK {
   float* list;
   uint32_t k, filled, min_pos;
   float kth;  // smallest of the k entries once filled == k
-  __device__ __forceinline__ void rescan() {
+  __device__ __forceinline__ void rescan() {  // (as a call it shrinks the kernel from 11.4k to 3.5k instructions and is 0.7-5 % slower)
     kth = list[0];
     min_pos = 0;
     for (uint32_t j = 1; j < k; ++j) {

@@ -23,6 +23,11 @@ def main():
     gen = datasets.ChunkedCorpus("emb", n, dim, 0x5EED)
     raw = gen.shard(0, 1) * np.random.default_rng(1).uniform(0.5, 4.0, size=(n, 1)).astype(np.float32)   # stored rows are not unit length
     q = gen.queries(nq) * 2.0
+    try:                                          # page-locked host buffer, as bench.py's legs use (a serving process would)
+        import torch
+        q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).pin_memory().numpy()
+    except Exception:
+        pass
     ts_s, ts_n, dec = datasets.temporal_attrs(n, 1, NOW[0])
     peaks = {}
     try:
