@@ -409,7 +409,8 @@ def run_ours(args, rank, world, local_rank):
         # save_snapshot's container (src/persistence.rs:41-64) written by datasets.write_snapshot, read back by the
         # engine's load_snapshot restatement (cm_index_from_snapshot: header, CRC-32, bincode body, validate per record).
         ctx_rows = np.random.default_rng(SEED ^ 0xC7).integers(0, max(1, args.contexts), size=n_rows).astype(np.uint32)
-        snap_path = "/tmp/chronomind_bench_%d_%dx%d.chrono" % (os.getpid(), n_rows, DIM)
+        snap_path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "chronomind_bench_%d_%dx%d.chrono" % (os.getpid(), n_rows, DIM))
+        st = None
         try:
             tw = time.time()
             info = datasets.write_snapshot(snap_path, shard, ts_s, ts_n, decay, ctx_rows, max(1, args.contexts),
@@ -418,9 +419,16 @@ def run_ours(args, rank, world, local_rank):
             tl = time.time()
             st = ChronoMindB200.from_snapshot(snap_path)
             tl = time.time() - tl
+        except OSError as e:                      # no room for a 3 GB scratch file: the same rows go in as a matrix
+            if args.source == "snapshot":
+                raise
+            log("[bench] snapshot file not written (%s): falling back to cm_index_from_matrix" % e)
+            st, use_snapshot, ctx_rows = None, False, None
+            source = "matrix handed to cm_index_from_matrix (the scratch snapshot file could not be written: %s)" % e
         finally:
             if os.path.exists(snap_path):
                 os.unlink(snap_path)
+    if use_snapshot:
         assert len(st) == n_rows and st.config.dimensions == DIM and st.external_id(n_rows - 1) == "m%09d" % (n_rows - 1)
         source = ("CHRONO1 v2 snapshot file, %.2f GB, %d records over %d contexts: written in %.1fs, loaded by cm_index_from_snapshot "
                   "in %.1fs (%.2f GB/s: read + CRC-32 + bincode decode + validate + preprocess)"
