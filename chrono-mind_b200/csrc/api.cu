@@ -373,7 +373,7 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
     CM_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq_pad * 4, s));
   else
     CM_CUDA(cudaMemsetAsync(ws->tc_state.p, 0, (size_t)nq_pad * 8, s));
-  CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));  // this chunk's counters
+  if (q_off) CM_CUDA(cudaMemsetAsync(small + 64, 0, 16, s));  // this chunk's counters (the first chunk's: zeroed with the totals)
   const void* q_bf16 = ws->qbf16.p;
   if (pq.bf16_ready)
     q_bf16 = static_cast<const uint8_t*>(ws->qbf16.p) + (size_t)q_off * d.k_pad * 2;  // this chunk of the fused copy
@@ -395,18 +395,22 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
     ProfileScope prof(s);
     CM_CUDA(launch_scan_tc(d, sl, s));
   }
-  // fork: the tail of this batch goes to the workspace's low-priority stream
+  // fork: with a second batch in flight the tail of this one goes to the workspace's low-priority stream (it then runs
+  // under the other batch's scan); a lone batch keeps its tail on the caller's stream — two event hops less per step
   cudaStream_t caller = s;
-  if (!ws->tail_stream) {
+  const bool fork_tail = sl.leave_room;
+  if (fork_tail && !ws->tail_stream) {
     int lo = 0, hi = 0;
     CM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = lowest priority (numerically greatest)
     CM_CUDA(cudaStreamCreateWithPriority(&ws->tail_stream, cudaStreamNonBlocking, lo));
     CM_CUDA(cudaEventCreateWithFlags(&ws->ev_scan, cudaEventDisableTiming));
     CM_CUDA(cudaEventCreateWithFlags(&ws->ev_tail, cudaEventDisableTiming));
   }
-  CM_CUDA(cudaEventRecord(ws->ev_scan, caller));
-  s = ws->tail_stream;
-  CM_CUDA(cudaStreamWaitEvent(s, ws->ev_scan, 0));
+  if (fork_tail) {
+    CM_CUDA(cudaEventRecord(ws->ev_scan, caller));
+    s = ws->tail_stream;
+    CM_CUDA(cudaStreamWaitEvent(s, ws->ev_scan, 0));
+  }
   RescoreLaunch rl;
   rl.qn = pq.qn;
   rl.ldq = pq.ld;
@@ -437,8 +441,10 @@ static cm_status exact_topk_tc(const cm_index* idx, Workspace* ws, const Prepare
   // chunk counters -> call totals; queries beyond what the fallback absorbed are counted in the status word
   CM_CUDA(launch_fold_scan_counters(small + 64, small + 80, one_launch ? 0xFFFFFFFFu : kFlagCap, d.status + 1, s));
   // join: whatever the caller enqueues next on its stream sees this batch's results
-  CM_CUDA(cudaEventRecord(ws->ev_tail, s));
-  CM_CUDA(cudaStreamWaitEvent(caller, ws->ev_tail, 0));
+  if (fork_tail) {
+    CM_CUDA(cudaEventRecord(ws->ev_tail, s));
+    CM_CUDA(cudaStreamWaitEvent(caller, ws->ev_tail, 0));
+  }
   return CM_OK;
 }
 
@@ -471,7 +477,7 @@ static cm_status exact_topk(const cm_index* idx, Workspace* ws, const PreparedQu
   tl_counters.exact_engine = use_tc ? 2 : 1;
   if (use_tc) {
     CM_CUDA(ws->small.ensure(kSmallBytes));
-    CM_CUDA(cudaMemsetAsync(ws->small.as<uint8_t>() + 80, 0, 16, s));  // call totals
+    CM_CUDA(cudaMemsetAsync(ws->small.as<uint8_t>() + 64, 0, 32, s));  // the first chunk's counters and the call totals
     for (uint32_t q0 = 0; q0 < nq; q0 += kTcQueryChunk) {  // bounded candidate buffer for very large batches
       const uint32_t nb = std::min(kTcQueryChunk, nq - q0);
       PreparedQueries part = pq;
