@@ -43,6 +43,10 @@
 //           accumulator rows of ITS queries against all 256 X rows
 //   warp 2  TMEM allocator — 512 columns = two 128x256 fp32 accumulators (double buffered) per CTA
 //   warps 4-7 epilogue (128 threads) — thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time
+//   warps 8-11 (kEpi2 instantiations, rows <= 192 columns) a second epilogue quad: quad e drains accumulator stage e
+// The per-thread running threshold is an exact top-k list (LocalTopK, k <= 32 or biased) or a score histogram over a
+// fixed ladder of bounds (Ladder, kLadder instantiations, k > 32); either is a lower bound of s_(k) built from scores of
+// k distinct live rows the thread has seen, and the threads of a query meet through tau_key (atomicMax).
 // Operand traffic: all-streamed, each CTA fetches 32 KB per 2·128·256·64 FLOP (128 FLOP/B, vs 85 for a 1-CTA 128x256
 // tile) = 64 B/clk per SM at full tensor rate, more than the L2 -> SM path delivers chip-wide (≈6.3-7.1 KB/clk =
 // 43-48 B/clk per SM). With 7 of a 768-wide row's 12 query blocks resident the stream drops to 17/24 of that.
