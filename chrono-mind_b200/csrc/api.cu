@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 
@@ -938,12 +939,14 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   std::vector<uint8_t> deleted(n, 0);
   uint64_t live = n;
   {
-    std::unordered_map<std::string, uint32_t> by_id;
+    // keys are views of the decoded records' own strings (snap.memories is not resized any more): no copy per record
+    std::unordered_map<std::string_view, uint32_t> by_id;
     by_id.reserve(n * 2);
     for (uint64_t i = 0; i < n; ++i) {
       if ((st = validate_snapshot_memory(snap, i)) != CM_OK) return st;
       const SnapshotMemory& m = snap.memories[i];
-      auto it = by_id.find(m.id);
+      const std::string_view key(m.id);
+      auto it = by_id.find(key);
       if (it != by_id.end()) {
         deleted[it->second] = 1;
         live--;
@@ -951,7 +954,7 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
       } else {
         if (by_id.size() >= snap.config.max_memories)
           return fail(CM_ERR_CAPACITY_EXCEEDED, "store is at capacity (" + std::to_string(snap.config.max_memories) + " memories)");
-        by_id.emplace(m.id, (uint32_t)i);
+        by_id.emplace(key, (uint32_t)i);
       }
       if (i + 1 > kArenaCapacity)  // `VectorIndex::insert` -> None (src/index/arena.rs:114-118)
         return fail(CM_ERR_INDEX_FULL, "index storage exhausted (16777216 slots, including tombstones); compact via snapshot reload");
@@ -980,9 +983,9 @@ cm_status cm_index_from_snapshot(const char* path, cm_index** out) {
   {
     std::unordered_map<std::string, uint32_t> ctx_of;
     for (uint64_t i = 0; i < n; ++i) {
-      const SnapshotMemory& m = snap.memories[i];
+      SnapshotMemory& m = snap.memories[i];
       idx->importance[i] = m.importance;
-      idx->ext_ids[i] = m.id;
+      idx->ext_ids[i] = std::move(m.id);  // the snapshot records are dropped right after this loop
       idx->ts_secs[i] = m.ts_secs;
       idx->ts_nanos[i] = m.ts_nanos;
       idx->decay[i] = m.decay_rate;
